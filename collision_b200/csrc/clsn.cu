@@ -1,0 +1,784 @@
+// collision_b200: context, pass orchestration and the C ABI (include/collision_b200.h).
+//
+// One context = one B200.  All state lives in HBM as padded per-vertex records (Vec4, one
+// 32-byte sector per gather); the host side only gathers/scatters caller arrays.
+// Pipeline of one detection pass (clsn_detect):
+//   [build, first pass of a step]  k_scene_bounds -> k_morton -> cub radix sort -> k_hierarchy
+//   k_refit<static|moving>   exact FP64 leaf boxes + FP32 node boxes, bottom-up
+//   k_traverse               stack-in-registers self query -> element pairs (a < b)
+//   k_narrow<static|moving>  one pair per thread, 15 feature tests, emits impulse records
+// and of clsn_apply: cub exclusive scan over per-point counts -> k_scatter -> k_reduce_points
+// (canonical-order sums, applied to avgVel) -> body records -> [rigid-body kernels].
+// Compiled with --fmad=false: every FP64 expression rounds exactly like the reference's.
+#include "collision_b200.h"
+
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "narrow.cuh"
+#include "lbvh.cuh"
+#include "reduce.cuh"
+#include "rigid.cuh"
+
+using namespace clsn;
+
+// ------------------------------------------------------------------ narrow-phase kernel
+// feature tables: local point slots (0..2 = element a, 3..5 = element b) of the 4 points of each test
+// tri-tri CCD (MovingTriToTri :286-323): k=0 tri a + vertex b_i, k=1 tri b + vertex a_i, then edges
+__constant__ unsigned char c_feat_tt_moving[15][4] = {
+    {0, 1, 2, 3}, {0, 1, 2, 4}, {0, 1, 2, 5}, {3, 4, 5, 0}, {3, 4, 5, 1}, {3, 4, 5, 2},
+    {0, 1, 3, 4}, {0, 1, 4, 5}, {0, 1, 5, 3}, {1, 2, 3, 4}, {1, 2, 4, 5}, {1, 2, 5, 3},
+    {2, 0, 3, 4}, {2, 0, 4, 5}, {2, 0, 5, 3}};
+// tri-tri proximity (TriToTri :592-625): k=0 tri b (tri2) + vertex a_i, k=1 tri a + vertex b_i
+__constant__ unsigned char c_feat_tt_static[15][4] = {
+    {3, 4, 5, 0}, {3, 4, 5, 1}, {3, 4, 5, 2}, {0, 1, 2, 3}, {0, 1, 2, 4}, {0, 1, 2, 5},
+    {0, 1, 3, 4}, {0, 1, 4, 5}, {0, 1, 5, 3}, {1, 2, 3, 4}, {1, 2, 4, 5}, {1, 2, 5, 3},
+    {2, 0, 3, 4}, {2, 0, 4, 5}, {2, 0, 5, 3}};
+// tri (a) - bond (b = slots 3,4) (TriToBond :508-530, MovingTriToBond :219-241)
+__constant__ unsigned char c_feat_tb[5][4] = {{0, 1, 2, 3}, {0, 1, 2, 4}, {0, 1, 3, 4}, {1, 2, 3, 4}, {2, 0, 3, 4}};
+
+#define NARROW_THREADS 128
+
+template <bool MOVING>
+__global__ void __launch_bounds__(NARROW_THREADS)
+k_narrow(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restrict__ elem, const Vec4* __restrict__ xo,
+         const Vec4* __restrict__ av, const uint8_t* __restrict__ vflags, const int* __restrict__ vbody, NarrowParams P, Emit E)
+{
+    // shared-memory staging of the six points of each thread's pair: [slot*3+c][thread]
+    __shared__ double s_x[18][NARROW_THREADS];
+    __shared__ double s_v[18][NARROW_THREADS];  // avgVel: CCD positions, and v_rel of the impulse in both modes
+    __shared__ int s_id[6][NARROW_THREADS];
+    __shared__ short s_fb[6][NARROW_THREADS];  // vertex flags (the body id is fetched only for all-rigid quads)
+    const int tid = threadIdx.x;
+    long long n_pairs = (long long)E.counters[CTR_PAIRS];
+    if (n_pairs > cap_pairs) n_pairs = cap_pairs;
+    const double h = MOVING ? P.eps : P.thickness;
+    unsigned long long n_true = 0;
+    for (long long base = (long long)blockIdx.x * NARROW_THREADS; base < n_pairs; base += (long long)gridDim.x * NARROW_THREADS) {
+        const long long pi = base + tid;
+        const bool live = pi < n_pairs;
+        int nfeat = 0, type = 0;  // 0 tri-tri, 1 tri-bond, 2 bond-bond
+        int2 pr = make_int2(0, 0);
+        if (live) {
+            pr = __ldg(pairs + pi);
+            const int4 A = __ldg(elem + pr.x), B = __ldg(elem + pr.y);
+            const int ids[6] = {A.x, A.y, A.z, B.x, B.y, B.z};
+            type = (A.z >= 0 ? 0 : 1) + (B.z >= 0 ? 0 : 1);
+            // with a < b and triangles numbered first, a mixed pair always has the triangle as a
+            nfeat = type == 0 ? 15 : (type == 1 ? 5 : 1);
+#pragma unroll
+            for (int s = 0; s < 6; ++s) {
+                const int id = ids[s];
+                s_id[s][tid] = id;
+                if (id >= 0) {
+                    const Vec4 x = ldg_vec4(xo + id);
+                    s_x[3 * s][tid] = x.x; s_x[3 * s + 1][tid] = x.y; s_x[3 * s + 2][tid] = x.z;
+                    const Vec4 v = ldg_vec4(av + id);
+                    s_v[3 * s][tid] = v.x; s_v[3 * s + 1][tid] = v.y; s_v[3 * s + 2][tid] = v.z;
+                    s_fb[s][tid] = (short)__ldg(vflags + id);
+                }
+            }
+        }
+        bool status = false;
+        // warp-uniform feature loop: every lane runs test f on its own pair
+        const int nf_max = __reduce_max_sync(0xffffffffu, nfeat);
+        for (int f = 0; f < nf_max; ++f) {
+            if (f >= nfeat) continue;
+            int sl[4];
+            bool edge;
+            if (type == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) sl[q] = MOVING ? c_feat_tt_moving[f][q] : c_feat_tt_static[f][q];
+                edge = f >= 6;
+            } else if (type == 1) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) sl[q] = c_feat_tb[f][q];
+                edge = f >= 2;
+            } else {
+                sl[0] = 0; sl[1] = 1; sl[2] = 3; sl[3] = 4;
+                edge = true;
+            }
+            Quad q;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int s = sl[i];
+                q.id[i] = s_id[s][tid];
+                q.flags[i] = s_fb[s][tid];
+                q.xo[i][0] = s_x[3 * s][tid]; q.xo[i][1] = s_x[3 * s + 1][tid]; q.xo[i][2] = s_x[3 * s + 2][tid];
+                q.av[i][0] = s_v[3 * s][tid]; q.av[i][1] = s_v[3 * s + 1][tid]; q.av[i][2] = s_v[3 * s + 2][tid];
+                q.body[i] = 0;
+            }
+            if ((q.flags[0] & 3) && (q.flags[1] & 3) && (q.flags[2] & 3) && (q.flags[3] & 3)) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) q.body[i] = __ldg(vbody + q.id[i]);
+            }
+            const unsigned long long key = ((unsigned long long)(unsigned)pr.x << 34) | ((unsigned long long)(unsigned)pr.y << 4) |
+                                           (unsigned long long)f;
+            if (feature_test<MOVING>(P, E, q, key, edge, h)) status = true;
+        }
+        if (status) ++n_true;
+    }
+    for (int o = 16; o > 0; o >>= 1) n_true += __shfl_xor_sync(0xffffffffu, n_true, o);
+    if ((tid & 31) == 0 && n_true) atomicAdd(&E.counters[CTR_TRUE], n_true);
+}
+
+// ------------------------------------------------------------------ context
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t reserve(size_t want)
+    {
+        if (want <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+        if (e == cudaSuccess) n = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+enum { PH_AVG = 0, PH_BUILD, PH_REFIT, PH_TRAVERSE, PH_NARROW, PH_REDUCE, PH_FINAL, PH_OTHER, PH_COUNT };
+
+struct clsn_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    clsn_params prm;
+    int V = 0, T = 0, B = 0, N = 0, nbody = 0;
+    bool has_movable = false;
+    // topology
+    DevBuf<int4> elem;
+    DevBuf<uint8_t> vflags;
+    DevBuf<int> vbody;
+    DevBuf<double> body_mass;
+    RigidTopo rigid;
+    // state
+    DevBuf<Vec4> xo, xn, av;
+    DevBuf<uint8_t> has;
+    DevBuf<double> imp_rg;
+    DevBuf<int> cnt_rg;
+    DevBuf<double> stage;  // 3V doubles, host<->device staging of packed arrays
+    // bvh
+    DevBuf<unsigned> code, code_sorted;
+    DevBuf<int> idx, leaf_elem, leaf_parent, flags;
+    DevBuf<WideNode> nodes;
+    DevBuf<double> lbox;
+    DevBuf<unsigned long long> bounds;
+    DevBuf<unsigned char> cub_tmp;
+    bool tree_built = false;
+    // pass buffers
+    DevBuf<int2> pairs, dbg_cand;
+    DevBuf<PointRec> prec;
+    DevBuf<BodyRec> brec;
+    DevBuf<Contact> contacts;
+    DevBuf<int> cnt, offs, fill, perm, perm_sorted;
+    DevBuf<unsigned long long> skey;
+    DevBuf<unsigned long long> counters;
+    DevBuf<double> acc_imp, acc_fric;
+    unsigned long long* h_counters = nullptr;  // pinned
+    double* h_pin = nullptr;                   // pinned staging for host arrays (3V doubles x 2)
+    size_t h_pin_n = 0;
+    // imported record set (multi-GPU)
+    const PointRec* imp_prec = nullptr;
+    const BodyRec* imp_brec = nullptr;
+    long long imp_nprec = -1, imp_nbrec = 0;
+    bool records_pending = false;
+    long long last_nprec = 0, last_nbrec = 0;
+    int rank = 0, nranks = 1;
+    bool dbg_candidates = false, dbg_contacts = false;
+    long long n_dbg_cand = 0, n_contacts = 0;
+    cudaEvent_t ev[2 * PH_COUNT + 2];
+    int sm_count = 148;
+};
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            c->err = std::string(#call) + ": " + cudaGetErrorString(_e);                      \
+            return _e == cudaErrorMemoryAllocation ? CLSN_E_NOMEM : CLSN_E_CUDA;              \
+        }                                                                                     \
+    } while (0)
+
+static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t > 0 ? (n + t - 1) / t : 1); }
+
+static int fail(clsn_ctx* c, int code, const char* msg)
+{
+    c->err = msg;
+    return code;
+}
+
+extern "C" int clsn_create(clsn_ctx** out, int device)
+{
+    if (!out) return CLSN_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return CLSN_E_CUDA;
+    clsn_ctx* c = new clsn_ctx();
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return CLSN_E_CUDA;
+    }
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    for (auto& e : c->ev) cudaEventCreate(&e);
+    cudaMallocHost((void**)&c->h_counters, 64 * sizeof(unsigned long long));
+    c->counters.reserve(64);
+    c->bounds.reserve(8);
+    clsn_params p;
+    p.eps = 1e-6; p.thickness = 1e-4; p.dt = 1e-3; p.k = 1000; p.m = 0.01; p.lambda = 0.02; p.cr = 0.0;
+    for (int i = 0; i < 3; ++i) { p.lo[i] = -1e30; p.hi[i] = 1e30; }
+    c->prm = p;
+    *out = c;
+    return CLSN_OK;
+}
+
+extern "C" void clsn_destroy(clsn_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->elem.release(); c->vflags.release(); c->vbody.release(); c->body_mass.release();
+    c->xo.release(); c->xn.release(); c->av.release(); c->has.release(); c->imp_rg.release(); c->cnt_rg.release();
+    c->stage.release(); c->code.release(); c->code_sorted.release(); c->idx.release(); c->leaf_elem.release();
+    c->leaf_parent.release(); c->flags.release(); c->nodes.release(); c->lbox.release(); c->bounds.release();
+    c->cub_tmp.release(); c->pairs.release(); c->dbg_cand.release(); c->prec.release(); c->brec.release();
+    c->contacts.release(); c->cnt.release(); c->offs.release(); c->fill.release(); c->perm.release();
+    c->perm_sorted.release(); c->skey.release(); c->counters.release(); c->acc_imp.release(); c->acc_fric.release();
+    c->rigid.release();
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    for (auto& e : c->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" const char* clsn_last_error(const clsn_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+extern "C" int clsn_set_params(clsn_ctx* c, const clsn_params* p)
+{
+    if (!c || !p) return CLSN_E_ARG;
+    c->prm = *p;
+    return CLSN_OK;
+}
+
+extern "C" int clsn_set_slice(clsn_ctx* c, int rank, int nranks)
+{
+    if (!c || nranks < 1 || rank < 0 || rank >= nranks) return CLSN_E_ARG;
+    c->rank = rank;
+    c->nranks = nranks;
+    return CLSN_OK;
+}
+
+extern "C" int clsn_set_debug(clsn_ctx* c, int cand, int contacts)
+{
+    if (!c) return CLSN_E_ARG;
+    c->dbg_candidates = cand != 0;
+    c->dbg_contacts = contacts != 0;
+    return CLSN_OK;
+}
+
+extern "C" int clsn_set_topology(clsn_ctx* c, int V, int T, const int32_t* tri_idx, const int32_t* tri_surf, int B,
+                                 const int32_t* bond_idx, const uint8_t* vflags, const int32_t* vbody, int nbody,
+                                 const double* body_mass)
+{
+    if (!c || V <= 0 || T < 0 || B < 0 || nbody <= 0 || !vflags || !vbody || !body_mass) return CLSN_E_ARG;
+    if ((T > 0 && (!tri_idx || !tri_surf)) || (B > 0 && !bond_idx)) return CLSN_E_ARG;
+    if ((long long)T + B >= (1ll << 30)) return fail(c, CLSN_E_ARG, "too many elements for the 30-bit pair key");
+    cudaSetDevice(c->device);
+    const int N = T + B;
+    std::vector<int4> el((size_t)(N > 0 ? N : 1));
+    for (int t = 0; t < T; ++t) {
+        int4 e;
+        e.x = tri_idx[3 * t]; e.y = tri_idx[3 * t + 1]; e.z = tri_idx[3 * t + 2];
+        if (e.x < 0 || e.x >= V || e.y < 0 || e.y >= V || e.z < 0 || e.z >= V) return fail(c, CLSN_E_ARG, "triangle index out of range");
+        if (tri_surf[t] < 0 || tri_surf[t] >= (1 << 28)) return fail(c, CLSN_E_ARG, "surface id out of range");
+        // isRigidBody(CD_HSE*): any vertex fixed or movable-RG (dcollid.cpp:1074-1099)
+        const bool rigid = ((vflags[e.x] | vflags[e.y] | vflags[e.z]) & 3) != 0;
+        e.w = tri_surf[t] | (rigid ? 0x10000000 : 0);
+        el[t] = e;
+    }
+    for (int b = 0; b < B; ++b) {
+        int4 e;
+        e.x = bond_idx[2 * b]; e.y = bond_idx[2 * b + 1]; e.z = -1;
+        if (e.x < 0 || e.x >= V || e.y < 0 || e.y >= V) return fail(c, CLSN_E_ARG, "bond index out of range");
+        e.w = 0x20000000;
+        el[T + b] = e;
+    }
+    c->has_movable = false;
+    for (int v = 0; v < V; ++v) {
+        if (vbody[v] < 0 || vbody[v] >= nbody) return fail(c, CLSN_E_ARG, "vbody out of range");
+        if (vflags[v] & 2) c->has_movable = true;
+    }
+    c->V = V; c->T = T; c->B = B; c->N = N; c->nbody = nbody;
+    CK(c->elem.reserve(el.size()));
+    CK(c->vflags.reserve(V)); CK(c->vbody.reserve(V)); CK(c->body_mass.reserve(nbody));
+    CK(cudaMemcpy(c->elem.p, el.data(), el.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->vflags.p, vflags, V, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->vbody.p, vbody, V * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->body_mass.p, body_mass, nbody * sizeof(double), cudaMemcpyHostToDevice));
+    CK(c->xo.reserve(V)); CK(c->xn.reserve(V)); CK(c->av.reserve(V)); CK(c->has.reserve(V));
+    CK(c->imp_rg.reserve(3 * (size_t)nbody)); CK(c->cnt_rg.reserve(nbody));
+    CK(cudaMemset(c->imp_rg.p, 0, 3 * (size_t)nbody * sizeof(double)));
+    CK(cudaMemset(c->cnt_rg.p, 0, nbody * sizeof(int)));
+    CK(cudaMemset(c->av.p, 0, V * sizeof(Vec4)));
+    CK(cudaMemset(c->has.p, 0, V));
+    CK(c->stage.reserve(6 * (size_t)V));
+    const size_t n1 = (size_t)(N > 0 ? N : 1);
+    CK(c->code.reserve(n1)); CK(c->code_sorted.reserve(n1)); CK(c->idx.reserve(n1)); CK(c->leaf_elem.reserve(n1));
+    CK(c->leaf_parent.reserve(n1)); CK(c->flags.reserve(n1)); CK(c->nodes.reserve(n1)); CK(c->lbox.reserve(6 * n1));
+    size_t tmp1 = 0, tmp2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp1, c->code.p, c->code_sorted.p, c->idx.p, c->leaf_elem.p, N > 0 ? N : 1, 0, 30);
+    CK(c->cnt.reserve((size_t)V + 1)); CK(c->offs.reserve((size_t)V + 1)); CK(c->fill.reserve((size_t)V + 1));
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp2, c->cnt.p, c->offs.p, V + 1);
+    CK(c->cub_tmp.reserve((tmp1 > tmp2 ? tmp1 : tmp2) + 256));
+    CK(cudaMemset(c->cnt.p, 0, ((size_t)V + 1) * sizeof(int)));
+    if (c->pairs.n == 0) CK(c->pairs.reserve((size_t)16 * n1 + 1024));
+    if (c->prec.n == 0) CK(c->prec.reserve((size_t)8 * n1 + 1024));
+    CK(c->perm.reserve(c->prec.n)); CK(c->perm_sorted.reserve(c->prec.n)); CK(c->skey.reserve(c->prec.n));
+    if (c->brec.n == 0) CK(c->brec.reserve(4096));
+    c->tree_built = false;
+    c->records_pending = false;
+    // host-side restatement of createImpZoneForRG's union-find lists (topology only)
+    int r = c->rigid.build(V, T, tri_idx, tri_surf, vflags);
+    if (r != 0) return fail(c, CLSN_E_CUDA, "rigid-body topology upload failed");
+    if (c->h_pin_n < 6 * (size_t)V) {
+        if (c->h_pin) cudaFreeHost(c->h_pin);
+        CK(cudaMallocHost((void**)&c->h_pin, 6 * (size_t)V * sizeof(double)));
+        c->h_pin_n = 6 * (size_t)V;
+    }
+    return CLSN_OK;
+}
+
+static int begin_step(clsn_ctx* c)
+{
+    // per-step accumulators cleared as FT_Propagate's point hook / recordOriginPosition do
+    // (test.cpp:192-224, dcollid.cpp:100): has_collsn; imp/fric/cnt live only inside a pass here
+    CK(cudaMemsetAsync(c->has.p, 0, c->V, c->stream));
+    c->tree_built = false;
+    c->records_pending = false;
+    return CLSN_OK;
+}
+
+extern "C" int clsn_upload_state_device(clsn_ctx* c, const double* d_x_old, const double* d_x_new)
+{
+    if (!c || !c->V || !d_x_old || !d_x_new) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    k_pack<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, d_x_old, c->xo.p);
+    k_pack<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, d_x_new, c->xn.p);
+    CK(cudaGetLastError());
+    return begin_step(c);
+}
+
+extern "C" int clsn_upload_state(clsn_ctx* c, const double* x_old, const double* x_new)
+{
+    if (!c || !c->V || !x_old || !x_new) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    const size_t n = 3 * (size_t)c->V;
+    memcpy(c->h_pin, x_old, n * sizeof(double));
+    memcpy(c->h_pin + n, x_new, n * sizeof(double));
+    CK(cudaMemcpyAsync(c->stage.p, c->h_pin, 2 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return clsn_upload_state_device(c, c->stage.p, c->stage.p + n);
+}
+
+extern "C" int clsn_download_state_device(clsn_ctx* c, double* d_x, double* d_avgvel)
+{
+    if (!c || !c->V) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    if (d_x) k_unpack<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->xn.p, d_x);
+    if (d_avgvel) k_unpack<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->av.p, d_avgvel);
+    CK(cudaGetLastError());
+    return CLSN_OK;
+}
+
+extern "C" int clsn_download_state(clsn_ctx* c, double* x, double* avgvel, uint8_t* has_collsn)
+{
+    if (!c || !c->V) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    const size_t n = 3 * (size_t)c->V;
+    int r = clsn_download_state_device(c, x ? c->stage.p : nullptr, avgvel ? c->stage.p + n : nullptr);
+    if (r) return r;
+    if (x) CK(cudaMemcpyAsync(c->h_pin, c->stage.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (avgvel) CK(cudaMemcpyAsync(c->h_pin + n, c->stage.p + n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (has_collsn) CK(cudaMemcpyAsync(has_collsn, c->has.p, c->V, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (x) memcpy(x, c->h_pin, n * sizeof(double));
+    if (avgvel) memcpy(avgvel, c->h_pin + n, n * sizeof(double));
+    return CLSN_OK;
+}
+
+extern "C" int clsn_set_avgvel(clsn_ctx* c, const double* avgvel)
+{
+    if (!c || !c->V || !avgvel) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    const size_t n = 3 * (size_t)c->V;
+    CK(cudaMemcpyAsync(c->stage.p, avgvel, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_pack<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->stage.p, c->av.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    return CLSN_OK;
+}
+
+extern "C" int clsn_avg_velocity(clsn_ctx* c)
+{
+    if (!c || !c->V) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaMemsetAsync(c->counters.p, 0, CTR_COUNT * sizeof(unsigned long long), c->stream));
+    k_avg_velocity<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->xo.p, c->xn.p, c->av.p, c->prm.dt, c->counters.p);
+    CK(cudaGetLastError());
+    return CLSN_OK;
+}
+
+// ------------------------------------------------------------------ detection pass
+static int build_tree(clsn_ctx* c)
+{
+    const int N = c->N;
+    static const unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull};
+    CK(cudaMemcpyAsync(c->bounds.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    k_scene_bounds<<<c->sm_count * 4, 256, 0, c->stream>>>(c->xo.p, c->V, c->bounds.p);
+    k_morton<<<nblk(N, 256), 256, 0, c->stream>>>(c->elem.p, N, c->xo.p, c->bounds.p, c->code.p, c->idx.p);
+    size_t tmp = c->cub_tmp.n;
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->code.p, c->code_sorted.p, c->idx.p, c->leaf_elem.p, N, 0, 30, c->stream));
+    if (N >= 2) k_hierarchy<<<nblk(N - 1, 256), 256, 0, c->stream>>>(c->code_sorted.p, N, c->nodes.p, c->leaf_parent.p);
+    CK(cudaGetLastError());
+    c->tree_built = true;
+    return CLSN_OK;
+}
+
+static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, int ev_base)
+{
+    const int N = c->N, V = c->V;
+    const bool moving = mode == CLSN_COLLISION;
+    if (N < 1) return fail(c, CLSN_E_ARG, "no elements");
+    NarrowParams P{c->prm.eps, c->prm.thickness, c->prm.dt, c->prm.k, c->prm.m, c->prm.lambda, c->prm.cr};
+    (void)timed; (void)ev_base;
+    if (!c->tree_built) {
+        int r = build_tree(c);
+        if (r) return r;
+    }
+    if (c->dbg_candidates && c->dbg_cand.n == 0) CK(c->dbg_cand.reserve((size_t)32 * N + 1024));
+    if (c->dbg_contacts && c->contacts.n == 0) CK(c->contacts.reserve((size_t)16 * N + 1024));
+    const int q_lo = (int)((long long)N * c->rank / c->nranks), q_hi = (int)((long long)N * (c->rank + 1) / c->nranks);
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        CK(cudaMemsetAsync(c->counters.p, 0, CTR_ERROR * sizeof(unsigned long long), c->stream));  // keep CTR_ERROR
+        CK(cudaMemsetAsync(c->counters.p + CTR_DBG_CAND, 0, sizeof(unsigned long long), c->stream));
+        CK(cudaMemsetAsync(c->flags.p, 0, (size_t)N * sizeof(int), c->stream));
+        CK(cudaMemsetAsync(c->cnt.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
+        CK(cudaMemsetAsync(c->cnt_rg.p, 0, c->nbody * sizeof(int), c->stream));
+        if (moving)
+            k_refit<true><<<nblk(N, 128), 128, 0, c->stream>>>(c->elem.p, c->leaf_elem.p, N, c->xo.p, c->av.p, c->prm.dt,
+                                                                 c->lbox.p, c->nodes.p, c->leaf_parent.p, c->flags.p);
+        else
+            k_refit<false><<<nblk(N, 128), 128, 0, c->stream>>>(c->elem.p, c->leaf_elem.p, N, c->xo.p, c->av.p, c->prm.dt,
+                                                                  c->lbox.p, c->nodes.p, c->leaf_parent.p, c->flags.p);
+        TraverseOut to;
+        to.pairs = c->pairs.p; to.cap_pairs = (long long)c->pairs.n;
+        to.dbg_cand = c->dbg_candidates ? c->dbg_cand.p : nullptr; to.cap_dbg = (long long)c->dbg_cand.n;
+        to.counters = c->counters.p;
+        if (q_hi > q_lo)
+            k_traverse<<<nblk(q_hi - q_lo, 128), 128, 0, c->stream>>>(c->nodes.p, c->lbox.p, c->leaf_elem.p, c->elem.p, N, q_lo, q_hi, to);
+        Emit E;
+        E.prec = c->prec.p; E.brec = c->brec.p; E.contacts = c->dbg_contacts ? c->contacts.p : nullptr;
+        E.counters = c->counters.p;
+        E.cap_prec = (long long)c->prec.n; E.cap_brec = (long long)c->brec.n; E.cap_contacts = (long long)c->contacts.n;
+        E.cnt = c->cnt.p; E.cnt_rg = c->cnt_rg.p; E.body_mass = c->body_mass.p;
+        const int grid = c->sm_count * 8;
+        if (moving)
+            k_narrow<true><<<grid, NARROW_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p,
+                                                                    c->vflags.p, c->vbody.p, P, E);
+        else
+            k_narrow<false><<<grid, NARROW_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p,
+                                                                     c->vflags.p, c->vbody.p, P, E);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(c->h_counters, c->counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        const unsigned long long* h = c->h_counters;
+        bool redo = false;
+        if (h[CTR_PAIRS] > c->pairs.n) { CK(c->pairs.reserve((size_t)(h[CTR_PAIRS] * 5 / 4 + 1024))); redo = true; }
+        if (h[CTR_PREC] > c->prec.n) {
+            size_t want = (size_t)(h[CTR_PREC] * 5 / 4 + 1024);
+            CK(c->prec.reserve(want)); CK(c->perm.reserve(want)); CK(c->perm_sorted.reserve(want)); CK(c->skey.reserve(want));
+            redo = true;
+        }
+        if (h[CTR_BREC] > c->brec.n) { CK(c->brec.reserve((size_t)(h[CTR_BREC] * 5 / 4 + 1024))); redo = true; }
+        if (c->dbg_candidates && h[CTR_DBG_CAND] > c->dbg_cand.n) { CK(c->dbg_cand.reserve((size_t)(h[CTR_DBG_CAND] * 5 / 4 + 1024))); redo = true; }
+        if (c->dbg_contacts && h[CTR_CONTACTS] > c->contacts.n) { CK(c->contacts.reserve((size_t)(h[CTR_CONTACTS] * 5 / 4 + 1024))); redo = true; }
+        if (redo) continue;
+        if (h[CTR_ERROR]) return fail(c, CLSN_E_NUMERIC, "NaN/Inf or degenerate normal (reference: clean_up(ERROR))");
+        if (st) {
+            st->candidates = (int64_t)h[CTR_CAND];
+            st->pairs_tested = (int64_t)h[CTR_PAIRS];
+            st->true_pairs = (int64_t)h[CTR_TRUE];
+            st->contacts = (int64_t)h[CTR_CONTACTS];
+            st->contributions = (int64_t)(h[CTR_PREC] + h[CTR_BREC]);
+        }
+        c->last_nprec = (long long)h[CTR_PREC];
+        c->last_nbrec = (long long)h[CTR_BREC];
+        c->n_dbg_cand = (long long)h[CTR_DBG_CAND];
+        c->n_contacts = (long long)h[CTR_CONTACTS];
+        c->records_pending = true;
+        c->imp_nprec = -1;
+        return CLSN_OK;
+    }
+    return fail(c, CLSN_E_NOMEM, "pair/record buffers kept overflowing");
+}
+
+extern "C" int clsn_detect(clsn_ctx* c, int mode, clsn_pass_stats* st)
+{
+    if (!c || !c->V || (mode != CLSN_PROXIMITY && mode != CLSN_COLLISION)) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    return run_detect(c, mode, st, false, 0);
+}
+
+// group + reduce the pending records.  mode 0: apply to avgVel; mode 1: into acc arrays only.
+static int reduce_records(clsn_ctx* c, int mode)
+{
+    const int V = c->V;
+    const PointRec* prec = c->prec.p;
+    const BodyRec* brec = c->brec.p;
+    long long nprec = c->last_nprec, nbrec = c->last_nbrec;
+    unsigned long long* n_prec_dev = c->counters.p + CTR_PREC;
+    unsigned long long* n_brec_dev = c->counters.p + CTR_BREC;
+    if (c->imp_nprec >= 0) {
+        // externally gathered record set: recount per point
+        prec = c->imp_prec; brec = c->imp_brec; nprec = c->imp_nprec; nbrec = c->imp_nbrec;
+        unsigned long long hc[2] = {(unsigned long long)nprec, (unsigned long long)nbrec};
+        CK(cudaMemcpyAsync(c->counters.p + 32, hc, sizeof(hc), cudaMemcpyHostToDevice, c->stream));
+        n_prec_dev = c->counters.p + 32;
+        n_brec_dev = c->counters.p + 33;
+        CK(cudaMemsetAsync(c->cnt.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
+        CK(cudaMemsetAsync(c->cnt_rg.p, 0, c->nbody * sizeof(int), c->stream));
+        if (nprec > 0 || nbrec > 0)
+            k_count_records<<<c->sm_count * 4, 256, 0, c->stream>>>(prec, nprec, brec, nbrec, c->cnt.p, c->cnt_rg.p);
+        if ((size_t)nprec > c->perm.n) {
+            CK(c->perm.reserve((size_t)nprec)); CK(c->perm_sorted.reserve((size_t)nprec)); CK(c->skey.reserve((size_t)nprec));
+        }
+    }
+    if (nprec > 0) {
+        size_t tmp = c->cub_tmp.n;
+        CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->cnt.p, c->offs.p, V + 1, c->stream));
+        CK(cudaMemsetAsync(c->fill.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
+        const long long cap = c->imp_nprec >= 0 ? nprec : (long long)c->prec.n;
+        k_scatter<<<c->sm_count * 8, 256, 0, c->stream>>>(prec, n_prec_dev, cap, c->offs.p, c->fill.p, c->perm.p, c->skey.p);
+        if (mode == 1) {
+            CK(c->acc_imp.reserve(3 * (size_t)V)); CK(c->acc_fric.reserve(3 * (size_t)V));
+            CK(cudaMemsetAsync(c->acc_imp.p, 0, 3 * (size_t)V * sizeof(double), c->stream));
+            CK(cudaMemsetAsync(c->acc_fric.p, 0, 3 * (size_t)V * sizeof(double), c->stream));
+        }
+        k_reduce_points<<<c->sm_count * 8, 256, 0, c->stream>>>(prec, c->offs.p, c->cnt.p, V, c->perm.p, c->perm_sorted.p, c->skey.p,
+                                                                  c->vflags.p, c->av.p, c->has.p, mode, c->acc_imp.p, c->acc_fric.p,
+                                                                  c->counters.p);
+    } else if (mode == 1) {
+        CK(c->acc_imp.reserve(3 * (size_t)V)); CK(c->acc_fric.reserve(3 * (size_t)V));
+        CK(cudaMemsetAsync(c->acc_imp.p, 0, 3 * (size_t)V * sizeof(double), c->stream));
+        CK(cudaMemsetAsync(c->acc_fric.p, 0, 3 * (size_t)V * sizeof(double), c->stream));
+    }
+    if (nbrec > 0 && mode == 0) {
+        const long long cap = c->imp_nprec >= 0 ? nbrec : (long long)c->brec.n;
+        k_reduce_bodies<<<nblk(c->nbody, 64), 64, 0, c->stream>>>(brec, n_brec_dev, cap, c->nbody, c->imp_rg.p);
+    }
+    CK(cudaGetLastError());
+    return CLSN_OK;
+}
+
+extern "C" int clsn_apply(clsn_ctx* c, int rigidify)
+{
+    if (!c || !c->V) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    if (c->records_pending) {
+        int r = reduce_records(c, 0);
+        if (r) return r;
+        const long long nbrec = c->imp_nprec >= 0 ? c->imp_nbrec : c->last_nbrec;
+        if (nbrec > 0 || c->has_movable) {
+            // cnt_rg > 0 can also persist from set_body_accumulators (parity tests)
+            k_apply_bodies<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->vflags.p, c->vbody.p, c->imp_rg.p, c->cnt_rg.p,
+                                                                    c->av.p, c->has.p);
+            CK(cudaMemsetAsync(c->cnt_rg.p, 0, c->nbody * sizeof(int), c->stream));
+        }
+        CK(cudaMemsetAsync(c->cnt.p, 0, ((size_t)c->V + 1) * sizeof(int), c->stream));
+        c->records_pending = false;
+        c->imp_nprec = -1;
+    }
+    if (rigidify && c->has_movable && c->prm.dt > 0.0) {
+        int r = c->rigid.rigidify(c->xo.p, c->av.p, c->vflags.p, c->prm.m, c->prm.dt, c->counters.p, c->stream);
+        if (r != 0) return fail(c, CLSN_E_CUDA, "rigid-body kernels failed");
+    }
+    CK(cudaGetLastError());
+    return CLSN_OK;
+}
+
+extern "C" int clsn_boundary(clsn_ctx* c)
+{
+    if (!c || !c->V) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    const clsn_params& p = c->prm;
+    k_boundary<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->vflags.p, c->xo.p, c->av.p, c->has.p, p.dt, p.lambda, p.lo[0],
+                                                         p.lo[1], p.lo[2], p.hi[0], p.hi[1], p.hi[2]);
+    CK(cudaGetLastError());
+    return CLSN_OK;
+}
+
+extern "C" int clsn_final_position(clsn_ctx* c)
+{
+    if (!c || !c->V) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    k_final_position<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->xo.p, c->av.p, c->xn.p, c->prm.dt);
+    CK(cudaGetLastError());
+    return CLSN_OK;
+}
+
+// resolveCollision, dcollid.cpp:317-362 (detectProximity :390-406, detectCollision :430-468)
+extern "C" int clsn_resolve(clsn_ctx* c, clsn_step_stats* stats)
+{
+    if (!c || !c->V) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    clsn_step_stats s;
+    memset(&s, 0, sizeof(s));
+    int r;
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    if ((r = clsn_avg_velocity(c))) return r;
+    if ((r = run_detect(c, CLSN_PROXIMITY, &s.proximity, true, 0))) return r;
+    if ((r = clsn_apply(c, 1))) return r;
+    bool is_collision = true;
+    int niter = 1, cd = 0;
+    while (is_collision) {
+        if ((r = run_detect(c, CLSN_COLLISION, &s.ccd[cd], true, 0))) return r;
+        is_collision = s.ccd[cd].true_pairs > 0;
+        if (cd == 0 && is_collision) s.has_collision = 1;
+        ++cd;
+        if ((r = clsn_apply(c, 1))) return r;
+        if (++niter > CLSN_MAX_CCD_PASSES) break;
+    }
+    s.n_ccd_passes = cd;
+    s.still_colliding = is_collision ? 1 : 0;
+    if ((r = clsn_boundary(c))) return r;
+    if ((r = clsn_final_position(c))) return r;
+    CK(cudaEventRecord(c->ev[1], c->stream));
+    CK(cudaMemcpyAsync(c->h_counters, c->counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->h_counters[CTR_ERROR]) return fail(c, CLSN_E_NUMERIC, "NaN/Inf in the collision step (reference: clean_up(ERROR))");
+    CK(cudaEventElapsedTime(&s.ms_total, c->ev[0], c->ev[1]));
+    if (stats) *stats = s;
+    return CLSN_OK;
+}
+
+extern "C" int clsn_step_host(clsn_ctx* c, const double* x_old, const double* x_new, double* x_out, double* vel_inout,
+                              uint8_t* has_out, clsn_step_stats* stats)
+{
+    if (!c || !c->V || !x_old || !x_new || !x_out) return CLSN_E_ARG;
+    int r;
+    if ((r = clsn_upload_state(c, x_old, x_new))) return r;
+    if ((r = clsn_resolve(c, stats))) return r;
+    const size_t n = 3 * (size_t)c->V;
+    std::vector<uint8_t> has_local;
+    uint8_t* has = has_out;
+    if (!has && vel_inout) {
+        has_local.resize(c->V);
+        has = has_local.data();
+    }
+    // avgVel only travels back when the caller wants velocities updated
+    std::vector<double> av;
+    if (vel_inout) av.resize(n);
+    if ((r = clsn_download_state(c, x_out, vel_inout ? av.data() : nullptr, has))) return r;
+    if (vel_inout)  // updateFinalVelocity, dcollid.cpp:598-624
+        for (int p = 0; p < c->V; ++p)
+            if (has[p])
+                for (int j = 0; j < 3; ++j) vel_inout[3 * (size_t)p + j] = av[3 * (size_t)p + j];
+    return CLSN_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU record exchange
+extern "C" int clsn_export_records(clsn_ctx* c, void** d_prec, int64_t* n_prec, void** d_brec, int64_t* n_brec, int64_t* true_pairs)
+{
+    if (!c || !c->records_pending) return CLSN_E_ARG;
+    if (d_prec) *d_prec = c->prec.p;
+    if (n_prec) *n_prec = c->last_nprec;
+    if (d_brec) *d_brec = c->brec.p;
+    if (n_brec) *n_brec = c->last_nbrec;
+    if (true_pairs) *true_pairs = (int64_t)c->h_counters[CTR_TRUE];
+    return CLSN_OK;
+}
+
+extern "C" int clsn_import_records(clsn_ctx* c, const void* d_prec, int64_t n_prec, const void* d_brec, int64_t n_brec)
+{
+    if (!c || n_prec < 0 || n_brec < 0) return CLSN_E_ARG;
+    c->imp_prec = (const PointRec*)d_prec;
+    c->imp_brec = (const BodyRec*)d_brec;
+    c->imp_nprec = n_prec;
+    c->imp_nbrec = n_brec;
+    c->records_pending = true;
+    return CLSN_OK;
+}
+
+// ------------------------------------------------------------------ debug readbacks
+extern "C" int64_t clsn_num_candidates(clsn_ctx* c) { return c ? c->n_dbg_cand : 0; }
+extern "C" int clsn_get_candidates(clsn_ctx* c, int32_t* pairs)
+{
+    if (!c || !pairs || !c->dbg_candidates) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaMemcpy(pairs, c->dbg_cand.p, (size_t)c->n_dbg_cand * sizeof(int2), cudaMemcpyDeviceToHost));
+    return CLSN_OK;
+}
+extern "C" int64_t clsn_num_contacts(clsn_ctx* c) { return c ? c->n_contacts : 0; }
+extern "C" int clsn_get_contacts(clsn_ctx* c, clsn_contact* out)
+{
+    if (!c || !out || !c->dbg_contacts) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    static_assert(sizeof(clsn_contact) == sizeof(Contact), "contact layout");
+    CK(cudaMemcpy(out, c->contacts.p, (size_t)c->n_contacts * sizeof(Contact), cudaMemcpyDeviceToHost));
+    return CLSN_OK;
+}
+
+extern "C" int clsn_get_accumulators(clsn_ctx* c, double* imp, double* fric, int32_t* cnt, double* imp_rg, int32_t* cnt_rg)
+{
+    if (!c || !c->V || !c->records_pending) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    int r = reduce_records(c, 1);
+    if (r) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    const size_t n = 3 * (size_t)c->V;
+    if (imp) CK(cudaMemcpy(imp, c->acc_imp.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (fric) CK(cudaMemcpy(fric, c->acc_fric.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (cnt) CK(cudaMemcpy(cnt, c->cnt.p, (size_t)c->V * sizeof(int), cudaMemcpyDeviceToHost));
+    if (imp_rg || cnt_rg) {
+        // body sums as they will be after this pass: reduce into a scratch copy
+        DevBuf<double> tmp;
+        CK(tmp.reserve(3 * (size_t)c->nbody));
+        CK(cudaMemcpy(tmp.p, c->imp_rg.p, 3 * (size_t)c->nbody * sizeof(double), cudaMemcpyDeviceToDevice));
+        const long long nbrec = c->imp_nprec >= 0 ? c->imp_nbrec : c->last_nbrec;
+        if (nbrec > 0) {
+            unsigned long long* n_dev = c->imp_nprec >= 0 ? c->counters.p + 33 : c->counters.p + CTR_BREC;
+            const BodyRec* brec = c->imp_nprec >= 0 ? c->imp_brec : c->brec.p;
+            const long long cap = c->imp_nprec >= 0 ? nbrec : (long long)c->brec.n;
+            k_reduce_bodies<<<nblk(c->nbody, 64), 64, 0, c->stream>>>(brec, n_dev, cap, c->nbody, tmp.p);
+            CK(cudaStreamSynchronize(c->stream));
+        }
+        if (imp_rg) CK(cudaMemcpy(imp_rg, tmp.p, 3 * (size_t)c->nbody * sizeof(double), cudaMemcpyDeviceToHost));
+        if (cnt_rg) CK(cudaMemcpy(cnt_rg, c->cnt_rg.p, (size_t)c->nbody * sizeof(int), cudaMemcpyDeviceToHost));
+        tmp.release();
+    }
+    return CLSN_OK;
+}
+
+extern "C" int clsn_set_body_accumulators(clsn_ctx* c, const double* imp_rg, const int32_t* cnt_rg)
+{
+    if (!c || !c->V) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaStreamSynchronize(c->stream));
+    if (imp_rg) CK(cudaMemcpy(c->imp_rg.p, imp_rg, 3 * (size_t)c->nbody * sizeof(double), cudaMemcpyHostToDevice));
+    if (cnt_rg) CK(cudaMemcpy(c->cnt_rg.p, cnt_rg, (size_t)c->nbody * sizeof(int), cudaMemcpyHostToDevice));
+    return CLSN_OK;
+}

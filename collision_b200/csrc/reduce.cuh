@@ -1,0 +1,218 @@
+// Deterministic impulse reduction + per-vertex passes (sm_100a).
+//
+// The reference accumulates "collsnImpulse += ..., friction += ..., collsn_num += 1" through
+// pointers while it walks its tree (dcollid3d.cpp:1053-1079, 1235-1284) and then applies
+// avgVel += (imp + fric)/num once per point (updateAverageVelocity, dcollid.cpp:677-751).
+// Here the narrow phase has emitted 64-byte records; they are grouped per point with a
+// counting sort (count -> exclusive scan -> scatter) and each point's records are summed
+// sequentially in canonical key order (ea, eb, feature) -- no floating-point atomics, bit-identical
+// from run to run and for any number of ranks.
+#pragma once
+#include "narrow.cuh"
+#include "lbvh.cuh"
+
+namespace clsn {
+
+// records -> per-point slots.  fill[] must be zero.
+__global__ void k_scatter(const PointRec* __restrict__ rec, const unsigned long long* __restrict__ n_rec_ptr,
+                          long long cap, const int* __restrict__ offs, int* fill, int* __restrict__ perm,
+                          unsigned long long* __restrict__ skey)
+{
+    long long n = (long long)*n_rec_ptr;
+    if (n > cap) n = cap;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        const ulonglong2 h = *reinterpret_cast<const ulonglong2*>(rec + r);
+        const int p = (int)(unsigned)h.y;
+        const int slot = offs[p] + atomicAdd(fill + p, 1);
+        perm[slot] = (int)r;
+        skey[slot] = h.x;
+    }
+}
+
+// per-point / per-body record counts of an externally gathered record set (multi-GPU import)
+__global__ void k_count_records(const PointRec* __restrict__ prec, long long nprec, const BodyRec* __restrict__ brec,
+                                long long nbrec, int* cnt, int* cnt_rg)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < nprec; r += stride) atomicAdd(cnt + prec[r].point, 1);
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < nbrec; r += stride) atomicAdd(cnt_rg + brec[r].body, 1);
+}
+
+// One warp per point.  Rank the point's keys (all-pairs compare, keys are unique), store the
+// records in rank order, then lanes 0..5 each sum one of imp.xyz / fric.xyz sequentially.
+// mode 0: apply to avgVel (updateAverageVelocity :707-724); mode 1: write the sums to acc arrays.
+__global__ void __launch_bounds__(256)
+k_reduce_points(const PointRec* __restrict__ rec, const int* __restrict__ offs, const int* __restrict__ cnt, int V,
+                const int* __restrict__ perm, int* __restrict__ perm_sorted, const unsigned long long* __restrict__ skey,
+                const uint8_t* __restrict__ vflags, Vec4* av, uint8_t* has, int mode, double* __restrict__ acc_imp,
+                double* __restrict__ acc_fric, unsigned long long* counters)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int p = blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < V; p += gridDim.x * warps_per_block) {
+        const int n = cnt[p];
+        if (n == 0) continue;
+        const int base = offs[p];
+        // rank = number of smaller keys
+        for (int t = lane; t < n; t += 32) {
+            const unsigned long long k = skey[base + t];
+            int rank = 0;
+            for (int u = 0; u < n; ++u) rank += skey[base + u] < k ? 1 : 0;
+            perm_sorted[base + rank] = perm[base + t];
+        }
+        __syncwarp();
+        double sum = 0.0;
+        if (lane < 6) {
+            for (int t = 0; t < n; ++t) {
+                const int r = perm_sorted[base + t];
+                const double* val = reinterpret_cast<const double*>(rec + r) + 2;  // imp[3], fric[3]
+                sum += val[lane];
+            }
+        }
+        const double fr = __shfl_down_sync(0xffffffffu, sum, 3);  // lanes 0..2 get fric.xyz
+        if (mode == 0) {
+            if (lane < 3 && !(vflags[p] & 1)) {
+                double* a = reinterpret_cast<double*>(av + p) + lane;
+                const double v = *a + (sum + fr) / n;
+                *a = v;
+                if (isinf(v) || isnan(v)) atomicAdd(&counters[CTR_ERROR], 1ull);
+                if (lane == 0) has[p] = 1;
+            }
+        } else if (lane < 6) {
+            if (lane < 3) acc_imp[3 * (size_t)p + lane] = sum;
+            else acc_fric[3 * (size_t)p + lane - 3] = sum;
+        }
+        __syncwarp();
+    }
+}
+
+// Rigid-rigid contacts: per-body sums in key order.  One thread per body; records are few.
+// imp_rg accumulates across passes and steps -- the reference never zeroes collsnImpulse_RG
+// (dcollid.cpp:726-733).
+__global__ void k_reduce_bodies(const BodyRec* __restrict__ rec, const unsigned long long* __restrict__ n_rec_ptr,
+                                long long cap, int nbody, double* imp_rg)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbody) return;
+    long long n = (long long)*n_rec_ptr;
+    if (n > cap) n = cap;
+    unsigned long long last = 0;
+    bool first = true;
+    double s[3] = {imp_rg[3 * b], imp_rg[3 * b + 1], imp_rg[3 * b + 2]};
+    while (true) {
+        // next record of this body in (key, slot-of-point) order; a key can appear twice for one body
+        // only if both sides of a contact are the same body, which the same-surface filter excludes
+        long long best = -1;
+        unsigned long long bk = ~0ull;
+        for (long long r = 0; r < n; ++r) {
+            if (rec[r].body != b) continue;
+            unsigned long long k = rec[r].key;
+            if (!first && k <= last) continue;
+            if (k < bk) { bk = k; best = r; }
+        }
+        if (best < 0) break;
+        s[0] += rec[best].v[0]; s[1] += rec[best].v[1]; s[2] += rec[best].v[2];
+        last = bk;
+        first = false;
+    }
+    imp_rg[3 * b] = s[0]; imp_rg[3 * b + 1] = s[1]; imp_rg[3 * b + 2] = s[2];
+}
+
+// updateAverageVelocity :726-733: avgVel += collsnImpulse_RG / collsn_num_RG for every non-static
+// point of a body that was hit this pass
+__global__ void k_apply_bodies(int V, const uint8_t* __restrict__ vflags, const int* __restrict__ vbody,
+                               const double* __restrict__ imp_rg, const int* __restrict__ cnt_rg, Vec4* av, uint8_t* has)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= V) return;
+    if (vflags[p] & 1) return;
+    const int b = vbody[p];
+    const int n = cnt_rg[b];
+    if (n <= 0) return;
+    has[p] = 1;
+    Vec4 v = av[p];
+    v.x += imp_rg[3 * b] / n;
+    v.y += imp_rg[3 * b + 1] / n;
+    v.z += imp_rg[3 * b + 2] / n;
+    av[p] = v;
+}
+
+// computeAverageVelocity, dcollid.cpp:160-220
+__global__ void k_avg_velocity(int V, const Vec4* __restrict__ xo, const Vec4* __restrict__ xn, Vec4* __restrict__ av,
+                               double dt, unsigned long long* counters)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= V) return;
+    Vec4 a = xo[p], b = xn[p], v;
+    if (dt > CLSN_ROUND_EPS) {
+        v.x = (b.x - a.x) / dt; v.y = (b.y - a.y) / dt; v.z = (b.z - a.z) / dt;
+    } else {
+        v.x = v.y = v.z = 0.0;
+    }
+    v.w = 0.0;
+    if (isnan(v.x) || isinf(v.x) || isnan(v.y) || isinf(v.y) || isnan(v.z) || isinf(v.z))
+        atomicAdd(&counters[CTR_ERROR], 1ull);
+    av[p] = v;
+}
+
+// detectDomainBoundaryCollision (dcollid.cpp:116-158) -- once per unique point, see SURVEY a14
+__global__ void k_boundary(int V, const uint8_t* __restrict__ vflags, const Vec4* __restrict__ xo, Vec4* av, uint8_t* has,
+                           double dt, double mu, double lo0, double lo1, double lo2, double hi0, double hi1, double hi2)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= V) return;
+    if (vflags[p] & 2) return;  // isMovableRigidBody(pt): skipped (:123)
+    const Vec4 x = xo[p];
+    Vec4 v4 = av[p];
+    double v[3] = {v4.x, v4.y, v4.z};
+    const double xs[3] = {x.x, x.y, x.z};
+    const double L[3] = {lo0, lo1, lo2}, U[3] = {hi0, hi1, hi2};
+    double dv = 0;
+    bool hit = false;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const double cand = xs[j] + dt * v[j];
+        if (cand <= L[j] || cand >= U[j]) {
+            hit = true;
+            dv = fabs(v[j]);
+            v[j] = 0.0;
+        }
+    }
+    const double preVt = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (preVt > CLSN_MACH_EPS) {
+        const double f = stdmax(1.0 - mu * dv / preVt, 0.0);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) v[j] *= f;
+    }
+    if (hit) has[p] = 1;
+    v4.x = v[0]; v4.y = v[1]; v4.z = v[2];
+    av[p] = v4;
+}
+
+// updateFinalPosition, dcollid.cpp:562-584
+__global__ void k_final_position(int V, const Vec4* __restrict__ xo, const Vec4* __restrict__ av, Vec4* __restrict__ xn, double dt)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= V) return;
+    const Vec4 x = xo[p], v = av[p];
+    Vec4 r;
+    r.x = x.x + v.x * dt; r.y = x.y + v.y * dt; r.z = x.z + v.z * dt; r.w = 0.0;
+    xn[p] = r;
+}
+
+// packed xyz (3V doubles) <-> padded Vec4
+__global__ void k_pack(int V, const double* __restrict__ src, Vec4* __restrict__ dst)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= V) return;
+    dst[p] = Vec4{src[3 * (size_t)p], src[3 * (size_t)p + 1], src[3 * (size_t)p + 2], 0.0};
+}
+__global__ void k_unpack(int V, const Vec4* __restrict__ src, double* __restrict__ dst)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= V) return;
+    const Vec4 v = src[p];
+    dst[3 * (size_t)p] = v.x; dst[3 * (size_t)p + 1] = v.y; dst[3 * (size_t)p + 2] = v.z;
+}
+
+} // namespace clsn

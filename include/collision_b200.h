@@ -1,0 +1,153 @@
+/* collision_b200 -- C ABI of the B200 collision step.
+ *
+ * Drop-in boundary for the per-step hot path of antdvid/Collision: everything that
+ * CollisionSolver::resolveCollision() (dcollid.cpp:317-362) does between "the caller filled
+ * x_old / candidate Coords" and "avgVel / Coords / vel / has_collsn are final", i.e.
+ *   computeAverageVelocity   dcollid.cpp:160-220
+ *   detectProximity          dcollid.cpp:390-406  (aabbProximity :366-388, AABB.cpp, TriToTri ...)
+ *   detectCollision          dcollid.cpp:430-468  (aabbCollision :409-428, MovingTriToTri ...)
+ *   updateAverageVelocity    dcollid.cpp:677-751  (+ updateImpactZoneVelocityForRG :267-288)
+ *   detectDomainBoundaryCollision :116-158, updateFinalPosition :562-584, updateFinalVelocity :598-624
+ * runs on the GPU behind these entry points.  The host-side mirror of the reference's own
+ * interface (CollisionSolver3d, CD_HSE/CD_TRI/CD_BOND/CD_POINT) that calls them lives in
+ * collision_b200/host/collid_b200.h; INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Plain C types only.  All host arrays are caller-owned; "3V" arrays are xyz per vertex.
+ * Every function returns 0 on success or a negative clsn_status; clsn_last_error() gives text.
+ * A context is bound to one CUDA device and is not thread-safe.  There is no CPU fallback:
+ * without a usable device clsn_create fails.
+ */
+#ifndef COLLISION_B200_H
+#define COLLISION_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct clsn_ctx clsn_ctx;
+
+typedef enum {
+    CLSN_OK = 0,
+    CLSN_E_CUDA = -1,      /* CUDA runtime error                                        */
+    CLSN_E_ARG = -2,       /* bad argument / call order                                 */
+    CLSN_E_NUMERIC = -3,   /* NaN/Inf where the reference calls clean_up(ERROR)          */
+    CLSN_E_NOMEM = -4,     /* device allocation failed                                  */
+    CLSN_E_UNSUPPORTED = -5/* element pair type the reference does not implement either  */
+} clsn_status;
+
+/* CollisionSolver's static parameters (dcollid.cpp:28-35, setters :57-89) + domain box
+ * (setDomainBoundary :109-114).  dt is what assembleFromInterface passes to setTimeStepSize. */
+typedef struct {
+    double eps;        /* setRoundingTolerance   default 1e-6  */
+    double thickness;  /* setFabricThickness     default 1e-4  */
+    double dt;         /* setTimeStepSize        default 1e-3  */
+    double k;          /* setSpringConstant      default 1000  */
+    double m;          /* setPointMass           default 0.01  */
+    double lambda;     /* setFrictionConstant    default 0.02  */
+    double cr;         /* setRestitutionCoef     default 0     */
+    double lo[3];      /* domain lower corner                  */
+    double hi[3];      /* domain upper corner                  */
+} clsn_params;
+
+enum { CLSN_PROXIMITY = 0, CLSN_COLLISION = 1 };
+enum { CLSN_VFLAG_FIXED = 1, CLSN_VFLAG_MOVABLE_RG = 2 };
+#define CLSN_MAX_CCD_PASSES 5 /* MAX_ITER, dcollid.cpp:433 */
+
+/* One detection pass (aabbProximity/aabbCollision + tree query). */
+typedef struct {
+    int64_t candidates;     /* element pairs with overlapping leaf boxes = narrow-phase callbacks  */
+    int64_t pairs_tested;   /* of those, pairs without a shared vertex handed to the feature tests */
+    int64_t true_pairs;     /* pairs for which isProximity/isCollision returned true (tree count)  */
+    int64_t contacts;       /* feature tests that fired                                            */
+    int64_t contributions;  /* per-point impulse records reduced                                   */
+} clsn_pass_stats;
+
+typedef struct {
+    clsn_pass_stats proximity;
+    int32_t n_ccd_passes;
+    int32_t has_collision;      /* hasCollision(): first CCD pass found something (dcollid.cpp:456) */
+    int32_t still_colliding;    /* MAX_ITER passes did not resolve: the reference would enter
+                                   computeImpactZone (host fail-safe, out of scope)                */
+    int32_t reserved;
+    clsn_pass_stats ccd[CLSN_MAX_CCD_PASSES];
+    float ms_total;             /* device time of the whole step (CUDA events)                     */
+    float ms_phase[8];          /* avgvel, build, refit, traverse, narrow, reduce, finalize, other */
+} clsn_step_stats;
+
+/* Contact record for parity checks (same layout as oracle/collision_oracle.h: orc_contact). */
+typedef struct {
+    int32_t ea, eb;   /* element pair, ea < eb (hseList order: triangles then bonds) */
+    int32_t feature;  /* index of the feature test inside the pair, reference loop order */
+    int32_t kind;     /* 0 point-triangle, 1 edge-edge */
+    int32_t p[4];     /* points as passed to PointToTri / EdgeToEdge */
+    double root;      /* time of impact (CCD) or 0 */
+    double dist;
+    double nor[3];
+    double w[3];      /* point-tri: w0..w2 ; edge-edge: a, b, 0 */
+} clsn_contact;
+
+/* ---- lifetime */
+int clsn_create(clsn_ctx** out, int device);
+void clsn_destroy(clsn_ctx*);
+const char* clsn_last_error(const clsn_ctx*);
+
+/* ---- setup (assembleFromInterface, dcollid3d.cpp:12-52): once per topology */
+int clsn_set_params(clsn_ctx*, const clsn_params*);
+/* tri_idx[3T], tri_surf[T] (surface id per triangle), bond_idx[2B], vflags[V] (CLSN_VFLAG_*),
+ * vbody[V] hyper-surface/body id per vertex in [0,nbody), body_mass[nbody] = total_mass(hs). */
+int clsn_set_topology(clsn_ctx*, int V, int T, const int32_t* tri_idx, const int32_t* tri_surf, int B,
+                      const int32_t* bond_idx, const uint8_t* vflags, const int32_t* vbody, int nbody,
+                      const double* body_mass);
+
+/* ---- per step, host buffers (the call sequence a drop-in CollisionSolver3d makes) */
+/* x_old[3V], x_new[3V] = Coords as the spring solver left them; clears per-step accumulators */
+int clsn_upload_state(clsn_ctx*, const double* x_old, const double* x_new);
+int clsn_resolve(clsn_ctx*, clsn_step_stats* stats); /* resolveCollision() minus strain limiting */
+/* any pointer may be NULL.  x[3V] final Coords, avgvel[3V], has_collsn[V] */
+int clsn_download_state(clsn_ctx*, double* x, double* avgvel, uint8_t* has_collsn);
+/* upload + resolve + download + "vel = avgVel where has_collsn" (updateFinalVelocity) in one call */
+int clsn_step_host(clsn_ctx*, const double* x_old, const double* x_new, double* x_out, double* vel_inout,
+                   uint8_t* has_collsn_out, clsn_step_stats* stats);
+
+/* ---- per step, device buffers (inputs already resident in HBM; 3V doubles, xyz per vertex) */
+int clsn_upload_state_device(clsn_ctx*, const double* d_x_old, const double* d_x_new);
+int clsn_download_state_device(clsn_ctx*, double* d_x, double* d_avgvel);
+
+/* ---- single phases (parity tests drive these from identical inputs) */
+int clsn_avg_velocity(clsn_ctx*);
+int clsn_detect(clsn_ctx*, int mode, clsn_pass_stats* stats); /* tree + query + narrow phase    */
+int clsn_apply(clsn_ctx*, int rigidify);                      /* reduce + updateAverageVelocity */
+int clsn_boundary(clsn_ctx*);
+int clsn_final_position(clsn_ctx*);
+int clsn_set_avgvel(clsn_ctx*, const double* avgvel);         /* host 3V */
+
+/* ---- multi-GPU: this rank traverses query leaves [rank*N/nranks, (rank+1)*N/nranks) of the
+ * Morton order; contribution records are exchanged by the caller (NCCL all-gather of the buffers
+ * below) and every rank reduces the union in canonical order -> identical state on all ranks. */
+int clsn_set_slice(clsn_ctx*, int rank, int nranks);
+/* after clsn_detect: device pointers + counts of the records this rank produced */
+int clsn_export_records(clsn_ctx*, void** d_point_records, int64_t* n_point_records, void** d_body_records,
+                        int64_t* n_body_records, int64_t* true_pairs);
+/* replace the record set to be reduced by clsn_apply with externally gathered ones (device ptrs) */
+int clsn_import_records(clsn_ctx*, const void* d_point_records, int64_t n_point_records,
+                        const void* d_body_records, int64_t n_body_records);
+#define CLSN_POINT_RECORD_BYTES 64
+#define CLSN_BODY_RECORD_BYTES 48
+
+/* ---- debug / parity readbacks (host buffers) */
+int clsn_set_debug(clsn_ctx*, int record_candidates, int record_contacts);
+int64_t clsn_num_candidates(clsn_ctx*);
+int clsn_get_candidates(clsn_ctx*, int32_t* pairs /* 2 per pair, unsorted */);
+int64_t clsn_num_contacts(clsn_ctx*);
+int clsn_get_contacts(clsn_ctx*, clsn_contact* out /* unsorted */);
+/* accumulators as updateAverageVelocity would see them, reduced in canonical order:
+ * imp[3V], fric[3V], cnt[V], imp_rg[3*nbody], cnt_rg[nbody] */
+int clsn_get_accumulators(clsn_ctx*, double* imp, double* fric, int32_t* cnt, double* imp_rg, int32_t* cnt_rg);
+int clsn_set_body_accumulators(clsn_ctx*, const double* imp_rg, const int32_t* cnt_rg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

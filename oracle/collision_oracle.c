@@ -58,6 +58,7 @@ void orc_set_libm(int mode) { g_libm = mode; }
 int orc_get_libm(void) { return g_libm; }
 static double m_acos(double x) { return g_libm ? (double)acosq((__float128)x) : acos(x); }
 static double m_cos(double x) { return g_libm ? (double)cosq((__float128)x) : cos(x); }
+static double m_sin(double x) { return g_libm ? (double)sinq((__float128)x) : sin(x); }
 static double m_pow13(double x)
 {
     return g_libm ? (double)powq((__float128)x, (__float128)(1.0 / 3.0)) : pow(x, 1.0 / 3.0);
@@ -808,12 +809,12 @@ static void rigidify_list(orc_ctx* c, int head)
             double s = dot3(dx, w) / dot3(w, w);
             for (int i = 0; i < 3; ++i) xF[i] = s * w[i];
             sub3(dx, xF, xR);
-            double q = sin(dt * mag_w) / mag_w;
+            double q = m_sin(dt * mag_w) / mag_w;
             for (int i = 0; i < 3; ++i) tmpV[i] = q * w[i];
             cross3(tmpV, xR, wxR);
         }
         for (int i = 0; i < 3; ++i) {
-            double x_new = x_cm[i] + dt * v_cm[i] + xF[i] + cos(dt * mag_w) * xR[i] + wxR[i];
+            double x_new = x_cm[i] + dt * v_cm[i] + xF[i] + m_cos(dt * mag_w) * xR[i] + wxR[i];
             c->av[3 * p + i] = (x_new - c->xo[3 * p + i]) / dt;
             if (isnan(c->av[3 * p + i])) c->error = 1;
         }
