@@ -201,6 +201,14 @@ struct clsn_ctx {
     bool dbg_candidates = false, dbg_contacts = false;
     long long n_dbg_cand = 0, n_contacts = 0;
     cudaEvent_t ev[2 * PH_COUNT + 2];
+    // phase timing: events recorded on the stream between kernel groups, resolved after the step
+    std::vector<cudaEvent_t> marks;
+    std::vector<int> mark_phase;
+    size_t n_marks = 0;
+    bool timing = false;
+    long long launches = 0;        // kernels launched by this library (incl. CUB's) since the last reset
+    long long kernel_count[16] = {0};
+    cudaEvent_t bracket[2];
     int sm_count = 148;
 };
 
@@ -212,6 +220,21 @@ struct clsn_ctx {
             return _e == cudaErrorMemoryAllocation ? CLSN_E_NOMEM : CLSN_E_CUDA;              \
         }                                                                                     \
     } while (0)
+
+// record "everything enqueued since the previous mark belongs to `phase`"
+static void mark(clsn_ctx* c, int phase)
+{
+    if (!c->timing) return;
+    if (c->n_marks == c->marks.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->marks.push_back(e);
+        c->mark_phase.push_back(0);
+    }
+    cudaEventRecord(c->marks[c->n_marks], c->stream);
+    c->mark_phase[c->n_marks] = phase;
+    ++c->n_marks;
+}
 
 static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t > 0 ? (n + t - 1) / t : 1); }
 
@@ -235,6 +258,8 @@ extern "C" int clsn_create(clsn_ctx** out, int device)
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     for (auto& e : c->ev) cudaEventCreate(&e);
+    cudaEventCreate(&c->bracket[0]);
+    cudaEventCreate(&c->bracket[1]);
     cudaMallocHost((void**)&c->h_counters, 64 * sizeof(unsigned long long));
     c->counters.reserve(64);
     c->bounds.reserve(8);
@@ -262,6 +287,9 @@ extern "C" void clsn_destroy(clsn_ctx* c)
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     for (auto& e : c->ev) cudaEventDestroy(e);
+    for (auto& e : c->marks) cudaEventDestroy(e);
+    cudaEventDestroy(c->bracket[0]);
+    cudaEventDestroy(c->bracket[1]);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -380,6 +408,7 @@ extern "C" int clsn_upload_state_device(clsn_ctx* c, const double* d_x_old, cons
     k_pack<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, d_x_old, c->xo.p);
     k_pack<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, d_x_new, c->xn.p);
     CK(cudaGetLastError());
+    c->launches += 2;
     return begin_step(c);
 }
 
@@ -401,6 +430,7 @@ extern "C" int clsn_download_state_device(clsn_ctx* c, double* d_x, double* d_av
     if (d_x) k_unpack<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->xn.p, d_x);
     if (d_avgvel) k_unpack<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->av.p, d_avgvel);
     CK(cudaGetLastError());
+    c->launches += (d_x ? 1 : 0) + (d_avgvel ? 1 : 0);
     return CLSN_OK;
 }
 
@@ -439,6 +469,8 @@ extern "C" int clsn_avg_velocity(clsn_ctx* c)
     CK(cudaMemsetAsync(c->counters.p, 0, CTR_COUNT * sizeof(unsigned long long), c->stream));
     k_avg_velocity<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->xo.p, c->xn.p, c->av.p, c->prm.dt, c->counters.p);
     CK(cudaGetLastError());
+    c->launches += 1;
+    mark(c, PH_AVG);
     return CLSN_OK;
 }
 
@@ -454,6 +486,8 @@ static int build_tree(clsn_ctx* c)
     CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->code.p, c->code_sorted.p, c->idx.p, c->leaf_elem.p, N, 0, 30, c->stream));
     if (N >= 2) k_hierarchy<<<nblk(N - 1, 256), 256, 0, c->stream>>>(c->code_sorted.p, N, c->nodes.p, c->leaf_parent.p);
     CK(cudaGetLastError());
+    c->launches += 2 + 4 + (N >= 2 ? 1 : 0);  // bounds, morton, radix sort (4 onesweep kernels), hierarchy
+    mark(c, PH_BUILD);
     c->tree_built = true;
     return CLSN_OK;
 }
@@ -484,12 +518,16 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
         else
             k_refit<false><<<nblk(N, 128), 128, 0, c->stream>>>(c->elem.p, c->leaf_elem.p, N, c->xo.p, c->av.p, c->prm.dt,
                                                                   c->lbox.p, c->nodes.p, c->leaf_parent.p, c->flags.p);
+        c->launches += 1;
+        mark(c, PH_REFIT);
         TraverseOut to;
         to.pairs = c->pairs.p; to.cap_pairs = (long long)c->pairs.n;
         to.dbg_cand = c->dbg_candidates ? c->dbg_cand.p : nullptr; to.cap_dbg = (long long)c->dbg_cand.n;
         to.counters = c->counters.p;
         if (q_hi > q_lo)
             k_traverse<<<nblk(q_hi - q_lo, 128), 128, 0, c->stream>>>(c->nodes.p, c->lbox.p, c->leaf_elem.p, c->elem.p, N, q_lo, q_hi, to);
+        c->launches += (q_hi > q_lo) ? 1 : 0;
+        mark(c, PH_TRAVERSE);
         Emit E;
         E.prec = c->prec.p; E.brec = c->brec.p; E.contacts = c->dbg_contacts ? c->contacts.p : nullptr;
         E.counters = c->counters.p;
@@ -503,6 +541,8 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
             k_narrow<false><<<grid, NARROW_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p,
                                                                      c->vflags.p, c->vbody.p, P, E);
         CK(cudaGetLastError());
+        c->launches += 1;
+        mark(c, PH_NARROW);
         CK(cudaMemcpyAsync(c->h_counters, c->counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         const unsigned long long* h = c->h_counters;
@@ -581,6 +621,7 @@ static int reduce_records(clsn_ctx* c, int mode)
         k_reduce_points<<<c->sm_count * 8, 256, 0, c->stream>>>(prec, c->offs.p, c->cnt.p, V, c->perm.p, c->perm_sorted.p, c->skey.p,
                                                                   c->vflags.p, c->av.p, c->has.p, mode, c->acc_imp.p, c->acc_fric.p,
                                                                   c->counters.p);
+        c->launches += 2 + 2;  // scan (init + scan), scatter, reduce
     } else if (mode == 1) {
         CK(c->acc_imp.reserve(3 * (size_t)V)); CK(c->acc_fric.reserve(3 * (size_t)V));
         CK(cudaMemsetAsync(c->acc_imp.p, 0, 3 * (size_t)V * sizeof(double), c->stream));
@@ -589,6 +630,7 @@ static int reduce_records(clsn_ctx* c, int mode)
     if (nbrec > 0 && mode == 0) {
         const long long cap = c->imp_nprec >= 0 ? nbrec : (long long)c->brec.n;
         k_reduce_bodies<<<nblk(c->nbody, 64), 64, 0, c->stream>>>(brec, n_brec_dev, cap, c->nbody, c->imp_rg.p);
+        c->launches += 1;
     }
     CK(cudaGetLastError());
     return CLSN_OK;
@@ -607,6 +649,7 @@ extern "C" int clsn_apply(clsn_ctx* c, int rigidify)
             k_apply_bodies<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->vflags.p, c->vbody.p, c->imp_rg.p, c->cnt_rg.p,
                                                                     c->av.p, c->has.p);
             CK(cudaMemsetAsync(c->cnt_rg.p, 0, c->nbody * sizeof(int), c->stream));
+            c->launches += 1;
         }
         CK(cudaMemsetAsync(c->cnt.p, 0, ((size_t)c->V + 1) * sizeof(int), c->stream));
         c->records_pending = false;
@@ -615,8 +658,10 @@ extern "C" int clsn_apply(clsn_ctx* c, int rigidify)
     if (rigidify && c->has_movable && c->prm.dt > 0.0) {
         int r = c->rigid.rigidify(c->xo.p, c->av.p, c->vflags.p, c->prm.m, c->prm.dt, c->counters.p, c->stream);
         if (r != 0) return fail(c, CLSN_E_CUDA, "rigid-body kernels failed");
+        c->launches += c->rigid.nlists ? 2 : 0;
     }
     CK(cudaGetLastError());
+    mark(c, PH_REDUCE);
     return CLSN_OK;
 }
 
@@ -628,6 +673,7 @@ extern "C" int clsn_boundary(clsn_ctx* c)
     k_boundary<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->vflags.p, c->xo.p, c->av.p, c->has.p, p.dt, p.lambda, p.lo[0],
                                                          p.lo[1], p.lo[2], p.hi[0], p.hi[1], p.hi[2]);
     CK(cudaGetLastError());
+    c->launches += 1;
     return CLSN_OK;
 }
 
@@ -637,6 +683,8 @@ extern "C" int clsn_final_position(clsn_ctx* c)
     cudaSetDevice(c->device);
     k_final_position<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->xo.p, c->av.p, c->xn.p, c->prm.dt);
     CK(cudaGetLastError());
+    c->launches += 1;
+    mark(c, PH_FINAL);
     return CLSN_OK;
 }
 
@@ -648,7 +696,10 @@ extern "C" int clsn_resolve(clsn_ctx* c, clsn_step_stats* stats)
     clsn_step_stats s;
     memset(&s, 0, sizeof(s));
     int r;
+    c->timing = true;
+    c->n_marks = 0;
     CK(cudaEventRecord(c->ev[0], c->stream));
+    mark(c, PH_OTHER);
     if ((r = clsn_avg_velocity(c))) return r;
     if ((r = run_detect(c, CLSN_PROXIMITY, &s.proximity, true, 0))) return r;
     if ((r = clsn_apply(c, 1))) return r;
@@ -671,6 +722,11 @@ extern "C" int clsn_resolve(clsn_ctx* c, clsn_step_stats* stats)
     CK(cudaStreamSynchronize(c->stream));
     if (c->h_counters[CTR_ERROR]) return fail(c, CLSN_E_NUMERIC, "NaN/Inf in the collision step (reference: clean_up(ERROR))");
     CK(cudaEventElapsedTime(&s.ms_total, c->ev[0], c->ev[1]));
+    c->timing = false;
+    for (size_t i = 1; i < c->n_marks; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->marks[i - 1], c->marks[i]) == cudaSuccess) s.ms_phase[c->mark_phase[i]] += ms;
+    }
     if (stats) *stats = s;
     return CLSN_OK;
 }
@@ -697,6 +753,40 @@ extern "C" int clsn_step_host(clsn_ctx* c, const double* x_old, const double* x_
         for (int p = 0; p < c->V; ++p)
             if (has[p])
                 for (int j = 0; j < 3; ++j) vel_inout[3 * (size_t)p + j] = av[3 * (size_t)p + j];
+    return CLSN_OK;
+}
+
+// ------------------------------------------------------------------ measurement helpers
+// CUDA events on the library's own stream (torch.cuda.Event only sees torch's current stream)
+extern "C" int clsn_timer_start(clsn_ctx* c)
+{
+    if (!c) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventRecord(c->bracket[0], c->stream));
+    return CLSN_OK;
+}
+extern "C" int clsn_timer_stop(clsn_ctx* c, float* ms)
+{
+    if (!c || !ms) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaEventRecord(c->bracket[1], c->stream));
+    CK(cudaEventSynchronize(c->bracket[1]));
+    CK(cudaEventElapsedTime(ms, c->bracket[0], c->bracket[1]));
+    return CLSN_OK;
+}
+extern "C" int64_t clsn_launch_count(clsn_ctx* c, int reset)
+{
+    if (!c) return 0;
+    long long n = c->launches;
+    if (reset) c->launches = 0;
+    return n;
+}
+extern "C" int clsn_synchronize(clsn_ctx* c)
+{
+    if (!c) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaStreamSynchronize(c->stream));
     return CLSN_OK;
 }
 

@@ -52,7 +52,9 @@ class clsn_step_stats(C.Structure):
     def as_dict(self):
         return dict(proximity=self.proximity.as_dict(), n_ccd_passes=int(self.n_ccd_passes),
                     has_collision=bool(self.has_collision), still_colliding=bool(self.still_colliding),
-                    ccd=[self.ccd[i].as_dict() for i in range(int(self.n_ccd_passes))], ms_total=float(self.ms_total))
+                    ccd=[self.ccd[i].as_dict() for i in range(int(self.n_ccd_passes))], ms_total=float(self.ms_total),
+                    ms_phase=dict(zip(("avgvel", "build", "refit", "traverse", "narrow", "reduce", "finalize", "other"),
+                                      [float(v) for v in self.ms_phase])))
 
 
 CONTACT_DTYPE = np.dtype([("ea", "<i4"), ("eb", "<i4"), ("feature", "<i4"), ("kind", "<i4"), ("p", "<i4", (4,)),
@@ -96,6 +98,11 @@ def load_library():
     L.clsn_set_slice.argtypes = [V, I, I]
     L.clsn_export_records.argtypes = [V, P(V), P(C.c_int64), P(V), P(C.c_int64), P(C.c_int64)]
     L.clsn_import_records.argtypes = [V, V, C.c_int64, V, C.c_int64]
+    L.clsn_timer_start.argtypes = [V]
+    L.clsn_timer_stop.argtypes = [V, P(C.c_float)]
+    L.clsn_launch_count.restype = C.c_int64
+    L.clsn_launch_count.argtypes = [V, I]
+    L.clsn_synchronize.argtypes = [V]
     L.clsn_set_debug.argtypes = [V, I, I]
     L.clsn_num_candidates.restype = C.c_int64
     L.clsn_num_candidates.argtypes = [V]
@@ -305,6 +312,25 @@ class CollisionSolver3d:
         self.has_collision = bool(st.has_collision)
         self.last_stats = st.as_dict()
         return self.last_stats
+
+    def upload_device(self, d_x_old_ptr, d_x_new_ptr):
+        """x_old / x_new already in HBM (3V doubles each, e.g. torch tensors' data_ptr())."""
+        self._push_params()
+        self.ctx.check(self.ctx.L.clsn_upload_state_device(self.ctx.h, d_x_old_ptr, d_x_new_ptr))
+
+    def timer_start(self):
+        self.ctx.check(self.ctx.L.clsn_timer_start(self.ctx.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self.ctx.check(self.ctx.L.clsn_timer_stop(self.ctx.h, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self, reset=False) -> int:
+        return int(self.ctx.L.clsn_launch_count(self.ctx.h, 1 if reset else 0))
+
+    def synchronize(self):
+        self.ctx.check(self.ctx.L.clsn_synchronize(self.ctx.h))
 
     def set_avgvel(self, av):
         a = np.ascontiguousarray(av, dtype=np.float64)

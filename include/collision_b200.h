@@ -123,6 +123,12 @@ int clsn_boundary(clsn_ctx*);
 int clsn_final_position(clsn_ctx*);
 int clsn_set_avgvel(clsn_ctx*, const double* avgvel);         /* host 3V */
 
+/* ---- measurement: CUDA events on the library's stream, kernel-launch counter */
+int clsn_timer_start(clsn_ctx*);
+int clsn_timer_stop(clsn_ctx*, float* ms);
+int64_t clsn_launch_count(clsn_ctx*, int reset);
+int clsn_synchronize(clsn_ctx*);
+
 /* ---- multi-GPU: this rank traverses query leaves [rank*N/nranks, (rank+1)*N/nranks) of the
  * Morton order; contribution records are exchanged by the caller (NCCL all-gather of the buffers
  * below) and every rank reduces the union in canonical order -> identical state on all ranks. */
