@@ -1,0 +1,114 @@
+"""CPU tests of the host side: scene generators, the C ABI surface, failing loudly without a GPU,
+the correctly rounded math of the kernels (host build of crmath.cuh) and the multi-rank exchange."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_config4_is_one_million_triangles():
+    from collision_b200 import scenes
+    sc = scenes.layered_cloth(8, 251)
+    assert sc.T == 1_000_000 and sc.V == 504_008 and sc.n_surf == 8
+    sc2 = scenes.layered_cloth(8, 251)
+    assert np.array_equal(sc.x, sc2.x) and np.array_equal(sc.vel, sc2.vel)
+    assert (np.diff(sc.tri_surf) >= 0).all()
+
+
+def test_reference_decks_restated():
+    from collision_b200 import scenes
+    s = scenes.string_string()
+    assert s.B == 2 * 192 and s.V == 2 * 193 and s.T == 0          # cdinit.cpp:157-159
+    b = scenes.ball_plane()
+    assert (b.vflags[b.vhs == 0] == 2).all() and (b.vflags[b.vhs == 1] == 0).all()
+    assert np.allclose(b.lo, [0, 0, 0.25]) and np.allclose(b.hi, [0.5, 0.5, 0.75])
+    bb = scenes.box_boundary()
+    assert (bb.vflags == 2).all()
+
+
+def _lib_path():
+    from collision_b200 import build
+    return build.build()
+
+
+def test_c_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "collision_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(clsn_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(names) >= 30
+    lib = ctypes.CDLL(_lib_path())
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in include/collision_b200.h but not exported: {missing}"
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product refuses to work instead of computing on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from collision_b200.solver import CollisionError, CollisionSolver3d
+    with pytest.raises(CollisionError):
+        CollisionSolver3d()
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "collision_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "collision_oracle" not in src and "libcollision_ref" not in src, f
+
+
+def test_static_parameter_api():
+    from collision_b200.solver import CollisionSolver3d as S
+    old = S.getFrictionConstant()
+    S.setFrictionConstant(0.0)
+    assert S.getFrictionConstant() == 0.0
+    S.setFrictionConstant(old)
+    assert (S.getRoundingTolerance(), S.getFabricThickness(), S.getSpringConstant(), S.getPointMass()) == (1e-6, 1e-4, 1000.0, 0.01)
+
+
+def test_crmath_correctly_rounded_on_host():
+    """crmath.cuh (the kernels' acos/cos/pow) compiled for the host and compared with binary128."""
+    exe = "/tmp/clsn_crmath_check"
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-mfma", "-x", "c++", "-I", os.path.join(ROOT, "collision_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "crmath_check.cpp"), "-o", exe, "-lquadmath", "-lm"])
+    out = subprocess.check_output([exe, "300000"], text=True)
+    for line in out.strip().splitlines():
+        name, n, bad = line.split()
+        assert int(bad) == 0, f"{name}: {bad} of {n} results are not correctly rounded"
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from collision_b200.dist import gather_varlen
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo")
+n = [5 * 64, 0, 3 * 64][rank]
+local = (torch.arange(n, dtype=torch.int64) %% 251 + rank).to(torch.uint8)
+out = gather_varlen(local)
+exp = torch.cat([(torch.arange(m, dtype=torch.int64) %% 251 + r).to(torch.uint8) for r, m in enumerate([5 * 64, 0, 3 * 64])])
+assert torch.equal(out, exp), (rank, out.shape)
+empty = gather_varlen(torch.empty(0, dtype=torch.uint8))
+assert empty.numel() == 0
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_record_exchange_gloo_world3():
+    """the N > 1 exchange (variable-length all-gather of record buffers) on CPU tensors with gloo"""
+    code = _WORKER % ROOT
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", "--no-python", sys.executable, "-c", code]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 3
