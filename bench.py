@@ -185,6 +185,7 @@ def algorithmic_bytes(scene, st):
     Pt = sum(p["pairs_tested"] for p in passes)
     C = sum(p["contacts"] for p in passes)
     K = sum(p["contributions"] for p in passes)
+    F = sum(p.get("features", 0) for p in passes)
     n = len(passes)
     return {
         "avgvel": 72 * V,
@@ -194,7 +195,7 @@ def algorithmic_bytes(scene, st):
         "narrow": 8 * Pt + n * (48 * V + 12 * T) + 64 * K,                    # pairs in, vertex data once, records out
         "reduce": 2 * 64 * K + n * 80 * V,                                    # records grouped + read, apply per vertex
         "finalize": (48 + 73) * V,
-    }, dict(P=P, Pt=Pt, C=C, K=K, passes=n)
+    }, dict(P=P, Pt=Pt, Fbox=sum(p.get("box_survivors", 0) for p in passes), F=F, C=C, K=K, passes=n)
 
 
 # ----------------------------------------------------------------------------- CUDA arm

@@ -42,89 +42,256 @@ __constant__ unsigned char c_feat_tt_static[15][4] = {
 // tri (a) - bond (b = slots 3,4) (TriToBond :508-530, MovingTriToBond :219-241)
 __constant__ unsigned char c_feat_tb[5][4] = {{0, 1, 2, 3}, {0, 1, 2, 4}, {0, 1, 3, 4}, {1, 2, 3, 4}, {2, 0, 3, 4}};
 
-#define NARROW_THREADS 128
+#define CULL_THREADS 128
+#define FEAT_THREADS 128
+
+// swept box of one point over [0, dt] (static: the point itself)
+struct PBox {
+    double lo[3], hi[3];
+};
 
 template <bool MOVING>
-__global__ void __launch_bounds__(NARROW_THREADS)
-k_narrow(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restrict__ elem, const Vec4* __restrict__ xo,
-         const Vec4* __restrict__ av, const uint8_t* __restrict__ vflags, const int* __restrict__ vbody, NarrowParams P, Emit E)
+__device__ __forceinline__ PBox point_box(const Vec4* __restrict__ xo, const Vec4* __restrict__ av, int id, double dt)
 {
-    // shared-memory staging of the six points of each thread's pair: [slot*3+c][thread]
-    __shared__ double s_x[18][NARROW_THREADS];
-    __shared__ double s_v[18][NARROW_THREADS];  // avgVel: CCD positions, and v_rel of the impulse in both modes
-    __shared__ int s_id[6][NARROW_THREADS];
-    __shared__ short s_fb[6][NARROW_THREADS];  // vertex flags (the body id is fetched only for all-rigid quads)
-    const int tid = threadIdx.x;
-    long long n_pairs = (long long)E.counters[CTR_PAIRS];
-    if (n_pairs > cap_pairs) n_pairs = cap_pairs;
-    const double h = MOVING ? P.eps : P.thickness;
-    unsigned long long n_true = 0;
-    for (long long base = (long long)blockIdx.x * NARROW_THREADS; base < n_pairs; base += (long long)gridDim.x * NARROW_THREADS) {
-        const long long pi = base + tid;
-        const bool live = pi < n_pairs;
-        int nfeat = 0, type = 0;  // 0 tri-tri, 1 tri-bond, 2 bond-bond
-        int2 pr = make_int2(0, 0);
-        if (live) {
-            pr = __ldg(pairs + pi);
-            const int4 A = __ldg(elem + pr.x), B = __ldg(elem + pr.y);
-            const int ids[6] = {A.x, A.y, A.z, B.x, B.y, B.z};
-            type = (A.z >= 0 ? 0 : 1) + (B.z >= 0 ? 0 : 1);
-            // with a < b and triangles numbered first, a mixed pair always has the triangle as a
-            nfeat = type == 0 ? 15 : (type == 1 ? 5 : 1);
+    PBox b;
+    const Vec4 x = ldg_vec4(xo + id);
+    const double x0[3] = {x.x, x.y, x.z};
+    if (MOVING) {
+        const Vec4 v = ldg_vec4(av + id);
+        const double vv[3] = {v.x, v.y, v.z};
 #pragma unroll
-            for (int s = 0; s < 6; ++s) {
-                const int id = ids[s];
-                s_id[s][tid] = id;
-                if (id >= 0) {
-                    const Vec4 x = ldg_vec4(xo + id);
-                    s_x[3 * s][tid] = x.x; s_x[3 * s + 1][tid] = x.y; s_x[3 * s + 2][tid] = x.z;
-                    const Vec4 v = ldg_vec4(av + id);
-                    s_v[3 * s][tid] = v.x; s_v[3 * s + 1][tid] = v.y; s_v[3 * s + 2][tid] = v.z;
-                    s_fb[s][tid] = (short)__ldg(vflags + id);
+        for (int d = 0; d < 3; ++d) {
+            const double x1 = x0[d] + vv[d] * dt;
+            b.lo[d] = fmin(x0[d], x1);
+            b.hi[d] = fmax(x0[d], x1);
+        }
+    } else {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) b.lo[d] = b.hi[d] = x0[d];
+    }
+    return b;
+}
+__device__ __forceinline__ PBox box_union(const PBox& a, const PBox& b)
+{
+    PBox r;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        r.lo[d] = fmin(a.lo[d], b.lo[d]);
+        r.hi[d] = fmax(a.hi[d], b.hi[d]);
+    }
+    return r;
+}
+// Can the two sub-features come within the contact distance at any t in [0, dt]?  A feature test fires
+// only if, at some t in [0, dt], the point lies within h of the triangle's hull inflated by the
+// barycentric slack eps (PointToTri :911-919), resp. the two segments come within h (EdgeToEdge :747).
+// Every position used by the test lies in the swept boxes, so a gap larger than
+// margin = 2h + (3 eps + 1e-2) * extent along any axis means "the reference returns false" -- the
+// 1e-2 * extent term dwarfs every rounding error of the test itself (DESIGN.md "exact culls").
+__device__ __forceinline__ bool boxes_far(const PBox& a, const PBox& b, double h2, double rel)
+{
+    bool far = false;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const double ext = fmax(a.hi[d] - a.lo[d], b.hi[d] - b.lo[d]);
+        const double m = h2 + rel * ext;
+        far = far || (a.lo[d] - b.hi[d] > m) || (b.lo[d] - a.hi[d] > m);
+    }
+    return far;
+}
+
+// Stage 1: one pair per thread.  (i) feature-level swept-box culling; (ii) CCD only: coefficients of
+// the coplanarity cubic + the trig-free classifier coplanar_maybe().  Features that can still fire
+// are appended to the work list as (pair index | feature << 28).  The six points of the pair are
+// staged in shared memory ([slot*3+c][thread], conflict-free) so that the per-feature gather of
+// four points is a shared-memory read with a runtime slot index instead of a register shuffle.
+template <bool MOVING>
+__global__ void __launch_bounds__(CULL_THREADS, 3)
+k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restrict__ elem, const Vec4* __restrict__ xo,
+       const Vec4* __restrict__ av, NarrowParams P, unsigned* __restrict__ feats, long long cap_feats,
+       unsigned long long* counters)
+{
+    __shared__ double s_x[18][CULL_THREADS];
+    __shared__ double s_v[MOVING ? 18 : 1][CULL_THREADS];
+    const int tid = threadIdx.x;
+    long long n_pairs = (long long)counters[CTR_PAIRS];
+    if (n_pairs > cap_pairs) n_pairs = cap_pairs;
+    const double h2 = 2.0 * (MOVING ? P.eps : P.thickness);
+    const double rel = 3.0 * P.eps + 1e-2;
+    unsigned long long n_box = 0;
+    for (long long pi = (long long)blockIdx.x * blockDim.x + tid; pi < n_pairs; pi += (long long)gridDim.x * blockDim.x) {
+        const int2 pr = __ldg(pairs + pi);
+        const int4 A = __ldg(elem + pr.x), B = __ldg(elem + pr.y);
+        const int ids[6] = {A.x, A.y, A.z, B.x, B.y, B.z};
+        PBox pb[6];
+#pragma unroll
+        for (int s = 0; s < 6; ++s) {
+            if (ids[s] < 0) { pb[s] = pb[0]; continue; }
+            const Vec4 x = ldg_vec4(xo + ids[s]);
+            const double x0[3] = {x.x, x.y, x.z};
+            s_x[3 * s][tid] = x.x; s_x[3 * s + 1][tid] = x.y; s_x[3 * s + 2][tid] = x.z;
+            if (MOVING) {
+                const Vec4 v = ldg_vec4(av + ids[s]);
+                const double vv[3] = {v.x, v.y, v.z};
+                s_v[3 * s][tid] = v.x; s_v[3 * s + 1][tid] = v.y; s_v[3 * s + 2][tid] = v.z;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const double x1 = x0[d] + vv[d] * P.dt;
+                    pb[s].lo[d] = fmin(x0[d], x1);
+                    pb[s].hi[d] = fmax(x0[d], x1);
+                }
+            } else {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) pb[s].lo[d] = pb[s].hi[d] = x0[d];
+            }
+        }
+        unsigned mask = 0;
+        int type = 0;
+        if (A.z >= 0 && B.z >= 0) {
+            PBox ea[3], eb[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                ea[i] = box_union(pb[i], pb[(i + 1) % 3]);
+                eb[i] = box_union(pb[3 + i], pb[3 + (i + 1) % 3]);
+            }
+            const PBox ta = box_union(ea[0], pb[2]), tb = box_union(eb[0], pb[5]);
+            // point-triangle features 0..5 (order differs between proximity and CCD, see c_feat_tt_*)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const bool a_tri_b_pt = !boxes_far(ta, pb[3 + i], h2, rel);  // triangle a, vertex b_i
+                const bool b_tri_a_pt = !boxes_far(tb, pb[i], h2, rel);      // triangle b, vertex a_i
+                if (MOVING) {
+                    mask |= (a_tri_b_pt ? 1u : 0u) << i;
+                    mask |= (b_tri_a_pt ? 1u : 0u) << (3 + i);
+                } else {
+                    mask |= (b_tri_a_pt ? 1u : 0u) << i;
+                    mask |= (a_tri_b_pt ? 1u : 0u) << (3 + i);
                 }
             }
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    if (!boxes_far(ea[i], eb[j], h2, rel)) mask |= 1u << (6 + 3 * i + j);
+        } else if (A.z >= 0) {
+            type = 1;  // triangle a, bond b: features 0,1 = vertex, 2..4 = tri edge x bond
+            const PBox ta = box_union(box_union(pb[0], pb[1]), pb[2]), bb = box_union(pb[3], pb[4]);
+            if (!boxes_far(ta, pb[3], h2, rel)) mask |= 1u;
+            if (!boxes_far(ta, pb[4], h2, rel)) mask |= 2u;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                if (!boxes_far(box_union(pb[i], pb[(i + 1) % 3]), bb, h2, rel)) mask |= 1u << (2 + i);
+        } else {
+            type = 2;
+            mask = 1u;  // bond-bond: the leaf boxes are the feature boxes
         }
-        bool status = false;
-        // warp-uniform feature loop: every lane runs test f on its own pair
-        const int nf_max = __reduce_max_sync(0xffffffffu, nfeat);
-        for (int f = 0; f < nf_max; ++f) {
-            if (f >= nfeat) continue;
-            int sl[4];
-            bool edge;
-            if (type == 0) {
+        n_box += __popc(mask);
+        if (MOVING) {
+            // coplanarity classifier on the box survivors
+            unsigned todo = mask;
+            while (todo) {
+                const int f = __ffs(todo) - 1;
+                todo &= todo - 1;
+                int sl[4];
+                if (type == 0) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) sl[q] = MOVING ? c_feat_tt_moving[f][q] : c_feat_tt_static[f][q];
-                edge = f >= 6;
-            } else if (type == 1) {
+                    for (int q = 0; q < 4; ++q) sl[q] = c_feat_tt_moving[f][q];
+                } else if (type == 1) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) sl[q] = c_feat_tb[f][q];
-                edge = f >= 2;
-            } else {
-                sl[0] = 0; sl[1] = 1; sl[2] = 3; sl[3] = 4;
-                edge = true;
+                    for (int q = 0; q < 4; ++q) sl[q] = c_feat_tb[f][q];
+                } else {
+                    sl[0] = 0; sl[1] = 1; sl[2] = 3; sl[3] = 4;
+                }
+                Quad q;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int sidx = sl[i];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        q.xo[i][d] = s_x[3 * sidx + d][tid];
+                        q.av[i][d] = s_v[MOVING ? 3 * sidx + d : 0][tid];
+                    }
+                }
+                double ca, cb, cc, cd;
+                coplanar_coeffs(q, ca, cb, cc, cd);
+                if (!coplanar_maybe(ca, cb, cc, cd, P.dt)) mask &= ~(1u << f);
             }
-            Quad q;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int s = sl[i];
-                q.id[i] = s_id[s][tid];
-                q.flags[i] = s_fb[s][tid];
-                q.xo[i][0] = s_x[3 * s][tid]; q.xo[i][1] = s_x[3 * s + 1][tid]; q.xo[i][2] = s_x[3 * s + 2][tid];
-                q.av[i][0] = s_v[3 * s][tid]; q.av[i][1] = s_v[3 * s + 1][tid]; q.av[i][2] = s_v[3 * s + 2][tid];
-                q.body[i] = 0;
-            }
-            if ((q.flags[0] & 3) && (q.flags[1] & 3) && (q.flags[2] & 3) && (q.flags[3] & 3)) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) q.body[i] = __ldg(vbody + q.id[i]);
-            }
-            const unsigned long long key = ((unsigned long long)(unsigned)pr.x << 34) | ((unsigned long long)(unsigned)pr.y << 4) |
-                                           (unsigned long long)f;
-            if (feature_test<MOVING>(P, E, q, key, edge, h)) status = true;
         }
-        if (status) ++n_true;
+        const int n = __popc(mask);
+        if (n == 0) continue;
+        unsigned long long slot = reserve(&counters[CTR_FEATS], n);
+        while (mask) {
+            const int f = __ffs(mask) - 1;
+            mask &= mask - 1;
+            if ((long long)slot < cap_feats) feats[slot] = (unsigned)pi | ((unsigned)f << 28);
+            ++slot;
+        }
     }
-    for (int o = 16; o > 0; o >>= 1) n_true += __shfl_xor_sync(0xffffffffu, n_true, o);
-    if ((tid & 31) == 0 && n_true) atomicAdd(&E.counters[CTR_TRUE], n_true);
+    for (int o = 16; o > 0; o >>= 1) n_box += __shfl_xor_sync(0xffffffffu, n_box, o);
+    if ((tid & 31) == 0 && n_box) atomicAdd(&counters[CTR_BOXSURV], n_box);
+}
+
+// Stage 2: one surviving feature test per thread.
+template <bool MOVING>
+__global__ void __launch_bounds__(FEAT_THREADS, 4)
+k_features(const unsigned* __restrict__ feats, long long cap_feats, const int2* __restrict__ pairs, const int4* __restrict__ elem,
+           const Vec4* __restrict__ xo, const Vec4* __restrict__ av, const uint8_t* __restrict__ vflags,
+           const int* __restrict__ vbody, NarrowParams P, Emit E, unsigned* __restrict__ pair_hit)
+{
+    long long n = (long long)E.counters[CTR_FEATS];
+    if (n > cap_feats) n = cap_feats;
+    const double h = MOVING ? P.eps : P.thickness;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const unsigned w = __ldg(feats + t);
+        const unsigned pi = w & 0x0fffffffu;
+        const int f = (int)(w >> 28);
+        const int2 pr = __ldg(pairs + pi);
+        const int4 A = __ldg(elem + pr.x), B = __ldg(elem + pr.y);
+        const int ids[6] = {A.x, A.y, A.z, B.x, B.y, B.z};
+        int sl[4];
+        bool edge;
+        if (A.z >= 0 && B.z >= 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sl[q] = MOVING ? c_feat_tt_moving[f][q] : c_feat_tt_static[f][q];
+            edge = f >= 6;
+        } else if (A.z >= 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sl[q] = c_feat_tb[f][q];
+            edge = f >= 2;
+        } else {
+            sl[0] = 0; sl[1] = 1; sl[2] = 3; sl[3] = 4;
+            edge = true;
+        }
+        Quad q;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int id = ids[0];
+#pragma unroll
+            for (int s = 1; s < 6; ++s) id = sl[i] == s ? ids[s] : id;
+            q.id[i] = id;
+            const Vec4 x = ldg_vec4(xo + id), v = ldg_vec4(av + id);
+            q.xo[i][0] = x.x; q.xo[i][1] = x.y; q.xo[i][2] = x.z;
+            q.av[i][0] = v.x; q.av[i][1] = v.y; q.av[i][2] = v.z;
+            q.flags[i] = __ldg(vflags + id);
+            q.body[i] = 0;
+        }
+        if ((q.flags[0] & 3) && (q.flags[1] & 3) && (q.flags[2] & 3) && (q.flags[3] & 3)) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q.body[i] = __ldg(vbody + q.id[i]);
+        }
+        const unsigned long long key = ((unsigned long long)(unsigned)pr.x << 34) | ((unsigned long long)(unsigned)pr.y << 4) |
+                                       (unsigned long long)f;
+        if (feature_test<MOVING>(P, E, q, key, edge, h)) atomicOr(pair_hit + (pi >> 5), 1u << (pi & 31));
+    }
+}
+
+// number of pairs for which isProximity / isCollision returned true (the tree's `count`, AABB.cpp:296-297)
+__global__ void k_count_true(const unsigned* __restrict__ pair_hit, long long n_words, unsigned long long* counters)
+{
+    unsigned long long c = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (long long)gridDim.x * blockDim.x)
+        c += __popc(pair_hit[i]);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&counters[CTR_TRUE], c);
 }
 
 // ------------------------------------------------------------------ context
@@ -181,6 +348,7 @@ struct clsn_ctx {
     bool tree_built = false;
     // pass buffers
     DevBuf<int2> pairs, dbg_cand;
+    DevBuf<unsigned> feats, pair_hit;
     DevBuf<PointRec> prec;
     DevBuf<BodyRec> brec;
     DevBuf<Contact> contacts;
@@ -280,7 +448,7 @@ extern "C" void clsn_destroy(clsn_ctx* c)
     c->xo.release(); c->xn.release(); c->av.release(); c->has.release(); c->imp_rg.release(); c->cnt_rg.release();
     c->stage.release(); c->code.release(); c->code_sorted.release(); c->idx.release(); c->leaf_elem.release();
     c->leaf_parent.release(); c->flags.release(); c->nodes.release(); c->lbox.release(); c->bounds.release();
-    c->cub_tmp.release(); c->pairs.release(); c->dbg_cand.release(); c->prec.release(); c->brec.release();
+    c->cub_tmp.release(); c->pairs.release(); c->dbg_cand.release(); c->feats.release(); c->pair_hit.release(); c->prec.release(); c->brec.release();
     c->contacts.release(); c->cnt.release(); c->offs.release(); c->fill.release(); c->perm.release();
     c->perm_sorted.release(); c->skey.release(); c->counters.release(); c->acc_imp.release(); c->acc_fric.release();
     c->rigid.release();
@@ -375,6 +543,8 @@ extern "C" int clsn_set_topology(clsn_ctx* c, int V, int T, const int32_t* tri_i
     CK(c->cub_tmp.reserve((tmp1 > tmp2 ? tmp1 : tmp2) + 256));
     CK(cudaMemset(c->cnt.p, 0, ((size_t)V + 1) * sizeof(int)));
     if (c->pairs.n == 0) CK(c->pairs.reserve((size_t)16 * n1 + 1024));
+    if (c->feats.n == 0) CK(c->feats.reserve((size_t)64 * n1 + 1024));
+    CK(c->pair_hit.reserve(c->pairs.n / 32 + 2));
     if (c->prec.n == 0) CK(c->prec.reserve((size_t)8 * n1 + 1024));
     CK(c->perm.reserve(c->prec.n)); CK(c->perm_sorted.reserve(c->prec.n)); CK(c->skey.reserve(c->prec.n));
     if (c->brec.n == 0) CK(c->brec.reserve(4096));
@@ -508,7 +678,7 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
     const int q_lo = (int)((long long)N * c->rank / c->nranks), q_hi = (int)((long long)N * (c->rank + 1) / c->nranks);
     for (int attempt = 0; attempt < 8; ++attempt) {
         CK(cudaMemsetAsync(c->counters.p, 0, CTR_ERROR * sizeof(unsigned long long), c->stream));  // keep CTR_ERROR
-        CK(cudaMemsetAsync(c->counters.p + CTR_DBG_CAND, 0, sizeof(unsigned long long), c->stream));
+        CK(cudaMemsetAsync(c->counters.p + CTR_DBG_CAND, 0, 3 * sizeof(unsigned long long), c->stream));  // + CTR_FEATS, CTR_BOXSURV
         CK(cudaMemsetAsync(c->flags.p, 0, (size_t)N * sizeof(int), c->stream));
         CK(cudaMemsetAsync(c->cnt.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
         CK(cudaMemsetAsync(c->cnt_rg.p, 0, c->nbody * sizeof(int), c->stream));
@@ -533,21 +703,35 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
         E.counters = c->counters.p;
         E.cap_prec = (long long)c->prec.n; E.cap_brec = (long long)c->brec.n; E.cap_contacts = (long long)c->contacts.n;
         E.cnt = c->cnt.p; E.cnt_rg = c->cnt_rg.p; E.body_mass = c->body_mass.p;
-        const int grid = c->sm_count * 8;
-        if (moving)
-            k_narrow<true><<<grid, NARROW_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p,
-                                                                    c->vflags.p, c->vbody.p, P, E);
-        else
-            k_narrow<false><<<grid, NARROW_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p,
-                                                                     c->vflags.p, c->vbody.p, P, E);
+        if ((size_t)c->pairs.n >= (1ull << 28)) return fail(c, CLSN_E_NOMEM, "more than 2^28 pairs in one pass");
+        const long long hit_words = (long long)(c->pairs.n / 32 + 1);
+        CK(cudaMemsetAsync(c->pair_hit.p, 0, (size_t)hit_words * sizeof(unsigned), c->stream));
+        const int grid = c->sm_count * 16;
+        if (moving) {
+            k_cull<true><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p, P,
+                                                                c->feats.p, (long long)c->feats.n, c->counters.p);
+            k_features<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->pairs.p, c->elem.p, c->xo.p,
+                                                                    c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+        } else {
+            k_cull<false><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p, P,
+                                                                 c->feats.p, (long long)c->feats.n, c->counters.p);
+            k_features<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->pairs.p, c->elem.p, c->xo.p,
+                                                                     c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+        }
+        k_count_true<<<c->sm_count * 2, 256, 0, c->stream>>>(c->pair_hit.p, hit_words, c->counters.p);
         CK(cudaGetLastError());
-        c->launches += 1;
+        c->launches += 3;
         mark(c, PH_NARROW);
         CK(cudaMemcpyAsync(c->h_counters, c->counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         const unsigned long long* h = c->h_counters;
         bool redo = false;
-        if (h[CTR_PAIRS] > c->pairs.n) { CK(c->pairs.reserve((size_t)(h[CTR_PAIRS] * 5 / 4 + 1024))); redo = true; }
+        if (h[CTR_PAIRS] > c->pairs.n) {
+            CK(c->pairs.reserve((size_t)(h[CTR_PAIRS] * 5 / 4 + 1024)));
+            CK(c->pair_hit.reserve(c->pairs.n / 32 + 2));
+            redo = true;
+        }
+        if (h[CTR_FEATS] > c->feats.n) { CK(c->feats.reserve((size_t)(h[CTR_FEATS] * 5 / 4 + 1024))); redo = true; }
         if (h[CTR_PREC] > c->prec.n) {
             size_t want = (size_t)(h[CTR_PREC] * 5 / 4 + 1024);
             CK(c->prec.reserve(want)); CK(c->perm.reserve(want)); CK(c->perm_sorted.reserve(want)); CK(c->skey.reserve(want));
@@ -564,6 +748,8 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
             st->true_pairs = (int64_t)h[CTR_TRUE];
             st->contacts = (int64_t)h[CTR_CONTACTS];
             st->contributions = (int64_t)(h[CTR_PREC] + h[CTR_BREC]);
+            st->features = (int64_t)h[CTR_FEATS];
+            st->box_survivors = (int64_t)h[CTR_BOXSURV];
         }
         c->last_nprec = (long long)h[CTR_PREC];
         c->last_nbrec = (long long)h[CTR_BREC];

@@ -29,6 +29,13 @@
 
 namespace crm {
 
+// sin(j/16), cos(j/16), j = 0..13, as double-doubles.  A namespace-scope table (global memory on the
+// device, read through the L1) -- a function-local array would be rebuilt on the stack per call.
+#if defined(__CUDACC__)
+static __device__ const double d_sincos_tab[14][4] = {CRM_SINCOS_TABLE};
+#endif
+static const double h_sincos_tab[14][4] = {CRM_SINCOS_TABLE};
+
 struct dd {
     double hi, lo;
 };
@@ -81,9 +88,18 @@ CRM_HD dd neg(dd a) { return dd{-a.hi, -a.lo}; }
 
 // sin and cos of a double argument, |y| <= 6.5 (so that k*PIO2_1 is exact), as double-doubles.
 // The cubic only needs [-2pi/3, pi].
-CRM_HD void sincos_dd(double y, dd& sn, dd& cs)
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+static
+#endif
+void sincos_dd(double y, dd& sn, dd& cs)
 {
-    const double tab[14][4] = {CRM_SINCOS_TABLE};
+#if defined(__CUDA_ARCH__)
+    const double (*tab)[4] = d_sincos_tab;
+#else
+    const double (*tab)[4] = h_sincos_tab;
+#endif
     // y = k*pi/2 + r, |r| <= pi/4 (+ a hair); pi/2 carried to ~155 bits
     double k = rint(y * CRM_2_OVER_PI);
     dd r = two_sum(y, -(k * CRM_PIO2_1)); // k*PIO2_1 is exact (51-bit constant, |k| small)

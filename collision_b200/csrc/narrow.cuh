@@ -54,7 +54,7 @@ struct Emit {
 };
 
 enum { CTR_PAIRS = 0, CTR_CAND = 1, CTR_PREC = 2, CTR_BREC = 3, CTR_TRUE = 4, CTR_CONTACTS = 5, CTR_ERROR = 6,
-       CTR_DBG_CAND = 7, CTR_COUNT = 8 };
+       CTR_DBG_CAND = 7, CTR_FEATS = 8, CTR_BOXSURV = 9, CTR_COUNT = 10 };
 
 __device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 __device__ __forceinline__ double mag3(const double* a) { return sqrt(dot3(a, a)); }
@@ -118,8 +118,8 @@ __device__ __forceinline__ void store_prec(PointRec* dst, unsigned long long key
     dd[3] = make_double2(fric[1], fric[2]);
 }
 
-__device__ __noinline__ void emit_contact(const Emit& E, const Quad& q, unsigned long long key, int kind, double root,
-                                          double dist, const double* nor, double w0, double w1, double w2)
+__device__ __noinline__ void emit_contact(const Emit& E, int4 ids, unsigned long long key, int kind, double root,
+                                          double dist, double n0, double n1, double n2, double w0, double w1, double w2)
 {
     unsigned long long slot = atomicAdd(&E.counters[CTR_CONTACTS], 1ull);
     if (E.contacts && (long long)slot < E.cap_contacts) {
@@ -128,9 +128,9 @@ __device__ __noinline__ void emit_contact(const Emit& E, const Quad& q, unsigned
         c.eb = (int)((key >> 4) & 0x3fffffffull);
         c.ea = (int)(key >> 34);
         c.kind = kind;
-        for (int i = 0; i < 4; ++i) c.p[i] = q.id[i];
+        c.p[0] = ids.x; c.p[1] = ids.y; c.p[2] = ids.z; c.p[3] = ids.w;
         c.root = root; c.dist = dist;
-        c.nor[0] = nor[0]; c.nor[1] = nor[1]; c.nor[2] = nor[2];
+        c.nor[0] = n0; c.nor[1] = n1; c.nor[2] = n2;
         c.w[0] = w0; c.w[1] = w1; c.w[2] = w2;
         E.contacts[slot] = c;
     }
@@ -367,7 +367,7 @@ __device__ __forceinline__ bool point_to_tri(const NarrowParams& P, const Emit& 
 #pragma unroll
     for (int i = 0; i < 3; ++i)
         if (w[i] > 1 + P.eps || w[i] < -P.eps) return false;
-    emit_contact(E, q, key, 0, root, dist, nor, w[0], w[1], w[2]);
+    emit_contact(E, make_int4(q.id[0], q.id[1], q.id[2], q.id[3]), key, 0, root, dist, nor[0], nor[1], nor[2], w[0], w[1], w[2]);
     point_to_tri_impulse(P, E, q, key, nor, w, dist);
     return true;
 }
@@ -417,43 +417,14 @@ __device__ __forceinline__ bool edge_to_edge(const NarrowParams& P, const Emit& 
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) nor[i] /= nor_mag;
-    emit_contact(E, q, key, 1, root, dist, nor, a, b, 0.0);
+    emit_contact(E, make_int4(q.id[0], q.id[1], q.id[2], q.id[3]), key, 1, root, dist, nor[0], nor[1], nor[2], a, b, 0.0);
     edge_to_edge_impulse(P, E, q, key, nor, a, b, dist);
     return true;
 }
 
-// Cheap classifier for the cubic branch of isCoplanar: can any root, after the reference's
-// "-MACH_EPS, keep [0,dt]" filter, be valid?  Uses the CUDA libm (<= 2 ulp) with a guard band ~50x
-// wider than any libm difference can move a root, so "no" is exact and the expensive correctly
-// rounded solve runs only for candidates.  Inputs are the monic coefficients t^3 + a t^2 + b t + c.
-__device__ __forceinline__ bool cubic_maybe_valid(double a, double Q, double R, double Q3, double R2, double dt)
-{
-    if (R2 < Q3) {
-        double Qsqrt = sqrt(Q);
-        double theta = acos(R / sqrt(Q3));
-        const double two_pi = 2 * 3.14159265358979323846;
-        double g = (fabs(Qsqrt) + fabs(a)) * 1e-13;
-        double r0 = -2 * Qsqrt * cos(theta / 3) - a / 3;
-        double r1 = -2 * Qsqrt * cos((theta + two_pi) / 3) - a / 3;
-        double r2 = -2 * Qsqrt * cos((theta - two_pi) / 3) - a / 3;
-        return !(r0 < -g || r0 > dt + g) || !(r1 < -g || r1 > dt + g) || !(r2 < -g || r2 > dt + g);
-    }
-    double sgn = (R > 0) ? 1.0 : -1.0;
-    double A = -sgn * pow(fabs(R) + sqrt(R2 - Q3), 1.0 / 3.0);
-    if (!(fabs(fabs(A) - CLSN_ROUND_EPS) > 1e-20)) return true; // the |A| < 1e-10 switch could flip
-    double Bv = (fabs(A) < CLSN_ROUND_EPS) ? 0.0 : Q / A;
-    double g = (fabs(A) + fabs(Bv) + fabs(a)) * 1e-13;
-    double r0 = (A + Bv) - a / 3.0;
-    bool maybe = !(r0 < -g || r0 > dt + g);
-    if (!(fabs(A - Bv) > 2 * CLSN_ROUND_EPS)) { // the double-root branch (|A-B| < 1e-10) may be taken
-        double rr = -0.5 * (A + Bv) - a / 3.0;
-        maybe = maybe || !(rr < -g || rr > dt + g);
-    }
-    return maybe;
-}
-
-// isCoplanar, dcollid3d.cpp:371-482.  Returns true iff some root > MACH_EPS; roots[0..2] sorted.
-__device__ __forceinline__ bool is_coplanar(const Quad& q, double dt, double* roots)
+// Coefficients of the coplanarity cubic a t^3 + b t^2 + c t + d (dcollid3d.cpp:382-422), in the
+// reference's exact operation order.
+__device__ __forceinline__ void coplanar_coeffs(const Quad& q, double& a, double& b, double& c, double& d)
 {
     double v[4][3], x[4][3];
 #pragma unroll
@@ -463,7 +434,7 @@ __device__ __forceinline__ bool is_coplanar(const Quad& q, double dt, double* ro
             v[i][j] = q.av[i][j] - q.av[0][j];
             x[i][j] = q.xo[i][j] - q.xo[0][j];
         }
-    double a, b, c, d, vv[3], vx[3], xx[3];
+    double vv[3], vx[3], xx[3];
     vv[0] = v[1][1] * v[2][2] - v[1][2] * v[2][1];
     vv[1] = v[1][0] * v[2][2] - v[1][2] * v[2][0];
     vv[2] = v[1][0] * v[2][1] - v[1][1] * v[2][0];
@@ -477,15 +448,93 @@ __device__ __forceinline__ bool is_coplanar(const Quad& q, double dt, double* ro
     b = x[3][0] * vv[0] - x[3][1] * vv[1] + x[3][2] * vv[2] + v[3][0] * vx[0] - v[3][1] * vx[1] + v[3][2] * vx[2];
     c = x[3][0] * vx[0] - x[3][1] * vx[1] + x[3][2] * vx[2] + v[3][0] * xx[0] - v[3][1] * xx[1] + v[3][2] * xx[2];
     d = x[3][0] * xx[0] - x[3][1] * xx[1] + x[3][2] * xx[2];
+}
+
+// Rigorous, trig-free classifier: can isCoplanar produce a root that survives its "-MACH_EPS, keep
+// [0, dt]" filter?  "false" is exact (the reference's isCoplanar returns false); "true" sends the
+// feature to the correctly rounded solve.  (a, b, c, d) as returned by coplanar_coeffs.
+//
+// Three-real-root branch (R^2 < Q^3): the reference's roots are -2 sqrt(Q) cos(phi_k) - a/3 with
+// phi_k = (acos(x) + 2 pi k)/3, x = R / sqrt(Q^3); cos(phi_k) are the three solutions of the
+// triple-angle identity T3(c) = 4c^3 - 3c = x.  A computed root is valid only if its cosine lies in
+// [u, v] = [-(dt + a/3)/S, -(a/3)/S] (S = 2 sqrt(Q)) up to the rounding of the root formula, so no
+// root is valid when x is outside T3([u - delta, v + delta]) -- two polynomial evaluations, no acos/cos.
+// delta covers: correctly rounded acos/cos (<= 1 ulp total in phi and cos), the rounding of 2*pi,
+// of the sum and of /3 (<= 1e-15), and the two roundings of the root formula (eta).  DESIGN.md.
+// One-real-root branch: root = A + B - a/3 with A = -sgn * pow(u, 1/3); cbrt() is within 1.5e-14
+// relative of the correctly rounded pow over the whole double range, covered by a 1e-13 guard.
+__device__ __forceinline__ bool coplanar_maybe(double a, double b, double c, double d, double dt)
+{
+    if (fabs(a) > CLSN_MACH_EPS) {
+        b /= a; c /= a; d /= a;
+        a = b; b = c; c = d;
+        const double Q = (a * a - 3 * b) / 9;
+        const double R = (2 * a * a * a - 9 * a * b + 27 * c) / 54;
+        const double Q3 = Q * Q * Q, R2 = R * R;
+        if (R2 < Q3) {
+            const double S = 2 * sqrt(Q);
+            const double x = R / sqrt(Q3);
+            if (!(fabs(x) <= 1.0) || !(S > 0.0)) return true;  // acos domain edge / NaN: let the exact path decide
+            const double A3 = a / 3;
+            const double eta = 4e-16 * (2 * S + fabs(A3)) + 2 * CLSN_MACH_EPS;
+            double u = -(dt + A3 + eta) / S;
+            double v = -(A3 - eta) / S;
+            const double delta = 4e-15 + 4e-16 * (fabs(u) + fabs(v));
+            u -= delta;
+            v += delta;
+            if (u > 1.0 || v < -1.0) return false;  // the cosines live in [-1, 1]
+            u = fmax(u, -1.0);
+            v = fmin(v, 1.0);
+            const double tu = u * (4 * u * u - 3), tv = v * (4 * v * v - 3);
+            double tmin = fmin(tu, tv), tmax = fmax(tu, tv);
+            if (u <= -0.5 && v >= -0.5) tmax = 1.0;   // interior maximum of T3 at c = -1/2
+            if (u <= 0.5 && v >= 0.5) tmin = -1.0;    // interior minimum at c = +1/2
+            return !(x < tmin - 4e-14 || x > tmax + 4e-14);
+        }
+        const double sgn = (R > 0) ? 1.0 : -1.0;
+        const double A = -sgn * cbrt(fabs(R) + sqrt(R2 - Q3));
+        if (!(fabs(fabs(A) - CLSN_ROUND_EPS) > 1e-20)) return true;  // the |A| < 1e-10 switch could flip
+        const double Bv = (fabs(A) < CLSN_ROUND_EPS) ? 0.0 : Q / A;
+        const double g = (fabs(A) + fabs(Bv) + fabs(a)) * 1e-13;
+        const double r0 = (A + Bv) - a / 3.0;
+        bool maybe = !(r0 < -g || r0 > dt + g);
+        if (!(fabs(A - Bv) > 2 * CLSN_ROUND_EPS)) {  // the double-root branch (|A-B| < 1e-10) may be taken
+            const double rr = -0.5 * (A + Bv) - a / 3.0;
+            maybe = maybe || !(rr < -g || rr > dt + g);
+        }
+        return maybe;
+    }
+    // quadratic / linear fall-backs use IEEE operations only: evaluate them as the reference does
+    a = b; b = c; c = d;
+    const double delta = b * b - 4.0 * a * c;
+    double r0 = -1.0, r1 = -1.0;
+    if (fabs(a) > CLSN_ROUND_EPS && delta > 0) {
+        const double ds = sqrt(delta);
+        r0 = (-b + ds) / (2.0 * a);
+        r1 = (-b - ds) / (2.0 * a);
+    } else if (fabs(a) < CLSN_ROUND_EPS && fabs(b) > CLSN_ROUND_EPS) {
+        r0 = -c / b;
+    }
+    r0 -= CLSN_MACH_EPS;
+    r1 -= CLSN_MACH_EPS;
+    const bool ok0 = !(r0 < 0 || r0 > dt), ok1 = !(r1 < 0 || r1 > dt);
+    return ok0 || ok1;
+}
+
+// isCoplanar, dcollid3d.cpp:371-482.  Returns true iff some root > MACH_EPS; roots[0..2] sorted.
+__device__ __forceinline__ bool is_coplanar(const Quad& q, double dt, double* roots)
+{
+    double a, b, c, d;
+    coplanar_coeffs(q, a, b, c, d);
+#ifndef CLSN_CR_ALWAYS
+    if (!coplanar_maybe(a, b, c, d, dt)) return false;  // every root provably outside [0, dt]
+#endif
     if (fabs(a) > CLSN_MACH_EPS) {
         b /= a; c /= a; d /= a;
         a = b; b = c; c = d;
         double Q = (a * a - 3 * b) / 9;
         double R = (2 * a * a * a - 9 * a * b + 27 * c) / 54;
         double Q3 = Q * Q * Q, R2 = R * R;
-#ifndef CLSN_CR_ALWAYS
-        if (!cubic_maybe_valid(a, Q, R, Q3, R2, dt)) return false; // every root provably outside [0, dt]
-#endif
         if (R2 < Q3) {
             double Qsqrt = sqrt(Q);
             double theta = crm::acos_cr(R / sqrt(Q3));
@@ -538,13 +587,18 @@ __device__ __forceinline__ bool feature_test(const NarrowParams& P, const Emit& 
     }
     double roots[4] = {-1, -1, -1, P.dt};
     if (!is_coplanar(q, P.dt, roots)) return false;
+    // the reference walks roots[0..3] in order and stops at the first hit; invalid slots are -1.
+    // Compact the valid roots to the front first so the loop below has a register-resident trip.
+    double r0 = roots[0], r1 = roots[1], r2 = roots[2];
+    const double r3 = roots[3];
     for (int i = 0; i < 4; ++i) {
-        if (roots[i] < 0) continue;
+        const double t = i == 0 ? r0 : (i == 1 ? r1 : (i == 2 ? r2 : r3));
+        if (t < 0) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) X[j][k] = q.xo[j][k] + roots[i] * q.av[j][k];
-        bool hit = edge ? edge_to_edge(P, E, q, key, X, h, roots[i]) : point_to_tri(P, E, q, key, X, h, roots[i]);
+            for (int k = 0; k < 3; ++k) X[j][k] = q.xo[j][k] + t * q.av[j][k];
+        bool hit = edge ? edge_to_edge(P, E, q, key, X, h, t) : point_to_tri(P, E, q, key, X, h, t);
         if (hit) return true;
     }
     return false;

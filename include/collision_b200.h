@@ -62,6 +62,8 @@ typedef struct {
     int64_t true_pairs;     /* pairs for which isProximity/isCollision returned true (tree count)  */
     int64_t contacts;       /* feature tests that fired                                            */
     int64_t contributions;  /* per-point impulse records reduced                                   */
+    int64_t features;       /* feature tests evaluated (survived box cull and, CCD, the classifier) */
+    int64_t box_survivors;  /* feature tests that survived the swept-box cull                       */
 } clsn_pass_stats;
 
 typedef struct {
