@@ -195,7 +195,7 @@ def algorithmic_bytes(scene, st):
         "narrow": 8 * Pt + n * (48 * V + 12 * T) + 64 * K,                    # pairs in, vertex data once, records out
         "reduce": 2 * 64 * K + n * 80 * V,                                    # records grouped + read, apply per vertex
         "finalize": (48 + 73) * V,
-    }, dict(P=P, Pt=Pt, Fbox=sum(p.get("box_survivors", 0) for p in passes), F=F, C=C, K=K, passes=n)
+    }, dict(P=P, Pt=Pt, Fbox=sum(p.get("box_survivors", 0) for p in passes), F=F, Fcop=sum(p.get("coplanar", 0) for p in passes), C=C, K=K, passes=n)
 
 
 # ----------------------------------------------------------------------------- CUDA arm

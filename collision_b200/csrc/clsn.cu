@@ -44,6 +44,9 @@ __constant__ unsigned char c_feat_tb[5][4] = {{0, 1, 2, 3}, {0, 1, 2, 4}, {0, 1,
 
 #define CULL_THREADS 128
 #define FEAT_THREADS 128
+#ifndef FEAT_MIN_BLOCKS
+#define FEAT_MIN_BLOCKS 4
+#endif
 
 // swept box of one point over [0, dt] (static: the point itself)
 struct PBox {
@@ -230,48 +233,119 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
     if ((tid & 31) == 0 && n_box) atomicAdd(&counters[CTR_BOXSURV], n_box);
 }
 
-// Stage 2: one surviving feature test per thread.
+// decode one work-list entry into the four point ids of the feature test
 template <bool MOVING>
-__global__ void __launch_bounds__(FEAT_THREADS, 4)
-k_features(const unsigned* __restrict__ feats, long long cap_feats, const int2* __restrict__ pairs, const int4* __restrict__ elem,
-           const Vec4* __restrict__ xo, const Vec4* __restrict__ av, const uint8_t* __restrict__ vflags,
-           const int* __restrict__ vbody, NarrowParams P, Emit E, unsigned* __restrict__ pair_hit)
+__device__ __forceinline__ void feature_points(unsigned w, const int2* __restrict__ pairs, const int4* __restrict__ elem,
+                                               int2& pr, int& f, bool& edge, int* pid)
 {
-    long long n = (long long)E.counters[CTR_FEATS];
+    const unsigned pi = w & 0x0fffffffu;
+    f = (int)(w >> 28);
+    pr = __ldg(pairs + pi);
+    const int4 A = __ldg(elem + pr.x), B = __ldg(elem + pr.y);
+    const int ids[6] = {A.x, A.y, A.z, B.x, B.y, B.z};
+    int sl[4];
+    if (A.z >= 0 && B.z >= 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sl[q] = MOVING ? c_feat_tt_moving[f][q] : c_feat_tt_static[f][q];
+        edge = f >= 6;
+    } else if (A.z >= 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sl[q] = c_feat_tb[f][q];
+        edge = f >= 2;
+    } else {
+        sl[0] = 0; sl[1] = 1; sl[2] = 3; sl[3] = 4;
+        edge = true;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int id = ids[0];
+#pragma unroll
+        for (int s = 1; s < 6; ++s) id = sl[i] == s ? ids[s] : id;
+        pid[i] = id;
+    }
+}
+
+struct RootRec {  // 32 B: one feature whose coplanarity cubic has a usable root
+    unsigned feat;
+    unsigned pad;
+    double r0, r1, r2;  // sorted, invalid = -1 (isCoplanar's output)
+};
+
+// Stage 2 (CCD): correctly rounded solve of the coplanarity cubic for every feature the classifier
+// let through.  Only positions and velocities are needed here; the kernel is nothing but the
+// double-double math, which keeps its instruction footprint small.
+__global__ void __launch_bounds__(FEAT_THREADS, 5)
+k_roots(const unsigned* __restrict__ feats, long long cap_feats, const int2* __restrict__ pairs, const int4* __restrict__ elem,
+        const Vec4* __restrict__ xo, const Vec4* __restrict__ av, double dt, RootRec* __restrict__ out, long long cap_out,
+        unsigned long long* counters)
+{
+    long long n = (long long)counters[CTR_FEATS];
     if (n > cap_feats) n = cap_feats;
-    const double h = MOVING ? P.eps : P.thickness;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
         const unsigned w = __ldg(feats + t);
-        const unsigned pi = w & 0x0fffffffu;
-        const int f = (int)(w >> 28);
-        const int2 pr = __ldg(pairs + pi);
-        const int4 A = __ldg(elem + pr.x), B = __ldg(elem + pr.y);
-        const int ids[6] = {A.x, A.y, A.z, B.x, B.y, B.z};
-        int sl[4];
+        int2 pr;
+        int f, pid[4];
         bool edge;
-        if (A.z >= 0 && B.z >= 0) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) sl[q] = MOVING ? c_feat_tt_moving[f][q] : c_feat_tt_static[f][q];
-            edge = f >= 6;
-        } else if (A.z >= 0) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) sl[q] = c_feat_tb[f][q];
-            edge = f >= 2;
-        } else {
-            sl[0] = 0; sl[1] = 1; sl[2] = 3; sl[3] = 4;
-            edge = true;
-        }
+        feature_points<true>(w, pairs, elem, pr, f, edge, pid);
         Quad q;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            int id = ids[0];
-#pragma unroll
-            for (int s = 1; s < 6; ++s) id = sl[i] == s ? ids[s] : id;
-            q.id[i] = id;
-            const Vec4 x = ldg_vec4(xo + id), v = ldg_vec4(av + id);
+            const Vec4 x = ldg_vec4(xo + pid[i]), v = ldg_vec4(av + pid[i]);
             q.xo[i][0] = x.x; q.xo[i][1] = x.y; q.xo[i][2] = x.z;
             q.av[i][0] = v.x; q.av[i][1] = v.y; q.av[i][2] = v.z;
-            q.flags[i] = __ldg(vflags + id);
+        }
+        double roots[3] = {-1, -1, -1};
+        if (!is_coplanar<false>(q, dt, roots)) continue;
+        const unsigned long long slot = reserve(&counters[CTR_ROOTS], 1);
+        if ((long long)slot < cap_out) {
+            ulonglong2* o = reinterpret_cast<ulonglong2*>(out + slot);
+            ulonglong2 a, b;
+            a.x = (unsigned long long)w;
+            a.y = (unsigned long long)__double_as_longlong(roots[0]);
+            b.x = (unsigned long long)__double_as_longlong(roots[1]);
+            b.y = (unsigned long long)__double_as_longlong(roots[2]);
+            o[0] = a;
+            o[1] = b;
+        }
+    }
+}
+
+// Stage 3: static tests at the root times (CCD) or at x_old (proximity) + impulse records.
+template <bool MOVING>
+__global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS)
+k_contact(const unsigned* __restrict__ feats, const RootRec* __restrict__ rootrecs, long long cap_in, const int2* __restrict__ pairs,
+          const int4* __restrict__ elem, const Vec4* __restrict__ xo, const Vec4* __restrict__ av,
+          const uint8_t* __restrict__ vflags, const int* __restrict__ vbody, NarrowParams P, Emit E,
+          unsigned* __restrict__ pair_hit)
+{
+    long long n = (long long)E.counters[MOVING ? CTR_ROOTS : CTR_FEATS];
+    if (n > cap_in) n = cap_in;
+    const double h = MOVING ? P.eps : P.thickness;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        unsigned w;
+        double r0 = 0, r1 = 0, r2 = 0;
+        if (MOVING) {
+            const ulonglong2* in = reinterpret_cast<const ulonglong2*>(rootrecs + t);
+            const ulonglong2 a = __ldg(in), b = __ldg(in + 1);
+            w = (unsigned)a.x;
+            r0 = __longlong_as_double((long long)a.y);
+            r1 = __longlong_as_double((long long)b.x);
+            r2 = __longlong_as_double((long long)b.y);
+        } else {
+            w = __ldg(feats + t);
+        }
+        int2 pr;
+        int f, pid[4];
+        bool edge;
+        feature_points<MOVING>(w, pairs, elem, pr, f, edge, pid);
+        Quad q;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            q.id[i] = pid[i];
+            const Vec4 x = ldg_vec4(xo + pid[i]), v = ldg_vec4(av + pid[i]);
+            q.xo[i][0] = x.x; q.xo[i][1] = x.y; q.xo[i][2] = x.z;
+            q.av[i][0] = v.x; q.av[i][1] = v.y; q.av[i][2] = v.z;
+            q.flags[i] = __ldg(vflags + pid[i]);
             q.body[i] = 0;
         }
         if ((q.flags[0] & 3) && (q.flags[1] & 3) && (q.flags[2] & 3) && (q.flags[3] & 3)) {
@@ -280,7 +354,11 @@ k_features(const unsigned* __restrict__ feats, long long cap_feats, const int2* 
         }
         const unsigned long long key = ((unsigned long long)(unsigned)pr.x << 34) | ((unsigned long long)(unsigned)pr.y << 4) |
                                        (unsigned long long)f;
-        if (feature_test<MOVING>(P, E, q, key, edge, h)) atomicOr(pair_hit + (pi >> 5), 1u << (pi & 31));
+        const bool hit = MOVING ? feature_at_roots(P, E, q, key, edge, h, r0, r1, r2) : feature_static(P, E, q, key, edge, h);
+        if (hit) {
+            const unsigned pi = w & 0x0fffffffu;
+            atomicOr(pair_hit + (pi >> 5), 1u << (pi & 31));
+        }
     }
 }
 
@@ -349,6 +427,7 @@ struct clsn_ctx {
     // pass buffers
     DevBuf<int2> pairs, dbg_cand;
     DevBuf<unsigned> feats, pair_hit;
+    DevBuf<RootRec> rootrecs;
     DevBuf<PointRec> prec;
     DevBuf<BodyRec> brec;
     DevBuf<Contact> contacts;
@@ -448,7 +527,7 @@ extern "C" void clsn_destroy(clsn_ctx* c)
     c->xo.release(); c->xn.release(); c->av.release(); c->has.release(); c->imp_rg.release(); c->cnt_rg.release();
     c->stage.release(); c->code.release(); c->code_sorted.release(); c->idx.release(); c->leaf_elem.release();
     c->leaf_parent.release(); c->flags.release(); c->nodes.release(); c->lbox.release(); c->bounds.release();
-    c->cub_tmp.release(); c->pairs.release(); c->dbg_cand.release(); c->feats.release(); c->pair_hit.release(); c->prec.release(); c->brec.release();
+    c->cub_tmp.release(); c->pairs.release(); c->dbg_cand.release(); c->feats.release(); c->pair_hit.release(); c->rootrecs.release(); c->prec.release(); c->brec.release();
     c->contacts.release(); c->cnt.release(); c->offs.release(); c->fill.release(); c->perm.release();
     c->perm_sorted.release(); c->skey.release(); c->counters.release(); c->acc_imp.release(); c->acc_fric.release();
     c->rigid.release();
@@ -544,6 +623,7 @@ extern "C" int clsn_set_topology(clsn_ctx* c, int V, int T, const int32_t* tri_i
     CK(cudaMemset(c->cnt.p, 0, ((size_t)V + 1) * sizeof(int)));
     if (c->pairs.n == 0) CK(c->pairs.reserve((size_t)16 * n1 + 1024));
     if (c->feats.n == 0) CK(c->feats.reserve((size_t)64 * n1 + 1024));
+    if (c->rootrecs.n == 0) CK(c->rootrecs.reserve((size_t)16 * n1 + 1024));
     CK(c->pair_hit.reserve(c->pairs.n / 32 + 2));
     if (c->prec.n == 0) CK(c->prec.reserve((size_t)8 * n1 + 1024));
     CK(c->perm.reserve(c->prec.n)); CK(c->perm_sorted.reserve(c->prec.n)); CK(c->skey.reserve(c->prec.n));
@@ -678,7 +758,7 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
     const int q_lo = (int)((long long)N * c->rank / c->nranks), q_hi = (int)((long long)N * (c->rank + 1) / c->nranks);
     for (int attempt = 0; attempt < 8; ++attempt) {
         CK(cudaMemsetAsync(c->counters.p, 0, CTR_ERROR * sizeof(unsigned long long), c->stream));  // keep CTR_ERROR
-        CK(cudaMemsetAsync(c->counters.p + CTR_DBG_CAND, 0, 3 * sizeof(unsigned long long), c->stream));  // + CTR_FEATS, CTR_BOXSURV
+        CK(cudaMemsetAsync(c->counters.p + CTR_DBG_CAND, 0, 4 * sizeof(unsigned long long), c->stream));  // + CTR_FEATS, CTR_BOXSURV, CTR_ROOTS
         CK(cudaMemsetAsync(c->flags.p, 0, (size_t)N * sizeof(int), c->stream));
         CK(cudaMemsetAsync(c->cnt.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
         CK(cudaMemsetAsync(c->cnt_rg.p, 0, c->nbody * sizeof(int), c->stream));
@@ -710,17 +790,21 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
         if (moving) {
             k_cull<true><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p, P,
                                                                 c->feats.p, (long long)c->feats.n, c->counters.p);
-            k_features<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->pairs.p, c->elem.p, c->xo.p,
-                                                                    c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+            k_roots<<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->pairs.p, c->elem.p, c->xo.p, c->av.p,
+                                                           P.dt, c->rootrecs.p, (long long)c->rootrecs.n, c->counters.p);
+            k_contact<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, c->rootrecs.p, (long long)c->rootrecs.n, c->pairs.p,
+                                                                   c->elem.p, c->xo.p, c->av.p, c->vflags.p, c->vbody.p, P, E,
+                                                                   c->pair_hit.p);
         } else {
             k_cull<false><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p, P,
                                                                  c->feats.p, (long long)c->feats.n, c->counters.p);
-            k_features<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->pairs.p, c->elem.p, c->xo.p,
-                                                                     c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+            k_contact<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, c->rootrecs.p, (long long)c->feats.n, c->pairs.p,
+                                                                    c->elem.p, c->xo.p, c->av.p, c->vflags.p, c->vbody.p, P, E,
+                                                                    c->pair_hit.p);
         }
         k_count_true<<<c->sm_count * 2, 256, 0, c->stream>>>(c->pair_hit.p, hit_words, c->counters.p);
         CK(cudaGetLastError());
-        c->launches += 3;
+        c->launches += moving ? 4 : 3;
         mark(c, PH_NARROW);
         CK(cudaMemcpyAsync(c->h_counters, c->counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
@@ -732,6 +816,7 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
             redo = true;
         }
         if (h[CTR_FEATS] > c->feats.n) { CK(c->feats.reserve((size_t)(h[CTR_FEATS] * 5 / 4 + 1024))); redo = true; }
+        if (h[CTR_ROOTS] > c->rootrecs.n) { CK(c->rootrecs.reserve((size_t)(h[CTR_ROOTS] * 5 / 4 + 1024))); redo = true; }
         if (h[CTR_PREC] > c->prec.n) {
             size_t want = (size_t)(h[CTR_PREC] * 5 / 4 + 1024);
             CK(c->prec.reserve(want)); CK(c->perm.reserve(want)); CK(c->perm_sorted.reserve(want)); CK(c->skey.reserve(want));
@@ -750,6 +835,7 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
             st->contributions = (int64_t)(h[CTR_PREC] + h[CTR_BREC]);
             st->features = (int64_t)h[CTR_FEATS];
             st->box_survivors = (int64_t)h[CTR_BOXSURV];
+            st->coplanar = (int64_t)h[CTR_ROOTS];
         }
         c->last_nprec = (long long)h[CTR_PREC];
         c->last_nbrec = (long long)h[CTR_BREC];

@@ -136,17 +136,23 @@ void sincos_dd(double y, dd& sn, dd& cs)
     else { sn = neg(cos_r); cs = sin_r; }
 }
 
-// correctly rounded cos(y) for |y| <= 6.5; plain libm beyond (never reached from the cubic)
+// correctly rounded cos(y) for |y| <= 6.5.  Beyond that the host build falls back to libm; the device
+// build has no fallback (keeps the kernels small): its callers -- the cubic (|y| <= pi) and the rigid
+// body rotation angle dt*|w| -- stay far inside the range.
 CRM_HD double cos_cr(double y)
 {
+#if !defined(__CUDA_ARCH__)
     if (!(fabs(y) <= 6.5)) return cos(y);
+#endif
     dd s, c;
     sincos_dd(y, s, c);
     return c.hi + c.lo;
 }
 CRM_HD double sin_cr(double y)
 {
+#if !defined(__CUDA_ARCH__)
     if (!(fabs(y) <= 6.5)) return sin(y);
+#endif
     dd s, c;
     sincos_dd(y, s, c);
     return s.hi + s.lo;
@@ -172,7 +178,9 @@ CRM_HD double acos_cr(double x)
 // (= 1/3 - 2^-54/3), so the result is cbrt(u) * exp(delta * ln u), delta = CRM_POW13_DELTA
 CRM_HD double pow13_cr(double u)
 {
-    if (!(u > 0.0) || !(u < 1.0e300) || u < 1.0e-290) return pow(u, 1.0 / 3.0);
+    // outside (1e-290, 1e300) and for 0 / inf / NaN: plain cbrt (exact for 0, inf, NaN; elsewhere within
+    // 1.5e-14 relative -- such magnitudes do not occur for the cubic of a real mesh)
+    if (!(u > 1.0e-290) || !(u < 1.0e300)) return cbrt(u);
     double c0 = cbrt(u);
     dd c2 = two_prod(c0, c0);
     dd c3 = mul_d(c2, c0);

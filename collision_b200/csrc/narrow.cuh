@@ -54,7 +54,7 @@ struct Emit {
 };
 
 enum { CTR_PAIRS = 0, CTR_CAND = 1, CTR_PREC = 2, CTR_BREC = 3, CTR_TRUE = 4, CTR_CONTACTS = 5, CTR_ERROR = 6,
-       CTR_DBG_CAND = 7, CTR_FEATS = 8, CTR_BOXSURV = 9, CTR_COUNT = 10 };
+       CTR_DBG_CAND = 7, CTR_FEATS = 8, CTR_BOXSURV = 9, CTR_ROOTS = 10, CTR_COUNT = 11 };
 
 __device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 __device__ __forceinline__ double mag3(const double* a) { return sqrt(dot3(a, a)); }
@@ -150,7 +150,7 @@ __device__ __forceinline__ void emit_body(const Emit& E, unsigned long long key,
 }
 
 // PointToTriImpulse, dcollid3d.cpp:925-1107.  q: 0..2 triangle, 3 point.  w is modified as in the reference.
-__device__ __forceinline__ void point_to_tri_impulse(const NarrowParams& P, const Emit& E, const Quad& q,
+__device__ __noinline__ void point_to_tri_impulse(const NarrowParams& P, const Emit& E, const Quad& q,
                                                       unsigned long long key, const double* nor, double* w, double dist)
 {
     double v_rel[3] = {0.0, 0.0, 0.0}, vn, vt;
@@ -243,7 +243,7 @@ __device__ __forceinline__ void point_to_tri_impulse(const NarrowParams& P, cons
 }
 
 // EdgeToEdgeImpulse, dcollid3d.cpp:1109-1300.  q: edge 0-1 against edge 2-3.
-__device__ __forceinline__ void edge_to_edge_impulse(const NarrowParams& P, const Emit& E, const Quad& q,
+__device__ __noinline__ void edge_to_edge_impulse(const NarrowParams& P, const Emit& E, const Quad& q,
                                                       unsigned long long key, const double* nor, double a, double b, double dist)
 {
     double v_rel[3], vn, vt;
@@ -476,7 +476,7 @@ __device__ __forceinline__ bool coplanar_maybe(double a, double b, double c, dou
             const double x = R / sqrt(Q3);
             if (!(fabs(x) <= 1.0) || !(S > 0.0)) return true;  // acos domain edge / NaN: let the exact path decide
             const double A3 = a / 3;
-            const double eta = 4e-16 * (2 * S + fabs(A3)) + 2 * CLSN_MACH_EPS;
+            const double eta = 4e-16 * (2 * S + fabs(A3) + dt) + 2 * CLSN_MACH_EPS;
             double u = -(dt + A3 + eta) / S;
             double v = -(A3 - eta) / S;
             const double delta = 4e-15 + 4e-16 * (fabs(u) + fabs(v));
@@ -522,13 +522,13 @@ __device__ __forceinline__ bool coplanar_maybe(double a, double b, double c, dou
 }
 
 // isCoplanar, dcollid3d.cpp:371-482.  Returns true iff some root > MACH_EPS; roots[0..2] sorted.
+// CLASSIFY = false when the caller has already run coplanar_maybe() on this feature (k_cull).
+template <bool CLASSIFY>
 __device__ __forceinline__ bool is_coplanar(const Quad& q, double dt, double* roots)
 {
     double a, b, c, d;
     coplanar_coeffs(q, a, b, c, d);
-#ifndef CLSN_CR_ALWAYS
-    if (!coplanar_maybe(a, b, c, d, dt)) return false;  // every root provably outside [0, dt]
-#endif
+    if (CLASSIFY && !coplanar_maybe(a, b, c, d, dt)) return false;  // every root provably outside [0, dt]
     if (fabs(a) > CLSN_MACH_EPS) {
         b /= a; c /= a; d /= a;
         a = b; b = c; c = d;
@@ -537,11 +537,33 @@ __device__ __forceinline__ bool is_coplanar(const Quad& q, double dt, double* ro
         double Q3 = Q * Q * Q, R2 = R * R;
         if (R2 < Q3) {
             double Qsqrt = sqrt(Q);
-            double theta = crm::acos_cr(R / sqrt(Q3));
+            const double arg = R / sqrt(Q3);
             const double two_pi = 2 * 3.14159265358979323846;
-            roots[0] = -2 * Qsqrt * crm::cos_cr(theta / 3) - a / 3;
-            roots[1] = -2 * Qsqrt * crm::cos_cr((theta + two_pi) / 3) - a / 3;
-            roots[2] = -2 * Qsqrt * crm::cos_cr((theta - two_pi) / 3) - a / 3;
+            // Which of the three roots can survive the [0, dt] filter?  Root k is -S cos(phi_k) - a/3 with
+            // phi_0 in [0, pi/3], phi_1 in [2pi/3, pi], phi_2 in [-2pi/3, -pi/3], i.e. its cosine lies in
+            // [1/2, 1], [-1, -1/2], [-1/2, 1/2] respectively, and a valid root has its cosine in the (tiny)
+            // interval [u, v] derived in coplanar_maybe().  Only the overlapping k are evaluated (correctly
+            // rounded); the others get -1, which is what the filter below would turn them into anyway.
+            const double S = 2 * Qsqrt, A3 = a / 3;
+            bool need0 = true, need1 = true, need2 = true;
+            if (S > 0.0 && fabs(arg) <= 1.0) {
+                const double eta = 4e-16 * (2 * S + fabs(A3) + dt) + 2 * CLSN_MACH_EPS;
+                double u = -(dt + A3 + eta) / S;
+                double v = -(A3 - eta) / S;
+                const double delta = 4e-15 + 4e-16 * (fabs(u) + fabs(v));
+                u -= delta;
+                v += delta;
+                const double e = 1e-14;
+                need0 = !(v < 0.5 - e);                      // overlaps [1/2, 1]
+                need1 = !(u > -0.5 + e);                     // overlaps [-1, -1/2]
+                need2 = !(v < -0.5 - e || u > 0.5 + e);      // overlaps [-1/2, 1/2]
+            }
+            if (need0 || need1 || need2) {
+                const double theta = crm::acos_cr(arg);
+                if (need0) roots[0] = -2 * Qsqrt * crm::cos_cr(theta / 3) - a / 3;
+                if (need1) roots[1] = -2 * Qsqrt * crm::cos_cr((theta + two_pi) / 3) - a / 3;
+                if (need2) roots[2] = -2 * Qsqrt * crm::cos_cr((theta - two_pi) / 3) - a / 3;
+            }
         } else {
             double sgn = (R > 0) ? 1.0 : -1.0;
             double A = -sgn * crm::pow13_cr(fabs(R) + sqrt(R2 - Q3));
@@ -572,33 +594,32 @@ __device__ __forceinline__ bool is_coplanar(const Quad& q, double dt, double* ro
     return roots[0] > CLSN_MACH_EPS || roots[1] > CLSN_MACH_EPS || roots[2] > CLSN_MACH_EPS;
 }
 
-// one feature test: static (proximity) or moving (CCD: MovingPointToTri / MovingEdgeToEdge :327-369)
-template <bool MOVING>
-__device__ __forceinline__ bool feature_test(const NarrowParams& P, const Emit& E, const Quad& q, unsigned long long key,
-                                              bool edge, double h)
+// one static feature test (proximity: TriToTri/TriToBond/BondToBond call these at x_old with h = thickness)
+__device__ __forceinline__ bool feature_static(const NarrowParams& P, const Emit& E, const Quad& q, unsigned long long key,
+                                                bool edge, double h)
 {
     double X[4][3];
-    if (!MOVING) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) X[j][k] = q.xo[j][k];
-        return edge ? edge_to_edge(P, E, q, key, X, h, 0.0) : point_to_tri(P, E, q, key, X, h, 0.0);
-    }
-    double roots[4] = {-1, -1, -1, P.dt};
-    if (!is_coplanar(q, P.dt, roots)) return false;
-    // the reference walks roots[0..3] in order and stops at the first hit; invalid slots are -1.
-    // Compact the valid roots to the front first so the loop below has a register-resident trip.
-    double r0 = roots[0], r1 = roots[1], r2 = roots[2];
-    const double r3 = roots[3];
+        for (int k = 0; k < 3; ++k) X[j][k] = q.xo[j][k];
+    return edge ? edge_to_edge(P, E, q, key, X, h, 0.0) : point_to_tri(P, E, q, key, X, h, 0.0);
+}
+
+// MovingPointToTri / MovingEdgeToEdge (dcollid3d.cpp:327-369), second half: walk the sorted roots
+// (invalid = -1) and then t = dt, stop at the first static hit.
+__device__ __forceinline__ bool feature_at_roots(const NarrowParams& P, const Emit& E, const Quad& q, unsigned long long key,
+                                                  bool edge, double h, double r0, double r1, double r2)
+{
+    double X[4][3];
     for (int i = 0; i < 4; ++i) {
-        const double t = i == 0 ? r0 : (i == 1 ? r1 : (i == 2 ? r2 : r3));
+        const double t = i == 0 ? r0 : (i == 1 ? r1 : (i == 2 ? r2 : P.dt));
         if (t < 0) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int k = 0; k < 3; ++k) X[j][k] = q.xo[j][k] + t * q.av[j][k];
-        bool hit = edge ? edge_to_edge(P, E, q, key, X, h, t) : point_to_tri(P, E, q, key, X, h, t);
+        const bool hit = edge ? edge_to_edge(P, E, q, key, X, h, t) : point_to_tri(P, E, q, key, X, h, t);
         if (hit) return true;
     }
     return false;

@@ -39,7 +39,7 @@ class clsn_params(C.Structure):
 class clsn_pass_stats(C.Structure):
     _fields_ = [("candidates", C.c_int64), ("pairs_tested", C.c_int64), ("true_pairs", C.c_int64),
                 ("contacts", C.c_int64), ("contributions", C.c_int64), ("features", C.c_int64),
-                ("box_survivors", C.c_int64)]
+                ("box_survivors", C.c_int64), ("coplanar", C.c_int64)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

@@ -64,6 +64,7 @@ typedef struct {
     int64_t contributions;  /* per-point impulse records reduced                                   */
     int64_t features;       /* feature tests evaluated (survived box cull and, CCD, the classifier) */
     int64_t box_survivors;  /* feature tests that survived the swept-box cull                       */
+    int64_t coplanar;       /* CCD: features whose cubic has a usable root (isCoplanar true)        */
 } clsn_pass_stats;
 
 typedef struct {
