@@ -47,40 +47,20 @@ __constant__ unsigned char c_feat_tb[5][4] = {{0, 1, 2, 3}, {0, 1, 2, 4}, {0, 1,
 #ifndef FEAT_MIN_BLOCKS
 #define FEAT_MIN_BLOCKS 4
 #endif
+#define CULL_ROW 19  // doubles per staged pair row (18 used): odd stride -> conflict-free column access
 
-// swept box of one point over [0, dt] (static: the point itself)
-struct PBox {
-    double lo[3], hi[3];
+// Conservative FP32 swept box of one point over [0, dt] (static: the point itself): rounded outward,
+// so every position the narrow phase can evaluate lies inside.
+struct FBox {
+    float lo[3], hi[3];
 };
-
-template <bool MOVING>
-__device__ __forceinline__ PBox point_box(const Vec4* __restrict__ xo, const Vec4* __restrict__ av, int id, double dt)
+__device__ __forceinline__ FBox fbox_union(const FBox& a, const FBox& b)
 {
-    PBox b;
-    const Vec4 x = ldg_vec4(xo + id);
-    const double x0[3] = {x.x, x.y, x.z};
-    if (MOVING) {
-        const Vec4 v = ldg_vec4(av + id);
-        const double vv[3] = {v.x, v.y, v.z};
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            const double x1 = x0[d] + vv[d] * dt;
-            b.lo[d] = fmin(x0[d], x1);
-            b.hi[d] = fmax(x0[d], x1);
-        }
-    } else {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) b.lo[d] = b.hi[d] = x0[d];
-    }
-    return b;
-}
-__device__ __forceinline__ PBox box_union(const PBox& a, const PBox& b)
-{
-    PBox r;
+    FBox r;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        r.lo[d] = fmin(a.lo[d], b.lo[d]);
-        r.hi[d] = fmax(a.hi[d], b.hi[d]);
+        r.lo[d] = fminf(a.lo[d], b.lo[d]);
+        r.hi[d] = fmaxf(a.hi[d], b.hi[d]);
     }
     return r;
 }
@@ -90,147 +70,176 @@ __device__ __forceinline__ PBox box_union(const PBox& a, const PBox& b)
 // Every position used by the test lies in the swept boxes, so a gap larger than
 // margin = 2h + (3 eps + 1e-2) * extent along any axis means "the reference returns false" -- the
 // 1e-2 * extent term dwarfs every rounding error of the test itself (DESIGN.md "exact culls").
-__device__ __forceinline__ bool boxes_far(const PBox& a, const PBox& b, double h2, double rel)
+// FP32 with directed rounding: the gap is rounded down, the margin up, so the cull stays conservative.
+__device__ __forceinline__ bool boxes_far(const FBox& a, const FBox& b, float h2, float rel)
 {
     bool far = false;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        const double ext = fmax(a.hi[d] - a.lo[d], b.hi[d] - b.lo[d]);
-        const double m = h2 + rel * ext;
-        far = far || (a.lo[d] - b.hi[d] > m) || (b.lo[d] - a.hi[d] > m);
+        const float ext = fmaxf(__fsub_ru(a.hi[d], a.lo[d]), __fsub_ru(b.hi[d], b.lo[d]));
+        const float m = __fmaf_ru(rel, ext, h2);
+        far = far || (__fsub_rd(a.lo[d], b.hi[d]) > m) || (__fsub_rd(b.lo[d], a.hi[d]) > m);
     }
     return far;
 }
 
-// Stage 1: one pair per thread.  (i) feature-level swept-box culling; (ii) CCD only: coefficients of
-// the coplanarity cubic + the trig-free classifier coplanar_maybe().  Features that can still fire
-// are appended to the work list as (pair index | feature << 28).  The six points of the pair are
-// staged in shared memory ([slot*3+c][thread], conflict-free) so that the per-feature gather of
-// four points is a shared-memory read with a runtime slot index instead of a register shuffle.
+// Stage 1: (i) one pair per thread: feature-level swept-box culling -> 15-bit mask; (ii) CCD only: the
+// box survivors of the warp's 32 pairs are pooled and dealt out evenly to the 32 lanes (the six points
+// of every pair are staged in shared memory, one row per pair), each lane computes the coefficients of
+// the coplanarity cubic and runs the trig-free classifier coplanar_maybe().  Features that can still
+// fire are appended to the work list as (pair index | feature << 28).
 template <bool MOVING>
-__global__ void __launch_bounds__(CULL_THREADS, 3)
+__global__ void __launch_bounds__(CULL_THREADS, 4)
 k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restrict__ elem, const Vec4* __restrict__ xo,
        const Vec4* __restrict__ av, NarrowParams P, unsigned* __restrict__ feats, long long cap_feats,
        unsigned long long* counters)
 {
-    __shared__ double s_x[18][CULL_THREADS];
-    __shared__ double s_v[MOVING ? 18 : 1][CULL_THREADS];
-    const int tid = threadIdx.x;
+    __shared__ double s_x[CULL_THREADS][CULL_ROW];
+    __shared__ double s_v[MOVING ? CULL_THREADS : 1][CULL_ROW];
+    __shared__ unsigned s_mask[CULL_THREADS];
+    __shared__ int s_pref[CULL_THREADS];
+    const int tid = threadIdx.x, lane = tid & 31, wb = tid & ~31;
     long long n_pairs = (long long)counters[CTR_PAIRS];
     if (n_pairs > cap_pairs) n_pairs = cap_pairs;
-    const double h2 = 2.0 * (MOVING ? P.eps : P.thickness);
-    const double rel = 3.0 * P.eps + 1e-2;
+    const float h2 = __double2float_ru(2.0 * (MOVING ? P.eps : P.thickness));
+    const float rel = __double2float_ru(3.0 * P.eps + 1e-2);
     unsigned long long n_box = 0;
-    for (long long pi = (long long)blockIdx.x * blockDim.x + tid; pi < n_pairs; pi += (long long)gridDim.x * blockDim.x) {
-        const int2 pr = __ldg(pairs + pi);
-        const int4 A = __ldg(elem + pr.x), B = __ldg(elem + pr.y);
-        const int ids[6] = {A.x, A.y, A.z, B.x, B.y, B.z};
-        PBox pb[6];
-#pragma unroll
-        for (int s = 0; s < 6; ++s) {
-            if (ids[s] < 0) { pb[s] = pb[0]; continue; }
-            const Vec4 x = ldg_vec4(xo + ids[s]);
-            const double x0[3] = {x.x, x.y, x.z};
-            s_x[3 * s][tid] = x.x; s_x[3 * s + 1][tid] = x.y; s_x[3 * s + 2][tid] = x.z;
-            if (MOVING) {
-                const Vec4 v = ldg_vec4(av + ids[s]);
-                const double vv[3] = {v.x, v.y, v.z};
-                s_v[3 * s][tid] = v.x; s_v[3 * s + 1][tid] = v.y; s_v[3 * s + 2][tid] = v.z;
-#pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    const double x1 = x0[d] + vv[d] * P.dt;
-                    pb[s].lo[d] = fmin(x0[d], x1);
-                    pb[s].hi[d] = fmax(x0[d], x1);
-                }
-            } else {
-#pragma unroll
-                for (int d = 0; d < 3; ++d) pb[s].lo[d] = pb[s].hi[d] = x0[d];
-            }
-        }
+    for (long long base = (long long)blockIdx.x * CULL_THREADS; base < n_pairs; base += (long long)gridDim.x * CULL_THREADS) {
+        const long long pi = base + tid;
         unsigned mask = 0;
-        int type = 0;
-        if (A.z >= 0 && B.z >= 0) {
-            PBox ea[3], eb[3];
+        if (pi < n_pairs) {
+            const int2 pr = __ldg(pairs + pi);
+            const int4 A = __ldg(elem + pr.x), B = __ldg(elem + pr.y);
+            const int ids[6] = {A.x, A.y, A.z, B.x, B.y, B.z};
+            FBox pb[6];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                ea[i] = box_union(pb[i], pb[(i + 1) % 3]);
-                eb[i] = box_union(pb[3 + i], pb[3 + (i + 1) % 3]);
-            }
-            const PBox ta = box_union(ea[0], pb[2]), tb = box_union(eb[0], pb[5]);
-            // point-triangle features 0..5 (order differs between proximity and CCD, see c_feat_tt_*)
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const bool a_tri_b_pt = !boxes_far(ta, pb[3 + i], h2, rel);  // triangle a, vertex b_i
-                const bool b_tri_a_pt = !boxes_far(tb, pb[i], h2, rel);      // triangle b, vertex a_i
+            for (int s = 0; s < 6; ++s) {
+                if (ids[s] < 0) { pb[s] = pb[0]; continue; }
+                const Vec4 x = ldg_vec4(xo + ids[s]);
+                const double x0[3] = {x.x, x.y, x.z};
+                s_x[tid][3 * s] = x.x; s_x[tid][3 * s + 1] = x.y; s_x[tid][3 * s + 2] = x.z;
                 if (MOVING) {
-                    mask |= (a_tri_b_pt ? 1u : 0u) << i;
-                    mask |= (b_tri_a_pt ? 1u : 0u) << (3 + i);
-                } else {
-                    mask |= (b_tri_a_pt ? 1u : 0u) << i;
-                    mask |= (a_tri_b_pt ? 1u : 0u) << (3 + i);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j)
-                    if (!boxes_far(ea[i], eb[j], h2, rel)) mask |= 1u << (6 + 3 * i + j);
-        } else if (A.z >= 0) {
-            type = 1;  // triangle a, bond b: features 0,1 = vertex, 2..4 = tri edge x bond
-            const PBox ta = box_union(box_union(pb[0], pb[1]), pb[2]), bb = box_union(pb[3], pb[4]);
-            if (!boxes_far(ta, pb[3], h2, rel)) mask |= 1u;
-            if (!boxes_far(ta, pb[4], h2, rel)) mask |= 2u;
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-                if (!boxes_far(box_union(pb[i], pb[(i + 1) % 3]), bb, h2, rel)) mask |= 1u << (2 + i);
-        } else {
-            type = 2;
-            mask = 1u;  // bond-bond: the leaf boxes are the feature boxes
-        }
-        n_box += __popc(mask);
-        if (MOVING) {
-            // coplanarity classifier on the box survivors
-            unsigned todo = mask;
-            while (todo) {
-                const int f = __ffs(todo) - 1;
-                todo &= todo - 1;
-                int sl[4];
-                if (type == 0) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) sl[q] = c_feat_tt_moving[f][q];
-                } else if (type == 1) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) sl[q] = c_feat_tb[f][q];
-                } else {
-                    sl[0] = 0; sl[1] = 1; sl[2] = 3; sl[3] = 4;
-                }
-                Quad q;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int sidx = sl[i];
+                    const Vec4 v = ldg_vec4(av + ids[s]);
+                    const double vv[3] = {v.x, v.y, v.z};
+                    s_v[tid][3 * s] = v.x; s_v[tid][3 * s + 1] = v.y; s_v[tid][3 * s + 2] = v.z;
 #pragma unroll
                     for (int d = 0; d < 3; ++d) {
-                        q.xo[i][d] = s_x[3 * sidx + d][tid];
-                        q.av[i][d] = s_v[MOVING ? 3 * sidx + d : 0][tid];
+                        const double x1 = x0[d] + vv[d] * P.dt;
+                        pb[s].lo[d] = __double2float_rd(fmin(x0[d], x1));
+                        pb[s].hi[d] = __double2float_ru(fmax(x0[d], x1));
+                    }
+                } else {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        pb[s].lo[d] = __double2float_rd(x0[d]);
+                        pb[s].hi[d] = __double2float_ru(x0[d]);
                     }
                 }
-                double ca, cb, cc, cd;
-                coplanar_coeffs(q, ca, cb, cc, cd);
-                if (!coplanar_maybe(ca, cb, cc, cd, P.dt)) mask &= ~(1u << f);
+            }
+            if (A.z >= 0 && B.z >= 0) {
+                FBox ea[3], eb[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    ea[i] = fbox_union(pb[i], pb[(i + 1) % 3]);
+                    eb[i] = fbox_union(pb[3 + i], pb[3 + (i + 1) % 3]);
+                }
+                const FBox ta = fbox_union(ea[0], pb[2]), tb = fbox_union(eb[0], pb[5]);
+                // point-triangle features 0..5 (order differs between proximity and CCD, see c_feat_tt_*)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const bool a_tri_b_pt = !boxes_far(ta, pb[3 + i], h2, rel);  // triangle a, vertex b_i
+                    const bool b_tri_a_pt = !boxes_far(tb, pb[i], h2, rel);      // triangle b, vertex a_i
+                    if (MOVING) {
+                        mask |= (a_tri_b_pt ? 1u : 0u) << i;
+                        mask |= (b_tri_a_pt ? 1u : 0u) << (3 + i);
+                    } else {
+                        mask |= (b_tri_a_pt ? 1u : 0u) << i;
+                        mask |= (a_tri_b_pt ? 1u : 0u) << (3 + i);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        if (!boxes_far(ea[i], eb[j], h2, rel)) mask |= 1u << (6 + 3 * i + j);
+            } else if (A.z >= 0) {
+                // triangle a, bond b: features 0,1 = vertex, 2..4 = tri edge x bond
+                const FBox ta = fbox_union(fbox_union(pb[0], pb[1]), pb[2]), bb = fbox_union(pb[3], pb[4]);
+                if (!boxes_far(ta, pb[3], h2, rel)) mask |= 1u;
+                if (!boxes_far(ta, pb[4], h2, rel)) mask |= 2u;
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    if (!boxes_far(fbox_union(pb[i], pb[(i + 1) % 3]), bb, h2, rel)) mask |= 1u << (2 + i);
+                mask |= 1u << 16;  // pair type 1
+            } else {
+                mask = 1u | (2u << 16);  // bond-bond (type 2): the leaf boxes are the feature boxes
             }
         }
-        const int n = __popc(mask);
-        if (n == 0) continue;
-        unsigned long long slot = reserve(&counters[CTR_FEATS], n);
-        while (mask) {
-            const int f = __ffs(mask) - 1;
-            mask &= mask - 1;
-            if ((long long)slot < cap_feats) feats[slot] = (unsigned)pi | ((unsigned)f << 28);
-            ++slot;
+        // pool the warp's survivors: exclusive prefix of the per-pair counts
+        const int cnt = __popc(mask & 0x7fffu);
+        n_box += cnt;
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        s_mask[tid] = mask;
+        s_pref[tid] = incl - cnt;
+        __syncwarp();
+        for (int k0 = 0; k0 < total; k0 += 32) {
+            const int k = k0 + lane;
+            bool keep = false;
+            unsigned entry = 0;
+            if (k < total) {
+                // owner = last lane whose exclusive prefix is <= k
+                int o = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1)
+                    if (s_pref[wb + o + step] <= k) o += step;
+                const unsigned m = s_mask[wb + o];
+                const int f = __fns(m & 0x7fffu, 0, k - s_pref[wb + o] + 1);
+                entry = (unsigned)(base + wb + o) | ((unsigned)f << 28);
+                keep = true;
+                if (MOVING) {
+                    const int type = (int)(m >> 16);
+                    int sl[4];
+                    if (type == 0) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) sl[q] = c_feat_tt_moving[f][q];
+                    } else if (type == 1) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) sl[q] = c_feat_tb[f][q];
+                    } else {
+                        sl[0] = 0; sl[1] = 1; sl[2] = 3; sl[3] = 4;
+                    }
+                    Quad q;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            q.xo[i][d] = s_x[wb + o][3 * sl[i] + d];
+                            q.av[i][d] = s_v[MOVING ? wb + o : 0][3 * sl[i] + d];
+                        }
+                    double ca, cb, cc, cd;
+                    coplanar_coeffs(q, ca, cb, cc, cd);
+                    keep = coplanar_maybe(ca, cb, cc, cd, P.dt);
+                }
+            }
+            const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+            if (ballot) {
+                unsigned long long slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(&counters[CTR_FEATS], (unsigned long long)__popc(ballot));
+                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                const unsigned long long slot = slot0 + __popc(ballot & ((1u << lane) - 1u));
+                if (keep && (long long)slot < cap_feats) feats[slot] = entry;
+            }
+        }
+        __syncwarp();
     }
     for (int o = 16; o > 0; o >>= 1) n_box += __shfl_xor_sync(0xffffffffu, n_box, o);
-    if ((tid & 31) == 0 && n_box) atomicAdd(&counters[CTR_BOXSURV], n_box);
+    if (lane == 0 && n_box) atomicAdd(&counters[CTR_BOXSURV], n_box);
 }
 
 // decode one work-list entry into the four point ids of the feature test
