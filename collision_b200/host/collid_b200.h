@@ -1,0 +1,214 @@
+// collid_b200.h -- C++ host mirror of the reference's collid.h for the GPU collision step.
+//
+// Same class and adapter names, same public methods and call sequence as antdvid/Collision
+// (collid.h:43-92 CD_HSE/CD_TRI/CD_BOND/CD_POINT, :128-244 CollisionSolver/CollisionSolver3d):
+//
+//     CollisionSolver3d* solver = new CollisionSolver3d();
+//     ... each step:
+//     solver->assembleFromInterface(intfc, dt);      // dcollid3d.cpp:12-52
+//     solver->setFrictionConstant(0.0);              // static setters, dcollid.cpp:57-89
+//     solver->resolveCollision();                    // dcollid.cpp:317-362
+//
+// The mesh model below (POINT / TRI / BOND / SURFACE / CURVE / INTERFACE / STATE) carries exactly the
+// fields the reference's three hot-path sources touch in FronTier's structs; inside a FronTier tree
+// these definitions are replaced by <FronTier.h> + ifluid_state.h.  All mesh data stays
+// caller-owned and is mutated in place like the reference does (Coords, STATE::avgVel/vel/has_collsn,
+// POINT::vel).  The work itself is done by libcollision_b200.so through include/collision_b200.h;
+// there is no CPU implementation behind this class.
+#ifndef COLLID_B200_H_
+#define COLLID_B200_H_
+
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "collision_b200.h"
+
+namespace clsn_host {
+
+// ---- minimal FronTier-shaped mesh model ------------------------------------------------------
+struct POINT;
+struct UF {  // impact-zone union-find links (collid.h:22-27); the GPU path keeps its own lists
+    POINT* next_pt;
+    POINT* root;
+    POINT* tail;
+    int num_pts;
+};
+struct STATE {  // collid.h:29-39 + the rigid-body fields (dcollid.cpp:726-733, cdinit.cpp:192-204)
+    double vel[3];
+    double collsnImpulse[3];
+    double collsnImpulse_RG[3];
+    double friction[3];
+    double avgVel[3];
+    double x_old[3];
+    int collsn_num;
+    int collsn_num_RG;
+    bool has_collsn;
+    bool is_fixed;
+    bool is_movableRG;
+    UF impZone;
+};
+struct HYPER_SURF {
+    int wave_type;
+    int body_index;
+    double total_mass;
+    double center_of_mass[3];
+    double center_of_mass_velo[3];
+};
+struct POINT {
+    double coords[3];
+    long global_index;
+    STATE* state;  // left_state(p)
+    HYPER_SURF* hs;
+    double vel[3];
+};
+struct SURFACE;
+struct TRI {
+    POINT* pts[3];
+    TRI* next;
+    SURFACE* surf;
+    double side_length0[3];
+};
+struct SURFACE {
+    HYPER_SURF* hs;
+    TRI* first_tri;
+    bool is_bdry;
+};
+struct BOND {
+    POINT* start;
+    POINT* end;
+    BOND* next;
+    double length0;
+};
+struct CURVE {
+    BOND* first;
+    bool is_string;  // hsbdry_type(c) == STRING_HSBDRY
+    HYPER_SURF* hs;
+};
+struct INTERFACE {
+    std::vector<SURFACE*> surfaces;
+    std::vector<CURVE*> curves;
+    double L[3], U[3];  // table->rect_grid.L / U
+};
+
+// ---- element adapters (collid.h:43-92) --------------------------------------------------------
+class CD_HSE {
+public:
+    virtual double max_static_coord(int) = 0;
+    virtual double min_static_coord(int) = 0;
+    virtual double max_moving_coord(int, double) = 0;
+    virtual double min_moving_coord(int, double) = 0;
+    virtual POINT* Point_of_hse(int) const = 0;
+    virtual int num_pts() const = 0;
+    virtual ~CD_HSE() {}
+};
+class CD_TRI : public CD_HSE {
+public:
+    TRI* m_tri;
+    explicit CD_TRI(TRI* tri) : m_tri(tri) {}
+    double max_static_coord(int);
+    double min_static_coord(int);
+    double max_moving_coord(int, double);
+    double min_moving_coord(int, double);
+    POINT* Point_of_hse(int) const;
+    int num_pts() const { return 3; }
+};
+class CD_BOND : public CD_HSE {
+public:
+    BOND* m_bond;
+    int m_dim;
+    CD_BOND(BOND* bond, int dim) : m_bond(bond), m_dim(dim) {}
+    double max_static_coord(int);
+    double min_static_coord(int);
+    double max_moving_coord(int, double);
+    double min_moving_coord(int, double);
+    POINT* Point_of_hse(int) const;
+    int num_pts() const { return 2; }
+};
+// Declared but never defined in the reference (collid.h:82-92); given trivial bodies here.  Pairs that
+// involve a CD_POINT stay unsupported, as in the reference (dcollid.cpp:787-791).
+class CD_POINT : public CD_HSE {
+public:
+    POINT* m_point;
+    explicit CD_POINT(POINT* point) : m_point(point) {}
+    double max_static_coord(int);
+    double min_static_coord(int);
+    double max_moving_coord(int, double);
+    double min_moving_coord(int, double);
+    POINT* Point_of_hse(int) const;
+    int num_pts() const { return 1; }
+};
+
+// ---- solver (collid.h:128-244) ----------------------------------------------------------------
+class CollisionSolver {
+private:
+    static double s_eps, s_thickness, s_dt, s_m, s_k, s_lambda, s_cr;  // process-global, as in the reference
+    bool has_collision;
+    double Boundary[3][2];
+
+protected:
+    int m_dim;
+    std::vector<CD_HSE*> hseList;
+    clsn_ctx* m_ctx;
+    // gathered view of the mesh (rebuilt when the element list changes)
+    std::vector<POINT*> m_points;
+    std::unordered_map<POINT*, int> m_point_id;
+    std::vector<int32_t> m_tri, m_tri_surf, m_bond;
+    std::vector<uint8_t> m_flags;
+    std::vector<int32_t> m_body;
+    std::vector<double> m_body_mass;
+    std::vector<double> m_xold, m_xnew, m_xout, m_vel;
+    std::vector<uint8_t> m_has;
+    clsn_step_stats m_stats;
+    bool m_topology_dirty;
+    void clearHseList();
+    void gatherTopology(const INTERFACE*);
+    void fail(int rc, const char* where) const;
+
+public:
+    explicit CollisionSolver(int dim);
+    virtual ~CollisionSolver();
+    static void setRoundingTolerance(double);
+    static double getRoundingTolerance();
+    static void setFabricThickness(double);
+    static double getFabricThickness();
+    static void setTimeStepSize(double);
+    static double getTimeStepSize();
+    static void setSpringConstant(double);
+    static double getSpringConstant();
+    static void setFrictionConstant(double);
+    static double getFrictionConstant();
+    static void setPointMass(double);
+    static double getPointMass();
+    static void setRestitutionCoef(double);
+    static double getRestitutionCoef();
+    static bool getImpZoneStatus() { return false; }  // the impact-zone fail-safe is host-side and not part of this path
+
+    virtual void assembleFromInterface(const INTERFACE*, double dt) = 0;
+    virtual void createImpZoneForRG(const INTERFACE*) = 0;
+    bool isProximity(const CD_HSE*, const CD_HSE*);
+    bool isCollision(const CD_HSE*, const CD_HSE*);
+    void resolveCollision();
+    void recordOriginPosition();
+    void setDomainBoundary(double* L, double* U);
+    double getDomainBoundary(int dir, int side) { return Boundary[dir][side]; }
+    bool hasCollision() { return has_collision; }
+    const clsn_step_stats& lastStats() const { return m_stats; }
+    bool stillColliding() const { return m_stats.still_colliding != 0; }  // the reference would enter computeImpactZone
+    static void printDebugVariable() {}
+};
+
+class CollisionSolver3d : public CollisionSolver {
+public:
+    CollisionSolver3d() : CollisionSolver(3) {}
+    void assembleFromInterface(const INTERFACE*, double dt);
+    void createImpZoneForRG(const INTERFACE*) {}  // the rigid-body lists are rebuilt from topology by clsn_set_topology
+};
+
+bool isStaticRigidBody(const POINT*);
+bool isMovableRigidBody(const POINT*);
+bool isRigidBody(const POINT*);
+
+}  // namespace clsn_host
+#endif

@@ -1,0 +1,98 @@
+// Drives the C++ host mirror the way the reference's test.cpp drives CollisionSolver3d (test.cpp:96-107):
+// reads a flat scene file written by tests/test_gpu_host_cpp.py, builds the POINT/TRI/BOND mesh, runs
+// `steps` x { spring solver stand-in; assembleFromInterface; setFrictionConstant; resolveCollision },
+// writes final coords + vel.  Usage: host_check scene.bin out.bin steps
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "collid_b200.h"
+using namespace clsn_host;
+
+template <class T>
+static std::vector<T> rd(FILE* f, size_t n)
+{
+    std::vector<T> v(n);
+    if (n && fread(v.data(), sizeof(T), n, f) != n) { fprintf(stderr, "short read\n"); exit(2); }
+    return v;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 4) return 2;
+    FILE* f = fopen(argv[1], "rb");
+    if (!f) return 2;
+    int hdr[6];  // V T B n_surf n_curve nhs
+    if (fread(hdr, sizeof(int), 6, f) != 6) return 2;
+    const int V = hdr[0], T = hdr[1], B = hdr[2], NS = hdr[3], NC = hdr[4], NH = hdr[5];
+    auto par = rd<double>(f, 13);  // eps thickness k m lambda cr dt lo[3] hi[3]
+    auto x = rd<double>(f, 3 * (size_t)V), vel = rd<double>(f, 3 * (size_t)V);
+    auto tri = rd<int>(f, 3 * (size_t)T), tsurf = rd<int>(f, T), bond = rd<int>(f, 2 * (size_t)B), bcur = rd<int>(f, B);
+    auto kind = rd<int>(f, NH);
+    auto mass = rd<double>(f, NH);
+    auto flags = rd<unsigned char>(f, V);
+    auto vhs = rd<int>(f, V);
+    fclose(f);
+    const int steps = atoi(argv[3]);
+
+    std::vector<HYPER_SURF> hs(NH);
+    for (int i = 0; i < NH; ++i) { hs[i] = HYPER_SURF(); hs[i].wave_type = kind[i]; hs[i].body_index = i; hs[i].total_mass = mass[i]; }
+    std::vector<STATE> st(V);
+    std::vector<POINT> pt(V);
+    for (int v = 0; v < V; ++v) {
+        st[v] = STATE();
+        pt[v] = POINT();
+        pt[v].global_index = v; pt[v].state = &st[v]; pt[v].hs = &hs[vhs[v]];
+        st[v].is_fixed = flags[v] & 1; st[v].is_movableRG = (flags[v] & 2) != 0;
+        for (int j = 0; j < 3; ++j) { pt[v].coords[j] = x[3 * v + j]; st[v].x_old[j] = x[3 * v + j]; st[v].vel[j] = pt[v].vel[j] = vel[3 * v + j]; }
+    }
+    std::vector<SURFACE> surf(NS);
+    std::vector<TRI> tris(T);
+    std::vector<TRI*> last(NS, nullptr);
+    for (int s = 0; s < NS; ++s) { surf[s].hs = &hs[s]; surf[s].first_tri = nullptr; surf[s].is_bdry = false; }
+    for (int t = 0; t < T; ++t) {
+        for (int i = 0; i < 3; ++i) tris[t].pts[i] = &pt[tri[3 * t + i]];
+        tris[t].next = nullptr; tris[t].surf = &surf[tsurf[t]];
+        if (last[tsurf[t]]) last[tsurf[t]]->next = &tris[t]; else surf[tsurf[t]].first_tri = &tris[t];
+        last[tsurf[t]] = &tris[t];
+    }
+    std::vector<CURVE> cur(NC);
+    std::vector<BOND> bonds(B);
+    std::vector<BOND*> blast(NC, nullptr);
+    for (int c = 0; c < NC; ++c) { cur[c].first = nullptr; cur[c].is_string = true; cur[c].hs = &hs[NS + c]; }
+    for (int b = 0; b < B; ++b) {
+        bonds[b].start = &pt[bond[2 * b]]; bonds[b].end = &pt[bond[2 * b + 1]]; bonds[b].next = nullptr; bonds[b].length0 = 0;
+        if (blast[bcur[b]]) blast[bcur[b]]->next = &bonds[b]; else cur[bcur[b]].first = &bonds[b];
+        blast[bcur[b]] = &bonds[b];
+    }
+    INTERFACE intfc;
+    for (auto& s : surf) intfc.surfaces.push_back(&s);
+    for (auto& c : cur) intfc.curves.push_back(&c);
+    for (int i = 0; i < 3; ++i) { intfc.L[i] = par[7 + i]; intfc.U[i] = par[10 + i]; }
+
+    CollisionSolver3d* solver = new CollisionSolver3d();
+    CollisionSolver::setRoundingTolerance(par[0]);
+    CollisionSolver::setFabricThickness(par[1]);
+    CollisionSolver::setSpringConstant(par[2]);
+    CollisionSolver::setPointMass(par[3]);
+    CollisionSolver::setRestitutionCoef(par[5]);
+    const double dt = par[6];
+    for (int step = 0; step < steps; ++step) {
+        // FT_Propagate's point hook + dummySpringSolver (test.cpp:192-258)
+        for (int v = 0; v < V; ++v)
+            for (int j = 0; j < 3; ++j) {
+                st[v].x_old[j] = pt[v].coords[j];
+                pt[v].coords[j] = st[v].x_old[j] + dt * st[v].vel[j];
+            }
+        solver->assembleFromInterface(&intfc, dt);
+        CollisionSolver::setFrictionConstant(par[4]);
+        solver->resolveCollision();
+    }
+    FILE* o = fopen(argv[2], "wb");
+    for (int v = 0; v < V; ++v) fwrite(pt[v].coords, sizeof(double), 3, o);
+    for (int v = 0; v < V; ++v) fwrite(st[v].vel, sizeof(double), 3, o);
+    fclose(o);
+    printf("host_check: %d steps, has_collision=%d, ccd passes last step=%d\n", steps, (int)solver->hasCollision(), solver->lastStats().n_ccd_passes);
+    delete solver;
+    return 0;
+}

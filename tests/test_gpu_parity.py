@@ -117,3 +117,69 @@ def test_empty_and_tiny_inputs():
         gpu, orc = make_pair(sc)
         run_step_by_phases(gpu, orc, sc, sc.x.copy(), sc.vel.copy())
         gpu.close()
+
+
+def test_sliced_equals_whole():
+    """Multi-GPU decomposition on one device: two contexts each traverse half of the query leaves, their
+    record buffers are concatenated (what the NCCL all-gather does) and reduced -> bit-identical to the
+    unsliced run, pass after pass."""
+    import ctypes as C
+    import torch
+    from collision_b200.dist import BODY_RECORD_BYTES, POINT_RECORD_BYTES, _DevPtr
+
+    sc = scenes.mixed()
+    whole, _ = make_pair(sc)
+    parts = [make_pair(sc)[0] for _ in range(2)]
+    for g in [whole] + parts:
+        g.set_debug(False, False)
+    for r, g in enumerate(parts):
+        g.ctx.check(g.ctx.L.clsn_set_slice(g.ctx.h, r, 2))
+    dev = torch.device("cuda", 0)
+    x, vel = sc.x.copy(), sc.vel.copy()
+    n_rec = 0
+    for step in range(3):
+        xn = x + sc.dt * vel
+        for g in [whole] + parts:
+            g.upload(x, xn)
+            g.avg_velocity()
+        for ps in range(4):
+            mode = 0 if ps == 0 else 1
+            sw = whole.detect(mode)
+            bufs_p, bufs_b, n_true = [], [], 0
+            for g in parts:
+                g.detect(mode)
+                pp, pb = C.c_void_p(), C.c_void_p()
+                npr, nbr, nt = C.c_int64(), C.c_int64(), C.c_int64()
+                g.ctx.check(g.ctx.L.clsn_export_records(g.ctx.h, C.byref(pp), C.byref(npr), C.byref(pb), C.byref(nbr), C.byref(nt)))
+                nb_p, nb_b = npr.value * POINT_RECORD_BYTES, nbr.value * BODY_RECORD_BYTES
+                bufs_p.append(torch.as_tensor(_DevPtr(pp.value, nb_p), device=dev)[:nb_p].clone())
+                bufs_b.append(torch.as_tensor(_DevPtr(pb.value, nb_b), device=dev)[:nb_b].clone())
+                n_true += nt.value
+            allp, allb = torch.cat(bufs_p), torch.cat(bufs_b)
+            torch.cuda.synchronize()
+            assert n_true == sw["true_pairs"]
+            assert allp.numel() // POINT_RECORD_BYTES + allb.numel() // BODY_RECORD_BYTES == sw["contributions"]
+            n_rec += sw["contributions"]
+            for g in parts:
+                g.ctx.check(g.ctx.L.clsn_import_records(g.ctx.h, allp.data_ptr() if allp.numel() else None,
+                                                        allp.numel() // POINT_RECORD_BYTES,
+                                                        allb.data_ptr() if allb.numel() else None,
+                                                        allb.numel() // BODY_RECORD_BYTES))
+                g.apply(True)
+            whole.apply(True)
+            _, avw, hasw = whole.download()
+            for g in parts:
+                _, av, has = g.download()
+                assert same_bits(av, avw) and np.array_equal(has, hasw)
+        for g in [whole] + parts:
+            g.boundary()
+            g.final_position()
+        xw, avw, hasw = whole.download()
+        for g in parts:
+            xg, _, _ = g.download()
+            assert same_bits(xg, xw)
+        vel[hasw != 0] = avw[hasw != 0]
+        x = xw
+    assert n_rec > 0
+    for g in [whole] + parts:
+        g.close()
