@@ -49,6 +49,18 @@ __constant__ unsigned char c_feat_tb[5][4] = {{0, 1, 2, 3}, {0, 1, 2, 4}, {0, 1,
 #endif
 #define CULL_ROW 19  // doubles per staged pair row (18 used): odd stride -> conflict-free column access
 
+// Work-list records.  They carry the four point ids of the feature test so that the consumer's gathers
+// start right after one record load (no pairs -> elem -> points pointer chase).
+struct FeatRec {  // 24 B
+    unsigned entry;  // pair index | feature << 28
+    int id[4];       // points as passed to PointToTri / EdgeToEdge
+    unsigned edge;   // 1 = edge-edge test, 0 = point-triangle
+};
+struct RootRec {  // 48 B: a feature whose coplanarity cubic has a usable root
+    FeatRec f;
+    double r0, r1, r2;  // sorted, invalid = -1 (isCoplanar's output)
+};
+
 // Conservative FP32 swept box of one point over [0, dt] (static: the point itself): rounded outward,
 // so every position the narrow phase can evaluate lies inside.
 struct FBox {
@@ -91,13 +103,14 @@ __device__ __forceinline__ bool boxes_far(const FBox& a, const FBox& b, float h2
 template <bool MOVING>
 __global__ void __launch_bounds__(CULL_THREADS, 4)
 k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restrict__ elem, const Vec4* __restrict__ xo,
-       const Vec4* __restrict__ av, NarrowParams P, unsigned* __restrict__ feats, long long cap_feats,
+       const Vec4* __restrict__ av, NarrowParams P, FeatRec* __restrict__ feats, long long cap_feats,
        unsigned long long* counters)
 {
     __shared__ double s_x[CULL_THREADS][CULL_ROW];
     __shared__ double s_v[MOVING ? CULL_THREADS : 1][CULL_ROW];
     __shared__ unsigned s_mask[CULL_THREADS];
     __shared__ int s_pref[CULL_THREADS];
+    __shared__ int s_id[CULL_THREADS][7];
     const int tid = threadIdx.x, lane = tid & 31, wb = tid & ~31;
     long long n_pairs = (long long)counters[CTR_PAIRS];
     if (n_pairs > cap_pairs) n_pairs = cap_pairs;
@@ -111,6 +124,8 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
             const int2 pr = __ldg(pairs + pi);
             const int4 A = __ldg(elem + pr.x), B = __ldg(elem + pr.y);
             const int ids[6] = {A.x, A.y, A.z, B.x, B.y, B.z};
+#pragma unroll
+            for (int s = 0; s < 6; ++s) s_id[tid][s] = ids[s];
             FBox pb[6];
 #pragma unroll
             for (int s = 0; s < 6; ++s) {
@@ -191,7 +206,9 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
         for (int k0 = 0; k0 < total; k0 += 32) {
             const int k = k0 + lane;
             bool keep = false;
-            unsigned entry = 0;
+            FeatRec rec;
+            rec.entry = 0; rec.edge = 0;
+            rec.id[0] = rec.id[1] = rec.id[2] = rec.id[3] = 0;
             if (k < total) {
                 // owner = last lane whose exclusive prefix is <= k
                 int o = 0;
@@ -200,20 +217,25 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
                     if (s_pref[wb + o + step] <= k) o += step;
                 const unsigned m = s_mask[wb + o];
                 const int f = __fns(m & 0x7fffu, 0, k - s_pref[wb + o] + 1);
-                entry = (unsigned)(base + wb + o) | ((unsigned)f << 28);
+                rec.entry = (unsigned)(base + wb + o) | ((unsigned)f << 28);
                 keep = true;
+                const int type = (int)(m >> 16);
+                int sl[4];
+                if (type == 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) sl[q] = MOVING ? c_feat_tt_moving[f][q] : c_feat_tt_static[f][q];
+                    rec.edge = f >= 6;
+                } else if (type == 1) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) sl[q] = c_feat_tb[f][q];
+                    rec.edge = f >= 2;
+                } else {
+                    sl[0] = 0; sl[1] = 1; sl[2] = 3; sl[3] = 4;
+                    rec.edge = 1;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rec.id[i] = s_id[wb + o][sl[i]];
                 if (MOVING) {
-                    const int type = (int)(m >> 16);
-                    int sl[4];
-                    if (type == 0) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) sl[q] = c_feat_tt_moving[f][q];
-                    } else if (type == 1) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) sl[q] = c_feat_tb[f][q];
-                    } else {
-                        sl[0] = 0; sl[1] = 1; sl[2] = 3; sl[3] = 4;
-                    }
                     Quad q;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
@@ -233,7 +255,12 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
                 if (lane == 0) slot0 = atomicAdd(&counters[CTR_FEATS], (unsigned long long)__popc(ballot));
                 slot0 = __shfl_sync(0xffffffffu, slot0, 0);
                 const unsigned long long slot = slot0 + __popc(ballot & ((1u << lane) - 1u));
-                if (keep && (long long)slot < cap_feats) feats[slot] = entry;
+                if (keep && (long long)slot < cap_feats) {
+                    uint2* dst = reinterpret_cast<uint2*>(feats + slot);
+                    dst[0] = make_uint2(rec.entry, (unsigned)rec.id[0]);
+                    dst[1] = make_uint2((unsigned)rec.id[1], (unsigned)rec.id[2]);
+                    dst[2] = make_uint2((unsigned)rec.id[3], rec.edge);
+                }
             }
         }
         __syncwarp();
@@ -242,64 +269,30 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
     if (lane == 0 && n_box) atomicAdd(&counters[CTR_BOXSURV], n_box);
 }
 
-// decode one work-list entry into the four point ids of the feature test
-template <bool MOVING>
-__device__ __forceinline__ void feature_points(unsigned w, const int2* __restrict__ pairs, const int4* __restrict__ elem,
-                                               int2& pr, int& f, bool& edge, int* pid)
+__device__ __forceinline__ FeatRec load_featrec(const FeatRec* p)
 {
-    const unsigned pi = w & 0x0fffffffu;
-    f = (int)(w >> 28);
-    pr = __ldg(pairs + pi);
-    const int4 A = __ldg(elem + pr.x), B = __ldg(elem + pr.y);
-    const int ids[6] = {A.x, A.y, A.z, B.x, B.y, B.z};
-    int sl[4];
-    if (A.z >= 0 && B.z >= 0) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) sl[q] = MOVING ? c_feat_tt_moving[f][q] : c_feat_tt_static[f][q];
-        edge = f >= 6;
-    } else if (A.z >= 0) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) sl[q] = c_feat_tb[f][q];
-        edge = f >= 2;
-    } else {
-        sl[0] = 0; sl[1] = 1; sl[2] = 3; sl[3] = 4;
-        edge = true;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int id = ids[0];
-#pragma unroll
-        for (int s = 1; s < 6; ++s) id = sl[i] == s ? ids[s] : id;
-        pid[i] = id;
-    }
+    const uint2* q = reinterpret_cast<const uint2*>(p);
+    const uint2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    FeatRec r;
+    r.entry = a.x; r.id[0] = (int)a.y; r.id[1] = (int)b.x; r.id[2] = (int)b.y; r.id[3] = (int)c.x; r.edge = c.y;
+    return r;
 }
-
-struct RootRec {  // 32 B: one feature whose coplanarity cubic has a usable root
-    unsigned feat;
-    unsigned pad;
-    double r0, r1, r2;  // sorted, invalid = -1 (isCoplanar's output)
-};
 
 // Stage 2 (CCD): correctly rounded solve of the coplanarity cubic for every feature the classifier
 // let through.  Only positions and velocities are needed here; the kernel is nothing but the
 // double-double math, which keeps its instruction footprint small.
 __global__ void __launch_bounds__(FEAT_THREADS, 5)
-k_roots(const unsigned* __restrict__ feats, long long cap_feats, const int2* __restrict__ pairs, const int4* __restrict__ elem,
-        const Vec4* __restrict__ xo, const Vec4* __restrict__ av, double dt, RootRec* __restrict__ out, long long cap_out,
-        unsigned long long* counters)
+k_roots(const FeatRec* __restrict__ feats, long long cap_feats, const Vec4* __restrict__ xo, const Vec4* __restrict__ av, double dt,
+        RootRec* __restrict__ out, long long cap_out, unsigned long long* counters)
 {
     long long n = (long long)counters[CTR_FEATS];
     if (n > cap_feats) n = cap_feats;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-        const unsigned w = __ldg(feats + t);
-        int2 pr;
-        int f, pid[4];
-        bool edge;
-        feature_points<true>(w, pairs, elem, pr, f, edge, pid);
+        const FeatRec fr = load_featrec(feats + t);
         Quad q;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const Vec4 x = ldg_vec4(xo + pid[i]), v = ldg_vec4(av + pid[i]);
+            const Vec4 x = ldg_vec4(xo + fr.id[i]), v = ldg_vec4(av + fr.id[i]);
             q.xo[i][0] = x.x; q.xo[i][1] = x.y; q.xo[i][2] = x.z;
             q.av[i][0] = v.x; q.av[i][1] = v.y; q.av[i][2] = v.z;
         }
@@ -307,14 +300,12 @@ k_roots(const unsigned* __restrict__ feats, long long cap_feats, const int2* __r
         if (!is_coplanar<false>(q, dt, roots)) continue;
         const unsigned long long slot = reserve(&counters[CTR_ROOTS], 1);
         if ((long long)slot < cap_out) {
-            ulonglong2* o = reinterpret_cast<ulonglong2*>(out + slot);
-            ulonglong2 a, b;
-            a.x = (unsigned long long)w;
-            a.y = (unsigned long long)__double_as_longlong(roots[0]);
-            b.x = (unsigned long long)__double_as_longlong(roots[1]);
-            b.y = (unsigned long long)__double_as_longlong(roots[2]);
-            o[0] = a;
-            o[1] = b;
+            uint2* o = reinterpret_cast<uint2*>(out + slot);
+            o[0] = make_uint2(fr.entry, (unsigned)fr.id[0]);
+            o[1] = make_uint2((unsigned)fr.id[1], (unsigned)fr.id[2]);
+            o[2] = make_uint2((unsigned)fr.id[3], fr.edge);
+            double* r = reinterpret_cast<double*>(out + slot) + 3;
+            r[0] = roots[0]; r[1] = roots[1]; r[2] = roots[2];
         }
     }
 }
@@ -322,39 +313,34 @@ k_roots(const unsigned* __restrict__ feats, long long cap_feats, const int2* __r
 // Stage 3: static tests at the root times (CCD) or at x_old (proximity) + impulse records.
 template <bool MOVING>
 __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS)
-k_contact(const unsigned* __restrict__ feats, const RootRec* __restrict__ rootrecs, long long cap_in, const int2* __restrict__ pairs,
-          const int4* __restrict__ elem, const Vec4* __restrict__ xo, const Vec4* __restrict__ av,
-          const uint8_t* __restrict__ vflags, const int* __restrict__ vbody, NarrowParams P, Emit E,
-          unsigned* __restrict__ pair_hit)
+k_contact(const FeatRec* __restrict__ feats, const RootRec* __restrict__ rootrecs, long long cap_in, const int2* __restrict__ pairs,
+          const Vec4* __restrict__ xo, const Vec4* __restrict__ av, const uint8_t* __restrict__ vflags,
+          const int* __restrict__ vbody, NarrowParams P, Emit E, unsigned* __restrict__ pair_hit)
 {
     long long n = (long long)E.counters[MOVING ? CTR_ROOTS : CTR_FEATS];
     if (n > cap_in) n = cap_in;
     const double h = MOVING ? P.eps : P.thickness;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-        unsigned w;
+        FeatRec fr;
         double r0 = 0, r1 = 0, r2 = 0;
         if (MOVING) {
-            const ulonglong2* in = reinterpret_cast<const ulonglong2*>(rootrecs + t);
-            const ulonglong2 a = __ldg(in), b = __ldg(in + 1);
-            w = (unsigned)a.x;
-            r0 = __longlong_as_double((long long)a.y);
-            r1 = __longlong_as_double((long long)b.x);
-            r2 = __longlong_as_double((long long)b.y);
+            fr = load_featrec(&rootrecs[t].f);
+            const double* r = reinterpret_cast<const double*>(rootrecs + t) + 3;
+            r0 = __ldg(r); r1 = __ldg(r + 1); r2 = __ldg(r + 2);
         } else {
-            w = __ldg(feats + t);
+            fr = load_featrec(feats + t);
         }
-        int2 pr;
-        int f, pid[4];
-        bool edge;
-        feature_points<MOVING>(w, pairs, elem, pr, f, edge, pid);
+        const unsigned pi = fr.entry & 0x0fffffffu;
+        const int f = (int)(fr.entry >> 28);
+        const int2 pr = __ldg(pairs + pi);
         Quad q;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            q.id[i] = pid[i];
-            const Vec4 x = ldg_vec4(xo + pid[i]), v = ldg_vec4(av + pid[i]);
+            q.id[i] = fr.id[i];
+            const Vec4 x = ldg_vec4(xo + fr.id[i]), v = ldg_vec4(av + fr.id[i]);
             q.xo[i][0] = x.x; q.xo[i][1] = x.y; q.xo[i][2] = x.z;
             q.av[i][0] = v.x; q.av[i][1] = v.y; q.av[i][2] = v.z;
-            q.flags[i] = __ldg(vflags + pid[i]);
+            q.flags[i] = __ldg(vflags + fr.id[i]);
             q.body[i] = 0;
         }
         if ((q.flags[0] & 3) && (q.flags[1] & 3) && (q.flags[2] & 3) && (q.flags[3] & 3)) {
@@ -363,11 +349,9 @@ k_contact(const unsigned* __restrict__ feats, const RootRec* __restrict__ rootre
         }
         const unsigned long long key = ((unsigned long long)(unsigned)pr.x << 34) | ((unsigned long long)(unsigned)pr.y << 4) |
                                        (unsigned long long)f;
+        const bool edge = fr.edge != 0;
         const bool hit = MOVING ? feature_at_roots(P, E, q, key, edge, h, r0, r1, r2) : feature_static(P, E, q, key, edge, h);
-        if (hit) {
-            const unsigned pi = w & 0x0fffffffu;
-            atomicOr(pair_hit + (pi >> 5), 1u << (pi & 31));
-        }
+        if (hit) atomicOr(pair_hit + (pi >> 5), 1u << (pi & 31));
     }
 }
 
@@ -435,7 +419,8 @@ struct clsn_ctx {
     bool tree_built = false;
     // pass buffers
     DevBuf<int2> pairs, dbg_cand;
-    DevBuf<unsigned> feats, pair_hit;
+    DevBuf<FeatRec> feats;
+    DevBuf<unsigned> pair_hit;
     DevBuf<RootRec> rootrecs;
     DevBuf<PointRec> prec;
     DevBuf<BodyRec> brec;
@@ -799,17 +784,15 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
         if (moving) {
             k_cull<true><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p, P,
                                                                 c->feats.p, (long long)c->feats.n, c->counters.p);
-            k_roots<<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->pairs.p, c->elem.p, c->xo.p, c->av.p,
-                                                           P.dt, c->rootrecs.p, (long long)c->rootrecs.n, c->counters.p);
+            k_roots<<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P.dt, c->rootrecs.p,
+                                                           (long long)c->rootrecs.n, c->counters.p);
             k_contact<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, c->rootrecs.p, (long long)c->rootrecs.n, c->pairs.p,
-                                                                   c->elem.p, c->xo.p, c->av.p, c->vflags.p, c->vbody.p, P, E,
-                                                                   c->pair_hit.p);
+                                                                   c->xo.p, c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
         } else {
             k_cull<false><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p, P,
                                                                  c->feats.p, (long long)c->feats.n, c->counters.p);
             k_contact<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, c->rootrecs.p, (long long)c->feats.n, c->pairs.p,
-                                                                    c->elem.p, c->xo.p, c->av.p, c->vflags.p, c->vbody.p, P, E,
-                                                                    c->pair_hit.p);
+                                                                    c->xo.p, c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
         }
         k_count_true<<<c->sm_count * 2, 256, 0, c->stream>>>(c->pair_hit.p, hit_words, c->counters.p);
         CK(cudaGetLastError());

@@ -1,0 +1,119 @@
+"""Full-size checks (BASELINE.json config 4: 1 000 000 triangles) through size-independent properties --
+the C oracle would need minutes there.  Determinism (bit-identical reruns: no floating-point atomics),
+slice decomposition == whole (the multi-GPU contract), and agreement with the oracle on a small
+member of the same scene family (same generator, same density of contacts)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from collision_b200 import scenes
+from collision_b200.solver import CollisionSolver3d
+from oracle import port
+from parity_util import same_bits
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def big():
+    return scenes.layered_cloth(8, 251)
+
+
+def _solver(sc):
+    g = CollisionSolver3d()
+    CollisionSolver3d.set_params_from(sc.params)
+    g.assembleFromInterface(sc, sc.dt)
+    return g
+
+
+def test_config4_deterministic_and_sane(big):
+    sc = big
+    assert sc.T == 1_000_000
+    g = _solver(sc)
+    outs = []
+    for rep in range(2):
+        x, vel = sc.x.copy(), sc.vel.copy()
+        xg = x + sc.dt * vel
+        has = g.resolveCollision(x, xg, vel)
+        outs.append((xg, vel.copy(), has.copy(), g.last_stats))
+    assert same_bits(outs[0][0], outs[1][0]) and same_bits(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2])
+    st = outs[0][3]
+    assert 1 <= st["n_ccd_passes"] <= 5
+    for p in [st["proximity"]] + st["ccd"]:
+        assert p["candidates"] >= p["pairs_tested"] >= p["true_pairs"] >= 0
+        assert p["box_survivors"] >= p["features"] >= 0 and p["contacts"] <= p["box_survivors"]
+        assert p["pairs_tested"] * 15 >= p["box_survivors"]
+    assert np.isfinite(outs[0][0]).all() and np.isfinite(outs[0][1]).all()
+    # every vertex that moved off its candidate position was flagged
+    moved = np.abs(outs[0][0] - (sc.x + sc.dt * sc.vel)).max(axis=1) > 0
+    assert (outs[0][2][moved] != 0).all()
+    g.close()
+
+
+def test_config4_slices_equal_whole_first_pass(big):
+    """3-way slice decomposition at 1 M triangles: candidate / pair / contact totals and the reduced
+    avgVel of the first CCD pass equal the unsliced run bit for bit."""
+    import torch
+    from collision_b200.dist import BODY_RECORD_BYTES, POINT_RECORD_BYTES, _DevPtr
+    sc = big
+    x, vel = sc.x, sc.vel
+    xn = x + sc.dt * vel
+    whole = _solver(sc)
+    whole.upload(x, xn)
+    whole.avg_velocity()
+    sw = whole.detect(1)
+    whole.apply(True)
+    _, avw, hasw = whole.download()
+    whole.close()
+    dev = torch.device("cuda", 0)
+    bufs, tot = [], dict(candidates=0, pairs_tested=0, contacts=0, true=0)
+    part = _solver(sc)
+    for r in range(3):
+        part.ctx.check(part.ctx.L.clsn_set_slice(part.ctx.h, r, 3))
+        part.upload(x, xn)
+        part.avg_velocity()
+        s = part.detect(1)
+        pp, pb = C.c_void_p(), C.c_void_p()
+        npr, nbr, nt = C.c_int64(), C.c_int64(), C.c_int64()
+        part.ctx.check(part.ctx.L.clsn_export_records(part.ctx.h, C.byref(pp), C.byref(npr), C.byref(pb), C.byref(nbr), C.byref(nt)))
+        nb = npr.value * POINT_RECORD_BYTES
+        bufs.append(torch.as_tensor(_DevPtr(pp.value, nb), device=dev)[:nb].clone())
+        assert nbr.value == 0
+        for k in ("candidates", "pairs_tested", "contacts"):
+            tot[k] += s[k]
+        tot["true"] += nt.value
+    assert tot["candidates"] == sw["candidates"] and tot["pairs_tested"] == sw["pairs_tested"]
+    assert tot["contacts"] == sw["contacts"] and tot["true"] == sw["true_pairs"]
+    allp = torch.cat(bufs)
+    torch.cuda.synchronize()
+    part.ctx.check(part.ctx.L.clsn_import_records(part.ctx.h, allp.data_ptr(), allp.numel() // POINT_RECORD_BYTES, None, 0))
+    part.apply(True)
+    _, av, has = part.download()
+    assert same_bits(av, avw) and np.array_equal(has, hasw)
+    part.close()
+
+
+def test_sample_of_config4_matches_oracle():
+    """a 6 400-triangle member of the config-4 family (8 layers, same generator), whole step against the
+    oracle (the binary128 libm of the oracle makes bigger members take minutes)"""
+    sc = scenes.layered_cloth(8, 21)
+    port.set_libm(port.LIBM_CR)
+    try:
+        orc = port.OracleSolver(sc)
+        g = _solver(sc)
+        x, vel = sc.x.copy(), sc.vel.copy()
+        xn = x + sc.dt * vel
+        orc.set_state(x, xn)
+        vo = vel.copy()
+        st_o = orc.resolve(vo)
+        xg, vg = xn.copy(), vel.copy()
+        g.resolveCollision(x, xg, vg)
+        st = g.last_stats
+        assert [p["true_pairs"] for p in st["ccd"]] == st_o[2:2 + st_o[1]]
+        assert [p["candidates"] for p in st["ccd"]] == st_o[9:9 + st_o[1]]
+        assert same_bits(xg, orc.get(port.F_X)) and same_bits(vg, vo)
+        g.close()
+    finally:
+        port.set_libm(port.LIBM_NATIVE)
