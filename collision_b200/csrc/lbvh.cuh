@@ -254,88 +254,122 @@ struct TraverseOut {
     unsigned long long* counters;
 };
 
-// Self-query.  Thread = one query leaf (sorted index i in [q_lo, q_hi)); reports leaves j > i whose
-// exact FP64 boxes overlap.  Subtrees whose last leaf is <= i are skipped (each pair once).
-__global__ void __launch_bounds__(128)
+#define TRAV_THREADS 128
+#define TRAV_QCAP 96
+
+// Self-query.  Thread = one query leaf (sorted index i in [q_lo, q_hi)); finds leaves j > i whose exact
+// FP64 boxes overlap (AABB::isCollid, AABB.cpp:56-60).  Subtrees whose last leaf is <= i are skipped, so
+// each unordered pair is found once.
+// The loop is kept lean and converged: every iteration is exactly one node visit per lane, and leaf
+// children that pass the conservative FP32 test are only pushed to a per-warp shared-memory queue.
+// Whenever the queue holds >= 32 entries the whole warp drains 32 of them together: exact FP64 test,
+// adjacency / same-surface-rigid filters (dcollid3d.cpp:279-284, dcollid.cpp:762) and a ballot-aggregated
+// append to the pair list -- all lanes busy instead of one or two.
+__global__ void __launch_bounds__(TRAV_THREADS)
 k_traverse(const WideNode* __restrict__ nodes, const double* __restrict__ lbox, const int* __restrict__ leaf_elem,
            const int4* __restrict__ elem, int N, int q_lo, int q_hi, TraverseOut out)
 {
-    int i = q_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int2 s_q[TRAV_THREADS / 32][TRAV_QCAP];
+    __shared__ int s_n[TRAV_THREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = q_lo + blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long n_cand = 0;
+    if (lane == 0) s_n[w] = 0;
+    __syncwarp();
+    float flo[3] = {0, 0, 0}, fhi[3] = {0, 0, 0};
+    int node = -1;  // -1 = this lane has finished
     if (i < q_hi && N >= 2) {
         const double2* lb = reinterpret_cast<const double2*>(lbox + 6 * (size_t)i);
-        double2 b0 = __ldg(lb), b1 = __ldg(lb + 1), b2 = __ldg(lb + 2);
-        const double qlo[3] = {b0.x, b0.y, b1.x}, qhi[3] = {b1.y, b2.x, b2.y};
-        float flo[3], fhi[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            flo[d] = __double2float_rd(qlo[d]);
-            fhi[d] = __double2float_ru(qhi[d]);
-        }
-        const int my_id = __ldg(leaf_elem + i);
-        const int4 me = __ldg(elem + my_id);
-        int stack[64];
-        int sp = 0;
-        int node = 0;
-        while (true) {
+        const double2 b0 = __ldg(lb), b1 = __ldg(lb + 1), b2 = __ldg(lb + 2);
+        flo[0] = __double2float_rd(b0.x); flo[1] = __double2float_rd(b0.y); flo[2] = __double2float_rd(b1.x);
+        fhi[0] = __double2float_ru(b1.y); fhi[1] = __double2float_ru(b2.x); fhi[2] = __double2float_ru(b2.y);
+        node = 0;
+    }
+    int stack[64];
+    int sp = 0;
+    bool more = __any_sync(0xffffffffu, node >= 0);
+    while (more || s_n[w] > 0) {
+        if (node >= 0) {
             const float4* np = reinterpret_cast<const float4*>(nodes + node);
-            float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
-            int4 n3 = __ldg(reinterpret_cast<const int4*>(np + 3));
+            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+            const int4 n3 = __ldg(reinterpret_cast<const int4*>(np + 3));
             // n0 = lo0.xyz hi0.x ; n1 = hi0.yz lo1.xy ; n2 = lo1.z hi1.xyz ; n3 = c0 c1 last parent
             const int c0 = n3.x, c1 = n3.y, last = n3.z;
             const int split = c0 < 0 ? ~c0 : c0;  // last leaf of the left child
-            bool o0 = split > i && flo[0] <= n0.w && fhi[0] >= n0.x && flo[1] <= n1.x && fhi[1] >= n0.y &&
-                      flo[2] <= n1.y && fhi[2] >= n0.z;
-            bool o1 = last > i && flo[0] <= n2.y && fhi[0] >= n1.z && flo[1] <= n2.z && fhi[1] >= n1.w &&
-                      flo[2] <= n2.w && fhi[2] >= n2.x;
+            const bool o0 = split > i && flo[0] <= n0.w && fhi[0] >= n0.x && flo[1] <= n1.x && fhi[1] >= n0.y &&
+                            flo[2] <= n1.y && fhi[2] >= n0.z;
+            const bool o1 = last > i && flo[0] <= n2.y && fhi[0] >= n1.z && flo[1] <= n2.z && fhi[1] >= n1.w &&
+                            flo[2] <= n2.w && fhi[2] >= n2.x;
             int next = -1;
-#pragma unroll
-            for (int side = 0; side < 2; ++side) {
-                const bool o = side ? o1 : o0;
-                const int c = side ? c1 : c0;
-                if (!o) continue;
-                if (c >= 0) {
-                    if (next < 0) next = c; else stack[sp++] = c;
-                    continue;
-                }
-                const int j = ~c;
-                if (j <= i) continue;
-                const double2* ob = reinterpret_cast<const double2*>(lbox + 6 * (size_t)j);
-                double2 c0b = __ldg(ob), c1b = __ldg(ob + 1), c2b = __ldg(ob + 2);
-                // AABB::isCollid, AABB.cpp:56-60 (closed intervals)
-                bool hit = qlo[0] <= c1b.y && qhi[0] >= c0b.x && qlo[1] <= c2b.x && qhi[1] >= c0b.y &&
-                           qlo[2] <= c2b.y && qhi[2] >= c1b.x;
-                if (!hit) continue;
-                ++n_cand;
-                const int other_id = __ldg(leaf_elem + j);
-                const int a = min(my_id, other_id), b = max(my_id, other_id);
-                if (out.dbg_cand) {
-                    unsigned long long s = atomicAdd(&out.counters[CTR_DBG_CAND], 1ull);
-                    if ((long long)s < out.cap_dbg) out.dbg_cand[s] = make_int2(a, b);
-                }
-                const int4 ot = __ldg(elem + other_id);
-                // pairs sharing a vertex return false at once in every narrow-phase driver
-                // (dcollid3d.cpp:209-214, 257-264, 279-284, 491-496, 546-553, 574-579)
-                bool shared = me.x == ot.x || me.x == ot.y || me.y == ot.x || me.y == ot.y;
-                if (ot.z >= 0) shared = shared || me.x == ot.z || me.y == ot.z;
-                if (me.z >= 0) shared = shared || me.z == ot.x || me.z == ot.y || (ot.z >= 0 && me.z == ot.z);
-                if (shared) continue;
-                // tri-tri on one surface with a rigid `a` is dropped (dcollid.cpp:762, 805)
-                if (me.z >= 0 && ot.z >= 0) {
-                    const int4 ea = my_id < other_id ? me : ot;
-                    if (((me.w ^ ot.w) & 0x0fffffff) == 0 && (ea.w & 0x10000000)) continue;
-                }
-                unsigned long long s = reserve(&out.counters[CTR_PAIRS], 1);
-                if ((long long)s < out.cap_pairs) out.pairs[s] = make_int2(a, b);
+            if (o0) {
+                if (c0 >= 0) next = c0;
+                else if (~c0 > i) s_q[w][atomicAdd(&s_n[w], 1)] = make_int2(i, ~c0);
+            }
+            if (o1) {
+                if (c1 >= 0) { if (next < 0) next = c1; else stack[sp++] = c1; }
+                else if (~c1 > i) s_q[w][atomicAdd(&s_n[w], 1)] = make_int2(i, ~c1);
             }
             if (next >= 0) node = next;
             else if (sp > 0) node = stack[--sp];
-            else break;
+            else node = -1;
         }
+        more = __any_sync(0xffffffffu, node >= 0);
+        __syncwarp();
+        // drain: full batches while traversing, everything at the end
+        int nq = s_n[w];
+        while (nq >= 32 || (!more && nq > 0)) {
+            const int take = nq < 32 ? nq : 32;
+            const int base = nq - take;
+            bool emit = false;
+            int a = 0, b = 0;
+            if (lane < take) {
+                const int2 e = s_q[w][base + lane];
+                const double2* qb = reinterpret_cast<const double2*>(lbox + 6 * (size_t)e.x);
+                const double2* ob = reinterpret_cast<const double2*>(lbox + 6 * (size_t)e.y);
+                const double2 q0 = __ldg(qb), q1 = __ldg(qb + 1), q2 = __ldg(qb + 2);
+                const double2 c0b = __ldg(ob), c1b = __ldg(ob + 1), c2b = __ldg(ob + 2);
+                // lo = (b0.x, b0.y, b1.x), hi = (b1.y, b2.x, b2.y); closed intervals
+                const bool hit = q0.x <= c1b.y && q1.y >= c0b.x && q0.y <= c2b.x && q2.x >= c0b.y && q1.x <= c2b.y && q2.y >= c1b.x;
+                if (hit) {
+                    ++n_cand;
+                    const int my_id = __ldg(leaf_elem + e.x), other_id = __ldg(leaf_elem + e.y);
+                    a = min(my_id, other_id);
+                    b = max(my_id, other_id);
+                    if (out.dbg_cand) {
+                        const unsigned long long sdb = atomicAdd(&out.counters[CTR_DBG_CAND], 1ull);
+                        if ((long long)sdb < out.cap_dbg) out.dbg_cand[sdb] = make_int2(a, b);
+                    }
+                    const int4 me = __ldg(elem + my_id), ot = __ldg(elem + other_id);
+                    // pairs sharing a vertex return false at once in every narrow-phase driver
+                    // (dcollid3d.cpp:209-214, 257-264, 279-284, 491-496, 546-553, 574-579)
+                    bool shared = me.x == ot.x || me.x == ot.y || me.y == ot.x || me.y == ot.y;
+                    if (ot.z >= 0) shared = shared || me.x == ot.z || me.y == ot.z;
+                    if (me.z >= 0) shared = shared || me.z == ot.x || me.z == ot.y || (ot.z >= 0 && me.z == ot.z);
+                    emit = !shared;
+                    // tri-tri on one surface with a rigid `a` is dropped (dcollid.cpp:762, 805)
+                    if (emit && me.z >= 0 && ot.z >= 0) {
+                        const int4 ea = my_id < other_id ? me : ot;
+                        if (((me.w ^ ot.w) & 0x0fffffff) == 0 && (ea.w & 0x10000000)) emit = false;
+                    }
+                }
+            }
+            const unsigned ballot = __ballot_sync(0xffffffffu, emit);
+            if (ballot) {
+                unsigned long long s0 = 0;
+                if (lane == 0) s0 = atomicAdd(&out.counters[CTR_PAIRS], (unsigned long long)__popc(ballot));
+                s0 = __shfl_sync(0xffffffffu, s0, 0);
+                const unsigned long long sl = s0 + __popc(ballot & ((1u << lane) - 1u));
+                if (emit && (long long)sl < out.cap_pairs) out.pairs[sl] = make_int2(a, b);
+            }
+            nq = base;
+            __syncwarp();
+        }
+        if (lane == 0) s_n[w] = nq;
+        __syncwarp();
     }
     // candidate count: warp-reduce, one atomic per warp
     for (int o = 16; o > 0; o >>= 1) n_cand += __shfl_xor_sync(0xffffffffu, n_cand, o);
-    if ((threadIdx.x & 31) == 0 && n_cand) atomicAdd(&out.counters[CTR_CAND], n_cand);
+    if (lane == 0 && n_cand) atomicAdd(&out.counters[CTR_CAND], n_cand);
 }
 
 } // namespace clsn
