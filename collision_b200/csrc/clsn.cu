@@ -249,14 +249,19 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
                     keep = coplanar_maybe(ca, cb, cc, cd, P.dt);
                 }
             }
-            const unsigned ballot = __ballot_sync(0xffffffffu, keep);
-            if (ballot) {
+            // point-triangle entries fill the list from the front, edge-edge entries from the back, so that
+            // the consumers' warps run one kind of test each
+#pragma unroll
+            for (int kind = 0; kind < 2; ++kind) {
+                const bool mine = keep && (rec.edge != 0) == (kind == 1);
+                const unsigned ballot = __ballot_sync(0xffffffffu, mine);
+                if (!ballot) continue;
                 unsigned long long slot0 = 0;
-                if (lane == 0) slot0 = atomicAdd(&counters[CTR_FEATS], (unsigned long long)__popc(ballot));
+                if (lane == 0) slot0 = atomicAdd(&counters[kind ? CTR_FEATS_EE : CTR_FEATS], (unsigned long long)__popc(ballot));
                 slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-                const unsigned long long slot = slot0 + __popc(ballot & ((1u << lane) - 1u));
-                if (keep && (long long)slot < cap_feats) {
-                    uint2* dst = reinterpret_cast<uint2*>(feats + slot);
+                const long long slot = (long long)(slot0 + __popc(ballot & ((1u << lane) - 1u)));
+                if (mine && slot < cap_feats) {
+                    uint2* dst = reinterpret_cast<uint2*>(feats + (kind ? cap_feats - 1 - slot : slot));
                     dst[0] = make_uint2(rec.entry, (unsigned)rec.id[0]);
                     dst[1] = make_uint2((unsigned)rec.id[1], (unsigned)rec.id[2]);
                     dst[2] = make_uint2((unsigned)rec.id[3], rec.edge);
@@ -285,10 +290,11 @@ __global__ void __launch_bounds__(FEAT_THREADS, 5)
 k_roots(const FeatRec* __restrict__ feats, long long cap_feats, const Vec4* __restrict__ xo, const Vec4* __restrict__ av, double dt,
         RootRec* __restrict__ out, long long cap_out, unsigned long long* counters)
 {
-    long long n = (long long)counters[CTR_FEATS];
-    if (n > cap_feats) n = cap_feats;
+    const long long n_pt = (long long)counters[CTR_FEATS], n_ee = (long long)counters[CTR_FEATS_EE];
+    if (n_pt + n_ee > cap_feats) return;  // overflow: the host grows the list and repeats the pass
+    const long long n = n_pt + n_ee;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-        const FeatRec fr = load_featrec(feats + t);
+        const FeatRec fr = load_featrec(t < n_pt ? feats + t : feats + (cap_feats - 1 - (t - n_pt)));
         Quad q;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -298,13 +304,18 @@ k_roots(const FeatRec* __restrict__ feats, long long cap_feats, const Vec4* __re
         }
         double roots[3] = {-1, -1, -1};
         if (!is_coplanar<false>(q, dt, roots)) continue;
-        const unsigned long long slot = reserve(&counters[CTR_ROOTS], 1);
-        if ((long long)slot < cap_out) {
-            uint2* o = reinterpret_cast<uint2*>(out + slot);
+        const bool ee = fr.edge != 0;
+        // reserve() aggregates the converged lanes onto ONE counter, so the two kinds reserve separately
+        long long slot = 0;
+        if (ee) slot = (long long)reserve(&counters[CTR_ROOTS_EE], 1);
+        else slot = (long long)reserve(&counters[CTR_ROOTS], 1);
+        if (slot < cap_out) {
+            RootRec* dst = ee ? out + (cap_out - 1 - slot) : out + slot;
+            uint2* o = reinterpret_cast<uint2*>(dst);
             o[0] = make_uint2(fr.entry, (unsigned)fr.id[0]);
             o[1] = make_uint2((unsigned)fr.id[1], (unsigned)fr.id[2]);
             o[2] = make_uint2((unsigned)fr.id[3], fr.edge);
-            double* r = reinterpret_cast<double*>(out + slot) + 3;
+            double* r = reinterpret_cast<double*>(dst) + 3;
             r[0] = roots[0]; r[1] = roots[1]; r[2] = roots[2];
         }
     }
@@ -317,18 +328,21 @@ k_contact(const FeatRec* __restrict__ feats, const RootRec* __restrict__ rootrec
           const Vec4* __restrict__ xo, const Vec4* __restrict__ av, const uint8_t* __restrict__ vflags,
           const int* __restrict__ vbody, NarrowParams P, Emit E, unsigned* __restrict__ pair_hit)
 {
-    long long n = (long long)E.counters[MOVING ? CTR_ROOTS : CTR_FEATS];
-    if (n > cap_in) n = cap_in;
+    const long long n_pt = (long long)E.counters[MOVING ? CTR_ROOTS : CTR_FEATS];
+    const long long n_ee = (long long)E.counters[MOVING ? CTR_ROOTS_EE : CTR_FEATS_EE];
+    if (n_pt + n_ee > cap_in) return;  // overflow: the host grows the list and repeats the pass
+    const long long n = n_pt + n_ee;
     const double h = MOVING ? P.eps : P.thickness;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const long long at = t < n_pt ? t : cap_in - 1 - (t - n_pt);
         FeatRec fr;
         double r0 = 0, r1 = 0, r2 = 0;
         if (MOVING) {
-            fr = load_featrec(&rootrecs[t].f);
-            const double* r = reinterpret_cast<const double*>(rootrecs + t) + 3;
+            fr = load_featrec(&rootrecs[at].f);
+            const double* r = reinterpret_cast<const double*>(rootrecs + at) + 3;
             r0 = __ldg(r); r1 = __ldg(r + 1); r2 = __ldg(r + 2);
         } else {
-            fr = load_featrec(feats + t);
+            fr = load_featrec(feats + at);
         }
         const unsigned pi = fr.entry & 0x0fffffffu;
         const int f = (int)(fr.entry >> 28);
@@ -752,7 +766,7 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
     const int q_lo = (int)((long long)N * c->rank / c->nranks), q_hi = (int)((long long)N * (c->rank + 1) / c->nranks);
     for (int attempt = 0; attempt < 8; ++attempt) {
         CK(cudaMemsetAsync(c->counters.p, 0, CTR_ERROR * sizeof(unsigned long long), c->stream));  // keep CTR_ERROR
-        CK(cudaMemsetAsync(c->counters.p + CTR_DBG_CAND, 0, 4 * sizeof(unsigned long long), c->stream));  // + CTR_FEATS, CTR_BOXSURV, CTR_ROOTS
+        CK(cudaMemsetAsync(c->counters.p + CTR_DBG_CAND, 0, 6 * sizeof(unsigned long long), c->stream));  // + CTR_FEATS, CTR_BOXSURV, CTR_ROOTS, CTR_FEATS_EE, CTR_ROOTS_EE
         CK(cudaMemsetAsync(c->flags.p, 0, (size_t)N * sizeof(int), c->stream));
         CK(cudaMemsetAsync(c->cnt.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
         CK(cudaMemsetAsync(c->cnt_rg.p, 0, c->nbody * sizeof(int), c->stream));
@@ -807,8 +821,14 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
             CK(c->pair_hit.reserve(c->pairs.n / 32 + 2));
             redo = true;
         }
-        if (h[CTR_FEATS] > c->feats.n) { CK(c->feats.reserve((size_t)(h[CTR_FEATS] * 5 / 4 + 1024))); redo = true; }
-        if (h[CTR_ROOTS] > c->rootrecs.n) { CK(c->rootrecs.reserve((size_t)(h[CTR_ROOTS] * 5 / 4 + 1024))); redo = true; }
+        if (h[CTR_FEATS] + h[CTR_FEATS_EE] > c->feats.n) {
+            CK(c->feats.reserve((size_t)((h[CTR_FEATS] + h[CTR_FEATS_EE]) * 5 / 4 + 1024)));
+            redo = true;
+        }
+        if (h[CTR_ROOTS] + h[CTR_ROOTS_EE] > c->rootrecs.n) {
+            CK(c->rootrecs.reserve((size_t)((h[CTR_ROOTS] + h[CTR_ROOTS_EE]) * 5 / 4 + 1024)));
+            redo = true;
+        }
         if (h[CTR_PREC] > c->prec.n) {
             size_t want = (size_t)(h[CTR_PREC] * 5 / 4 + 1024);
             CK(c->prec.reserve(want)); CK(c->perm.reserve(want)); CK(c->perm_sorted.reserve(want)); CK(c->skey.reserve(want));
@@ -825,9 +845,9 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
             st->true_pairs = (int64_t)h[CTR_TRUE];
             st->contacts = (int64_t)h[CTR_CONTACTS];
             st->contributions = (int64_t)(h[CTR_PREC] + h[CTR_BREC]);
-            st->features = (int64_t)h[CTR_FEATS];
+            st->features = (int64_t)(h[CTR_FEATS] + h[CTR_FEATS_EE]);
             st->box_survivors = (int64_t)h[CTR_BOXSURV];
-            st->coplanar = (int64_t)h[CTR_ROOTS];
+            st->coplanar = (int64_t)(h[CTR_ROOTS] + h[CTR_ROOTS_EE]);
         }
         c->last_nprec = (long long)h[CTR_PREC];
         c->last_nbrec = (long long)h[CTR_BREC];
