@@ -321,51 +321,101 @@ k_roots(const FeatRec* __restrict__ feats, long long cap_feats, const Vec4* __re
     }
 }
 
-// Stage 3: static tests at the root times (CCD) or at x_old (proximity) + impulse records.
+#define CONTACT_QCAP 64
+
+template <bool MOVING>
+__device__ __forceinline__ void load_contact_item(const FeatRec* __restrict__ feats, const RootRec* __restrict__ rootrecs, long long at,
+                                                  const Vec4* __restrict__ xo, const Vec4* __restrict__ av,
+                                                  const uint8_t* __restrict__ vflags, FeatRec& fr, Quad& q, double& r0, double& r1, double& r2)
+{
+    r0 = r1 = r2 = 0;
+    if (MOVING) {
+        fr = load_featrec(&rootrecs[at].f);
+        const double* r = reinterpret_cast<const double*>(rootrecs + at) + 3;
+        r0 = __ldg(r); r1 = __ldg(r + 1); r2 = __ldg(r + 2);
+    } else {
+        fr = load_featrec(feats + at);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        q.id[i] = fr.id[i];
+        const Vec4 x = ldg_vec4(xo + fr.id[i]), v = ldg_vec4(av + fr.id[i]);
+        q.xo[i][0] = x.x; q.xo[i][1] = x.y; q.xo[i][2] = x.z;
+        q.av[i][0] = v.x; q.av[i][1] = v.y; q.av[i][2] = v.z;
+        q.flags[i] = __ldg(vflags + fr.id[i]);
+        q.body[i] = 0;
+    }
+}
+
+// Stage 3: static tests at the root times (CCD) or at x_old (proximity), then impulse records.
+// Two phases per warp: (1) every lane finds the first time at which its feature fires (decision only) and
+// pushes (list index, time) to a per-warp shared-memory queue; (2) whenever 32 hits are queued the whole
+// warp turns them into contact + impulse records -- the expensive response code runs with all lanes
+// busy instead of the ~15 % that hit.
 template <bool MOVING>
 __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS)
 k_contact(const FeatRec* __restrict__ feats, const RootRec* __restrict__ rootrecs, long long cap_in, const int2* __restrict__ pairs,
           const Vec4* __restrict__ xo, const Vec4* __restrict__ av, const uint8_t* __restrict__ vflags,
           const int* __restrict__ vbody, NarrowParams P, Emit E, unsigned* __restrict__ pair_hit)
 {
+    __shared__ long long s_at[FEAT_THREADS / 32][CONTACT_QCAP];
+    __shared__ double s_time[FEAT_THREADS / 32][CONTACT_QCAP];
+    __shared__ int s_n[FEAT_THREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long n_pt = (long long)E.counters[MOVING ? CTR_ROOTS : CTR_FEATS];
     const long long n_ee = (long long)E.counters[MOVING ? CTR_ROOTS_EE : CTR_FEATS_EE];
     if (n_pt + n_ee > cap_in) return;  // overflow: the host grows the list and repeats the pass
     const long long n = n_pt + n_ee;
     const double h = MOVING ? P.eps : P.thickness;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-        const long long at = t < n_pt ? t : cap_in - 1 - (t - n_pt);
-        FeatRec fr;
-        double r0 = 0, r1 = 0, r2 = 0;
-        if (MOVING) {
-            fr = load_featrec(&rootrecs[at].f);
-            const double* r = reinterpret_cast<const double*>(rootrecs + at) + 3;
-            r0 = __ldg(r); r1 = __ldg(r + 1); r2 = __ldg(r + 2);
-        } else {
-            fr = load_featrec(feats + at);
+    if (lane == 0) s_n[w] = 0;
+    __syncwarp();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); ; t0 += stride) {
+        const long long t = t0 + lane;
+        if (t0 < n && t < n) {
+            const long long at = t < n_pt ? t : cap_in - 1 - (t - n_pt);
+            FeatRec fr;
+            Quad q;
+            double r0, r1, r2;
+            load_contact_item<MOVING>(feats, rootrecs, at, xo, av, vflags, fr, q, r0, r1, r2);
+            const double th = feature_first_hit<MOVING>(P, E, q, fr.edge != 0, h, r0, r1, r2);
+            if (th >= 0) {
+                const int pos = atomicAdd(&s_n[w], 1);
+                s_at[w][pos] = at;
+                s_time[w][pos] = th;
+            }
         }
-        const unsigned pi = fr.entry & 0x0fffffffu;
-        const int f = (int)(fr.entry >> 28);
-        const int2 pr = __ldg(pairs + pi);
-        Quad q;
+        __syncwarp();
+        const bool done = t0 + stride >= n;  // no further round for this warp
+        int nq = s_n[w];
+        while (nq >= 32 || (done && nq > 0)) {
+            const int take = nq < 32 ? nq : 32;
+            const int base = nq - take;
+            if (lane < take) {
+                const long long at = s_at[w][base + lane];
+                const double th = s_time[w][base + lane];
+                FeatRec fr;
+                Quad q;
+                double r0, r1, r2;
+                load_contact_item<MOVING>(feats, rootrecs, at, xo, av, vflags, fr, q, r0, r1, r2);
+                if ((q.flags[0] & 3) && (q.flags[1] & 3) && (q.flags[2] & 3) && (q.flags[3] & 3)) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            q.id[i] = fr.id[i];
-            const Vec4 x = ldg_vec4(xo + fr.id[i]), v = ldg_vec4(av + fr.id[i]);
-            q.xo[i][0] = x.x; q.xo[i][1] = x.y; q.xo[i][2] = x.z;
-            q.av[i][0] = v.x; q.av[i][1] = v.y; q.av[i][2] = v.z;
-            q.flags[i] = __ldg(vflags + fr.id[i]);
-            q.body[i] = 0;
+                    for (int i = 0; i < 4; ++i) q.body[i] = __ldg(vbody + q.id[i]);
+                }
+                const unsigned pi = fr.entry & 0x0fffffffu;
+                const int f = (int)(fr.entry >> 28);
+                const int2 pr = __ldg(pairs + pi);
+                const unsigned long long key = ((unsigned long long)(unsigned)pr.x << 34) | ((unsigned long long)(unsigned)pr.y << 4) |
+                                               (unsigned long long)f;
+                feature_emit<MOVING>(P, E, q, key, fr.edge != 0, h, th);
+                atomicOr(pair_hit + (pi >> 5), 1u << (pi & 31));
+            }
+            nq = base;
+            __syncwarp();
         }
-        if ((q.flags[0] & 3) && (q.flags[1] & 3) && (q.flags[2] & 3) && (q.flags[3] & 3)) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) q.body[i] = __ldg(vbody + q.id[i]);
-        }
-        const unsigned long long key = ((unsigned long long)(unsigned)pr.x << 34) | ((unsigned long long)(unsigned)pr.y << 4) |
-                                       (unsigned long long)f;
-        const bool edge = fr.edge != 0;
-        const bool hit = MOVING ? feature_at_roots(P, E, q, key, edge, h, r0, r1, r2) : feature_static(P, E, q, key, edge, h);
-        if (hit) atomicOr(pair_hit + (pi >> 5), 1u << (pi & 31));
+        if (lane == 0) s_n[w] = nq;
+        __syncwarp();
+        if (done) break;
     }
 }
 

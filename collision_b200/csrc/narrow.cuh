@@ -150,7 +150,7 @@ __device__ __forceinline__ void emit_body(const Emit& E, unsigned long long key,
 }
 
 // PointToTriImpulse, dcollid3d.cpp:925-1107.  q: 0..2 triangle, 3 point.  w is modified as in the reference.
-__device__ __noinline__ void point_to_tri_impulse(const NarrowParams& P, const Emit& E, const Quad& q,
+__device__ __forceinline__ void point_to_tri_impulse(const NarrowParams& P, const Emit& E, const Quad& q,
                                                       unsigned long long key, const double* nor, double* w, double dist)
 {
     double v_rel[3] = {0.0, 0.0, 0.0}, vn, vt;
@@ -243,7 +243,7 @@ __device__ __noinline__ void point_to_tri_impulse(const NarrowParams& P, const E
 }
 
 // EdgeToEdgeImpulse, dcollid3d.cpp:1109-1300.  q: edge 0-1 against edge 2-3.
-__device__ __noinline__ void edge_to_edge_impulse(const NarrowParams& P, const Emit& E, const Quad& q,
+__device__ __forceinline__ void edge_to_edge_impulse(const NarrowParams& P, const Emit& E, const Quad& q,
                                                       unsigned long long key, const double* nor, double a, double b, double dist)
 {
     double v_rel[3], vn, vt;
@@ -319,6 +319,9 @@ __device__ __noinline__ void edge_to_edge_impulse(const NarrowParams& P, const E
 }
 
 // PointToTri, dcollid3d.cpp:778-922.  X = positions at test time.
+// EMIT = false: decision only (no records, no counters) -- used to find the first hit of a feature;
+// EMIT = true: the same arithmetic followed by the contact record and the impulse.
+template <bool EMIT>
 __device__ __forceinline__ bool point_to_tri(const NarrowParams& P, const Emit& E, const Quad& q, unsigned long long key,
                                               const double X[4][3], double h, double root)
 {
@@ -360,19 +363,22 @@ __device__ __forceinline__ bool point_to_tri(const NarrowParams& P, const Emit& 
 #pragma unroll
         for (int i = 0; i < 3; ++i) nor[i] /= nor_mag;
     } else {
-        atomicAdd(&E.counters[CTR_ERROR], 1ull);  // reference: clean_up(ERROR)
+        if (!EMIT) atomicAdd(&E.counters[CTR_ERROR], 1ull);  // reference: clean_up(ERROR)
         return false;
     }
     if (dist > h) return false;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
         if (w[i] > 1 + P.eps || w[i] < -P.eps) return false;
-    emit_contact(E, make_int4(q.id[0], q.id[1], q.id[2], q.id[3]), key, 0, root, dist, nor[0], nor[1], nor[2], w[0], w[1], w[2]);
-    point_to_tri_impulse(P, E, q, key, nor, w, dist);
+    if (EMIT) {
+        emit_contact(E, make_int4(q.id[0], q.id[1], q.id[2], q.id[3]), key, 0, root, dist, nor[0], nor[1], nor[2], w[0], w[1], w[2]);
+        point_to_tri_impulse(P, E, q, key, nor, w, dist);
+    }
     return true;
 }
 
 // EdgeToEdge, dcollid3d.cpp:643-776
+template <bool EMIT>
 __device__ __forceinline__ bool edge_to_edge(const NarrowParams& P, const Emit& E, const Quad& q, unsigned long long key,
                                               const double X[4][3], double h, double root)
 {
@@ -412,13 +418,15 @@ __device__ __forceinline__ bool edge_to_edge(const NarrowParams& P, const Emit& 
     if (dist > h) return false;
     nor_mag = mag3(nor);
     if (nor_mag < CLSN_MACH_EPS) {
-        atomicAdd(&E.counters[CTR_ERROR], 1ull);  // reference: clean_up(ERROR)
+        if (!EMIT) atomicAdd(&E.counters[CTR_ERROR], 1ull);  // reference: clean_up(ERROR)
         return false;
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) nor[i] /= nor_mag;
-    emit_contact(E, make_int4(q.id[0], q.id[1], q.id[2], q.id[3]), key, 1, root, dist, nor[0], nor[1], nor[2], a, b, 0.0);
-    edge_to_edge_impulse(P, E, q, key, nor, a, b, dist);
+    if (EMIT) {
+        emit_contact(E, make_int4(q.id[0], q.id[1], q.id[2], q.id[3]), key, 1, root, dist, nor[0], nor[1], nor[2], a, b, 0.0);
+        edge_to_edge_impulse(P, E, q, key, nor, a, b, dist);
+    }
     return true;
 }
 
@@ -594,35 +602,48 @@ __device__ __forceinline__ bool is_coplanar(const Quad& q, double dt, double* ro
     return roots[0] > CLSN_MACH_EPS || roots[1] > CLSN_MACH_EPS || roots[2] > CLSN_MACH_EPS;
 }
 
-// one static feature test (proximity: TriToTri/TriToBond/BondToBond call these at x_old with h = thickness)
-__device__ __forceinline__ bool feature_static(const NarrowParams& P, const Emit& E, const Quad& q, unsigned long long key,
-                                                bool edge, double h)
+// positions of the four points at time t (CCD: x_old + t * avgVel, dcollid3d.cpp:338; proximity: x_old)
+template <bool MOVING>
+__device__ __forceinline__ void positions_at(const Quad& q, double t, double X[4][3])
 {
-    double X[4][3];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) X[j][k] = q.xo[j][k];
-    return edge ? edge_to_edge(P, E, q, key, X, h, 0.0) : point_to_tri(P, E, q, key, X, h, 0.0);
+        for (int k = 0; k < 3; ++k) X[j][k] = MOVING ? q.xo[j][k] + t * q.av[j][k] : q.xo[j][k];
 }
 
 // MovingPointToTri / MovingEdgeToEdge (dcollid3d.cpp:327-369), second half: walk the sorted roots
-// (invalid = -1) and then t = dt, stop at the first static hit.
-__device__ __forceinline__ bool feature_at_roots(const NarrowParams& P, const Emit& E, const Quad& q, unsigned long long key,
-                                                  bool edge, double h, double r0, double r1, double r2)
+// (invalid = -1) and then t = dt; the first time at which the static test fires wins.  Returns that time
+// (>= 0) or -1.  Decision only: the contact record and the impulse are produced later, by
+// feature_emit() at the returned time, with all lanes of a warp busy.
+template <bool MOVING>
+__device__ __forceinline__ double feature_first_hit(const NarrowParams& P, const Emit& E, const Quad& q, bool edge, double h,
+                                                     double r0, double r1, double r2)
 {
     double X[4][3];
+    if (!MOVING) {
+        positions_at<false>(q, 0.0, X);
+        const bool hit = edge ? edge_to_edge<false>(P, E, q, 0ull, X, h, 0.0) : point_to_tri<false>(P, E, q, 0ull, X, h, 0.0);
+        return hit ? 0.0 : -1.0;
+    }
     for (int i = 0; i < 4; ++i) {
         const double t = i == 0 ? r0 : (i == 1 ? r1 : (i == 2 ? r2 : P.dt));
         if (t < 0) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int k = 0; k < 3; ++k) X[j][k] = q.xo[j][k] + t * q.av[j][k];
-        const bool hit = edge ? edge_to_edge(P, E, q, key, X, h, t) : point_to_tri(P, E, q, key, X, h, t);
-        if (hit) return true;
+        positions_at<true>(q, t, X);
+        const bool hit = edge ? edge_to_edge<false>(P, E, q, 0ull, X, h, t) : point_to_tri<false>(P, E, q, 0ull, X, h, t);
+        if (hit) return t;
     }
-    return false;
+    return -1.0;
+}
+
+template <bool MOVING>
+__device__ __forceinline__ void feature_emit(const NarrowParams& P, const Emit& E, const Quad& q, unsigned long long key, bool edge,
+                                             double h, double t)
+{
+    double X[4][3];
+    positions_at<MOVING>(q, t, X);
+    if (edge) edge_to_edge<true>(P, E, q, key, X, h, t);
+    else point_to_tri<true>(P, E, q, key, X, h, t);
 }
 
 } // namespace clsn
