@@ -205,7 +205,7 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
         __syncwarp();
         for (int k0 = 0; k0 < total; k0 += 32) {
             const int k = k0 + lane;
-            bool keep = false;
+            bool keep = false, back = false;  // back: list end (CCD: non-trig cubic branches; proximity: edge-edge)
             FeatRec rec;
             rec.entry = 0; rec.edge = 0;
             rec.id[0] = rec.id[1] = rec.id[2] = rec.id[3] = 0;
@@ -235,6 +235,7 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) rec.id[i] = s_id[wb + o][sl[i]];
+                if (!MOVING) back = rec.edge != 0;
                 if (MOVING) {
                     Quad q;
 #pragma unroll
@@ -246,14 +247,17 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
                         }
                     double ca, cb, cc, cd;
                     coplanar_coeffs(q, ca, cb, cc, cd);
-                    keep = coplanar_maybe(ca, cb, cc, cd, P.dt);
+                    const int kindc = coplanar_maybe(ca, cb, cc, cd, P.dt);
+                    keep = kindc != 0;
+                    back = kindc == 2;
                 }
             }
-            // point-triangle entries fill the list from the front, edge-edge entries from the back, so that
-            // the consumers' warps run one kind of test each
+            // two kinds of entries, one filling the list from the front and one from the back, so that the
+            // consumer's warps are homogeneous: proximity -> point-triangle | edge-edge (k_contact);
+            // CCD -> trig branch | other branches of the cubic (k_roots, which re-splits by test kind)
 #pragma unroll
             for (int kind = 0; kind < 2; ++kind) {
-                const bool mine = keep && (rec.edge != 0) == (kind == 1);
+                const bool mine = keep && back == (kind == 1);
                 const unsigned ballot = __ballot_sync(0xffffffffu, mine);
                 if (!ballot) continue;
                 unsigned long long slot0 = 0;

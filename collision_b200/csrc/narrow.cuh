@@ -471,7 +471,8 @@ __device__ __forceinline__ void coplanar_coeffs(const Quad& q, double& a, double
 // of the sum and of /3 (<= 1e-15), and the two roundings of the root formula (eta).  DESIGN.md.
 // One-real-root branch: root = A + B - a/3 with A = -sgn * pow(u, 1/3); cbrt() is within 1.5e-14
 // relative of the correctly rounded pow over the whole double range, covered by a 1e-13 guard.
-__device__ __forceinline__ bool coplanar_maybe(double a, double b, double c, double d, double dt)
+// Returns 0 = no valid root possible, 1 = maybe (three-real-root / trig branch), 2 = maybe (other branches).
+__device__ __forceinline__ int coplanar_maybe(double a, double b, double c, double d, double dt)
 {
     if (fabs(a) > CLSN_MACH_EPS) {
         b /= a; c /= a; d /= a;
@@ -482,7 +483,7 @@ __device__ __forceinline__ bool coplanar_maybe(double a, double b, double c, dou
         if (R2 < Q3) {
             const double S = 2 * sqrt(Q);
             const double x = R / sqrt(Q3);
-            if (!(fabs(x) <= 1.0) || !(S > 0.0)) return true;  // acos domain edge / NaN: let the exact path decide
+            if (!(fabs(x) <= 1.0) || !(S > 0.0)) return 1;  // acos domain edge / NaN: let the exact path decide
             const double A3 = a / 3;
             const double eta = 4e-16 * (2 * S + fabs(A3) + dt) + 2 * CLSN_MACH_EPS;
             double u = -(dt + A3 + eta) / S;
@@ -490,18 +491,18 @@ __device__ __forceinline__ bool coplanar_maybe(double a, double b, double c, dou
             const double delta = 4e-15 + 4e-16 * (fabs(u) + fabs(v));
             u -= delta;
             v += delta;
-            if (u > 1.0 || v < -1.0) return false;  // the cosines live in [-1, 1]
+            if (u > 1.0 || v < -1.0) return 0;  // the cosines live in [-1, 1]
             u = fmax(u, -1.0);
             v = fmin(v, 1.0);
             const double tu = u * (4 * u * u - 3), tv = v * (4 * v * v - 3);
             double tmin = fmin(tu, tv), tmax = fmax(tu, tv);
             if (u <= -0.5 && v >= -0.5) tmax = 1.0;   // interior maximum of T3 at c = -1/2
             if (u <= 0.5 && v >= 0.5) tmin = -1.0;    // interior minimum at c = +1/2
-            return !(x < tmin - 4e-14 || x > tmax + 4e-14);
+            return !(x < tmin - 4e-14 || x > tmax + 4e-14) ? 1 : 0;
         }
         const double sgn = (R > 0) ? 1.0 : -1.0;
         const double A = -sgn * cbrt(fabs(R) + sqrt(R2 - Q3));
-        if (!(fabs(fabs(A) - CLSN_ROUND_EPS) > 1e-20)) return true;  // the |A| < 1e-10 switch could flip
+        if (!(fabs(fabs(A) - CLSN_ROUND_EPS) > 1e-20)) return 2;  // the |A| < 1e-10 switch could flip
         const double Bv = (fabs(A) < CLSN_ROUND_EPS) ? 0.0 : Q / A;
         const double g = (fabs(A) + fabs(Bv) + fabs(a)) * 1e-13;
         const double r0 = (A + Bv) - a / 3.0;
@@ -510,7 +511,7 @@ __device__ __forceinline__ bool coplanar_maybe(double a, double b, double c, dou
             const double rr = -0.5 * (A + Bv) - a / 3.0;
             maybe = maybe || !(rr < -g || rr > dt + g);
         }
-        return maybe;
+        return maybe ? 2 : 0;
     }
     // quadratic / linear fall-backs use IEEE operations only: evaluate them as the reference does
     a = b; b = c; c = d;
@@ -526,7 +527,7 @@ __device__ __forceinline__ bool coplanar_maybe(double a, double b, double c, dou
     r0 -= CLSN_MACH_EPS;
     r1 -= CLSN_MACH_EPS;
     const bool ok0 = !(r0 < 0 || r0 > dt), ok1 = !(r1 < 0 || r1 > dt);
-    return ok0 || ok1;
+    return (ok0 || ok1) ? 2 : 0;
 }
 
 // isCoplanar, dcollid3d.cpp:371-482.  Returns true iff some root > MACH_EPS; roots[0..2] sorted.
