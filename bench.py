@@ -251,6 +251,7 @@ def run_b200(args):
         for k, v in st.get("ms_phase", {}).items():
             phase_ms[k] = phase_ms.get(k, 0.0) + v
     ms = solver.timer_stop()
+    log("per-pass stats of the last step:", json.dumps({"proximity": st["proximity"], "ccd": st["ccd"]}))
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
     launches = solver.launch_count()

@@ -100,8 +100,11 @@ __device__ __forceinline__ bool boxes_far(const FBox& a, const FBox& b, float h2
 // of every pair are staged in shared memory, one row per pair), each lane computes the coefficients of
 // the coplanarity cubic and runs the trig-free classifier coplanar_maybe().  Features that can still
 // fire are appended to the work list as (pair index | feature << 28).
+#ifndef CULL_MIN_BLOCKS
+#define CULL_MIN_BLOCKS 4
+#endif
 template <bool MOVING>
-__global__ void __launch_bounds__(CULL_THREADS, 4)
+__global__ void __launch_bounds__(CULL_THREADS, CULL_MIN_BLOCKS)
 k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restrict__ elem, const Vec4* __restrict__ xo,
        const Vec4* __restrict__ av, NarrowParams P, FeatRec* __restrict__ feats, long long cap_feats,
        unsigned long long* counters)
@@ -290,7 +293,10 @@ __device__ __forceinline__ FeatRec load_featrec(const FeatRec* p)
 // Stage 2 (CCD): correctly rounded solve of the coplanarity cubic for every feature the classifier
 // let through.  Only positions and velocities are needed here; the kernel is nothing but the
 // double-double math, which keeps its instruction footprint small.
-__global__ void __launch_bounds__(FEAT_THREADS, 5)
+#ifndef ROOTS_MIN_BLOCKS
+#define ROOTS_MIN_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(FEAT_THREADS, ROOTS_MIN_BLOCKS)
 k_roots(const FeatRec* __restrict__ feats, long long cap_feats, const Vec4* __restrict__ xo, const Vec4* __restrict__ av, double dt,
         RootRec* __restrict__ out, long long cap_out, unsigned long long* counters)
 {
@@ -473,7 +479,9 @@ struct clsn_ctx {
     RigidTopo rigid;
     // state
     DevBuf<Vec4> xo, xn, av;
-    DevBuf<uint8_t> has;
+    DevBuf<uint8_t> has, dirty;
+    bool dirty_valid = false;   // dirty[] describes exactly the change between the last two CCD passes
+    int last_detect_mode = -1;
     DevBuf<double> imp_rg;
     DevBuf<int> cnt_rg;
     DevBuf<double> stage;  // 3V doubles, host<->device staging of packed arrays
@@ -586,7 +594,7 @@ extern "C" void clsn_destroy(clsn_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->elem.release(); c->vflags.release(); c->vbody.release(); c->body_mass.release();
-    c->xo.release(); c->xn.release(); c->av.release(); c->has.release(); c->imp_rg.release(); c->cnt_rg.release();
+    c->xo.release(); c->xn.release(); c->av.release(); c->has.release(); c->dirty.release(); c->imp_rg.release(); c->cnt_rg.release();
     c->stage.release(); c->code.release(); c->code_sorted.release(); c->idx.release(); c->leaf_elem.release();
     c->leaf_parent.release(); c->flags.release(); c->nodes.release(); c->lbox.release(); c->bounds.release();
     c->cub_tmp.release(); c->pairs.release(); c->dbg_cand.release(); c->feats.release(); c->pair_hit.release(); c->rootrecs.release(); c->prec.release(); c->brec.release();
@@ -667,7 +675,7 @@ extern "C" int clsn_set_topology(clsn_ctx* c, int V, int T, const int32_t* tri_i
     CK(cudaMemcpy(c->vflags.p, vflags, V, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->vbody.p, vbody, V * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->body_mass.p, body_mass, nbody * sizeof(double), cudaMemcpyHostToDevice));
-    CK(c->xo.reserve(V)); CK(c->xn.reserve(V)); CK(c->av.reserve(V)); CK(c->has.reserve(V));
+    CK(c->xo.reserve(V)); CK(c->xn.reserve(V)); CK(c->av.reserve(V)); CK(c->has.reserve(V)); CK(c->dirty.reserve(V));
     CK(c->imp_rg.reserve(3 * (size_t)nbody)); CK(c->cnt_rg.reserve(nbody));
     CK(cudaMemset(c->imp_rg.p, 0, 3 * (size_t)nbody * sizeof(double)));
     CK(cudaMemset(c->cnt_rg.p, 0, nbody * sizeof(int)));
@@ -710,6 +718,8 @@ static int begin_step(clsn_ctx* c)
     CK(cudaMemsetAsync(c->has.p, 0, c->V, c->stream));
     c->tree_built = false;
     c->records_pending = false;
+    c->dirty_valid = false;
+    c->last_detect_mode = -1;
     return CLSN_OK;
 }
 
@@ -771,6 +781,7 @@ extern "C" int clsn_set_avgvel(clsn_ctx* c, const double* avgvel)
     k_pack<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->stage.p, c->av.p);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
+    c->dirty_valid = false;
     return CLSN_OK;
 }
 
@@ -782,6 +793,7 @@ extern "C" int clsn_avg_velocity(clsn_ctx* c)
     k_avg_velocity<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->xo.p, c->xn.p, c->av.p, c->prm.dt, c->counters.p);
     CK(cudaGetLastError());
     c->launches += 1;
+    c->dirty_valid = false;
     mark(c, PH_AVG);
     return CLSN_OK;
 }
@@ -836,6 +848,8 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
         to.pairs = c->pairs.p; to.cap_pairs = (long long)c->pairs.n;
         to.dbg_cand = c->dbg_candidates ? c->dbg_cand.p : nullptr; to.cap_dbg = (long long)c->dbg_cand.n;
         to.counters = c->counters.p;
+        // pairs whose points did not change since the previous CCD pass repeat their (hit-free) outcome
+        to.dirty = (moving && c->dirty_valid && c->last_detect_mode == CLSN_COLLISION) ? c->dirty.p : nullptr;
         if (q_hi > q_lo)
             k_traverse<<<nblk(q_hi - q_lo, 128), 128, 0, c->stream>>>(c->nodes.p, c->lbox.p, c->leaf_elem.p, c->elem.p, N, q_lo, q_hi, to);
         c->launches += (q_hi > q_lo) ? 1 : 0;
@@ -909,6 +923,8 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
         c->n_contacts = (long long)h[CTR_CONTACTS];
         c->records_pending = true;
         c->imp_nprec = -1;
+        c->last_detect_mode = mode;
+        c->dirty_valid = false;  // becomes valid again once these records have been applied
         return CLSN_OK;
     }
     return fail(c, CLSN_E_NOMEM, "pair/record buffers kept overflowing");
@@ -957,8 +973,8 @@ static int reduce_records(clsn_ctx* c, int mode)
             CK(cudaMemsetAsync(c->acc_fric.p, 0, 3 * (size_t)V * sizeof(double), c->stream));
         }
         k_reduce_points<<<c->sm_count * 8, 256, 0, c->stream>>>(prec, c->offs.p, c->cnt.p, V, c->perm.p, c->perm_sorted.p, c->skey.p,
-                                                                  c->vflags.p, c->av.p, c->has.p, mode, c->acc_imp.p, c->acc_fric.p,
-                                                                  c->counters.p);
+                                                                  c->vflags.p, c->av.p, c->has.p, c->dirty.p, mode, c->acc_imp.p,
+                                                                  c->acc_fric.p, c->counters.p);
         c->launches += 2 + 2;  // scan (init + scan), scatter, reduce
     } else if (mode == 1) {
         CK(c->acc_imp.reserve(3 * (size_t)V)); CK(c->acc_fric.reserve(3 * (size_t)V));
@@ -979,19 +995,22 @@ extern "C" int clsn_apply(clsn_ctx* c, int rigidify)
     if (!c || !c->V) return CLSN_E_ARG;
     cudaSetDevice(c->device);
     if (c->records_pending) {
+        k_reset_dirty<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->vflags.p, c->dirty.p);
+        c->launches += 1;
         int r = reduce_records(c, 0);
         if (r) return r;
         const long long nbrec = c->imp_nprec >= 0 ? c->imp_nbrec : c->last_nbrec;
         if (nbrec > 0 || c->has_movable) {
             // cnt_rg > 0 can also persist from set_body_accumulators (parity tests)
             k_apply_bodies<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->vflags.p, c->vbody.p, c->imp_rg.p, c->cnt_rg.p,
-                                                                    c->av.p, c->has.p);
+                                                                    c->av.p, c->has.p, c->dirty.p);
             CK(cudaMemsetAsync(c->cnt_rg.p, 0, c->nbody * sizeof(int), c->stream));
             c->launches += 1;
         }
         CK(cudaMemsetAsync(c->cnt.p, 0, ((size_t)c->V + 1) * sizeof(int), c->stream));
         c->records_pending = false;
         c->imp_nprec = -1;
+        c->dirty_valid = true;
     }
     if (rigidify && c->has_movable && c->prm.dt > 0.0) {
         int r = c->rigid.rigidify(c->xo.p, c->av.p, c->vflags.p, c->prm.m, c->prm.dt, c->counters.p, c->stream);

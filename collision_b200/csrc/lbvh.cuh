@@ -252,6 +252,7 @@ struct TraverseOut {
     int2* dbg_cand;         // every overlapping pair (debug / parity), may be null
     long long cap_dbg;
     unsigned long long* counters;
+    const uint8_t* dirty;   // non-null: drop pairs none of whose points changed since the previous CCD pass
 };
 
 #define TRAV_THREADS 128
@@ -350,6 +351,16 @@ k_traverse(const WideNode* __restrict__ nodes, const double* __restrict__ lbox, 
                     if (emit && me.z >= 0 && ot.z >= 0) {
                         const int4 ea = my_id < other_id ? me : ot;
                         if (((me.w ^ ot.w) & 0x0fffffff) == 0 && (ea.w & 0x10000000)) emit = false;
+                    }
+                    // A feature test is a pure function of (x_old, avgVel) of its points.  If no point of the pair
+                    // was touched by the previous pass's updateAverageVelocity, every test repeats its previous
+                    // outcome, and that outcome was "no hit" (a hit would have changed one of the points; fixed and
+                    // rigid-body points always count as touched).  Such pairs contribute nothing: skip them.
+                    if (emit && out.dirty) {
+                        unsigned d = out.dirty[me.x] | out.dirty[me.y] | out.dirty[ot.x] | out.dirty[ot.y];
+                        if (me.z >= 0) d |= out.dirty[me.z];
+                        if (ot.z >= 0) d |= out.dirty[ot.z];
+                        if (!d) emit = false;
                     }
                 }
             }

@@ -44,7 +44,7 @@ __global__ void k_count_records(const PointRec* __restrict__ prec, long long npr
 __global__ void __launch_bounds__(256)
 k_reduce_points(const PointRec* __restrict__ rec, const int* __restrict__ offs, const int* __restrict__ cnt, int V,
                 const int* __restrict__ perm, int* __restrict__ perm_sorted, const unsigned long long* __restrict__ skey,
-                const uint8_t* __restrict__ vflags, Vec4* av, uint8_t* has, int mode, double* __restrict__ acc_imp,
+                const uint8_t* __restrict__ vflags, Vec4* av, uint8_t* has, uint8_t* dirty, int mode, double* __restrict__ acc_imp,
                 double* __restrict__ acc_fric, unsigned long long* counters)
 {
     const int lane = threadIdx.x & 31;
@@ -76,7 +76,7 @@ k_reduce_points(const PointRec* __restrict__ rec, const int* __restrict__ offs, 
                 const double v = *a + (sum + fr) / n;
                 *a = v;
                 if (isinf(v) || isnan(v)) atomicAdd(&counters[CTR_ERROR], 1ull);
-                if (lane == 0) has[p] = 1;
+                if (lane == 0) { has[p] = 1; dirty[p] = 1; }
             }
         } else if (lane < 6) {
             if (lane < 3) acc_imp[3 * (size_t)p + lane] = sum;
@@ -121,7 +121,8 @@ __global__ void k_reduce_bodies(const BodyRec* __restrict__ rec, const unsigned 
 // updateAverageVelocity :726-733: avgVel += collsnImpulse_RG / collsn_num_RG for every non-static
 // point of a body that was hit this pass
 __global__ void k_apply_bodies(int V, const uint8_t* __restrict__ vflags, const int* __restrict__ vbody,
-                               const double* __restrict__ imp_rg, const int* __restrict__ cnt_rg, Vec4* av, uint8_t* has)
+                               const double* __restrict__ imp_rg, const int* __restrict__ cnt_rg, Vec4* av, uint8_t* has,
+                               uint8_t* dirty)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= V) return;
@@ -130,11 +131,19 @@ __global__ void k_apply_bodies(int V, const uint8_t* __restrict__ vflags, const 
     const int n = cnt_rg[b];
     if (n <= 0) return;
     has[p] = 1;
+    dirty[p] = 1;
     Vec4 v = av[p];
     v.x += imp_rg[3 * b] / n;
     v.y += imp_rg[3 * b + 1] / n;
     v.z += imp_rg[3 * b + 2] / n;
     av[p] = v;
+}
+
+// start-of-apply state of the 'touched' flags: fixed and rigid-body points always count as touched
+__global__ void k_reset_dirty(int V, const uint8_t* __restrict__ vflags, uint8_t* __restrict__ dirty)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < V) dirty[p] = (vflags[p] & 3) ? 1 : 0;
 }
 
 // computeAverageVelocity, dcollid.cpp:160-220

@@ -72,9 +72,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if _build.needs_build():
-        path = _build.build()
+    path = os.environ.get("CLSN_LIB")  # tuning experiments only: an alternative build of the same sources
+    if not path:
+        path = _build.LIB_PATH
+        if _build.needs_build():
+            path = _build.build()
     L = C.CDLL(path)
     P, D, I, V = C.POINTER, C.c_double, C.c_int, C.c_void_p
     L.clsn_create.argtypes = [P(V), I]
