@@ -462,7 +462,7 @@ struct DevBuf {
     }
 };
 
-enum { PH_AVG = 0, PH_BUILD, PH_REFIT, PH_TRAVERSE, PH_NARROW, PH_REDUCE, PH_FINAL, PH_OTHER, PH_COUNT };
+enum { PH_AVG = 0, PH_BUILD, PH_REFIT, PH_TRAVERSE, PH_CULL, PH_ROOTS, PH_CONTACT, PH_REDUCE, PH_FINAL, PH_OTHER, PH_COUNT };
 
 struct clsn_ctx {
     int device = 0;
@@ -739,9 +739,9 @@ extern "C" int clsn_upload_state(clsn_ctx* c, const double* x_old, const double*
     if (!c || !c->V || !x_old || !x_new) return CLSN_E_ARG;
     cudaSetDevice(c->device);
     const size_t n = 3 * (size_t)c->V;
-    memcpy(c->h_pin, x_old, n * sizeof(double));
-    memcpy(c->h_pin + n, x_new, n * sizeof(double));
-    CK(cudaMemcpyAsync(c->stage.p, c->h_pin, 2 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    // straight from the caller's arrays: a true async DMA when they are pinned, driver-staged otherwise
+    CK(cudaMemcpyAsync(c->stage.p, x_old, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->stage.p + n, x_new, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     return clsn_upload_state_device(c, c->stage.p, c->stage.p + n);
 }
 
@@ -763,12 +763,10 @@ extern "C" int clsn_download_state(clsn_ctx* c, double* x, double* avgvel, uint8
     const size_t n = 3 * (size_t)c->V;
     int r = clsn_download_state_device(c, x ? c->stage.p : nullptr, avgvel ? c->stage.p + n : nullptr);
     if (r) return r;
-    if (x) CK(cudaMemcpyAsync(c->h_pin, c->stage.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (avgvel) CK(cudaMemcpyAsync(c->h_pin + n, c->stage.p + n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (x) CK(cudaMemcpyAsync(x, c->stage.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (avgvel) CK(cudaMemcpyAsync(avgvel, c->stage.p + n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (has_collsn) CK(cudaMemcpyAsync(has_collsn, c->has.p, c->V, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    if (x) memcpy(x, c->h_pin, n * sizeof(double));
-    if (avgvel) memcpy(avgvel, c->h_pin + n, n * sizeof(double));
     return CLSN_OK;
 }
 
@@ -866,20 +864,23 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
         if (moving) {
             k_cull<true><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p, P,
                                                                 c->feats.p, (long long)c->feats.n, c->counters.p);
+            mark(c, PH_CULL);
             k_roots<<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P.dt, c->rootrecs.p,
                                                            (long long)c->rootrecs.n, c->counters.p);
+            mark(c, PH_ROOTS);
             k_contact<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, c->rootrecs.p, (long long)c->rootrecs.n, c->pairs.p,
                                                                    c->xo.p, c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
         } else {
             k_cull<false><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p, P,
                                                                  c->feats.p, (long long)c->feats.n, c->counters.p);
+            mark(c, PH_CULL);
             k_contact<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, c->rootrecs.p, (long long)c->feats.n, c->pairs.p,
                                                                     c->xo.p, c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
         }
         k_count_true<<<c->sm_count * 2, 256, 0, c->stream>>>(c->pair_hit.p, hit_words, c->counters.p);
         CK(cudaGetLastError());
         c->launches += moving ? 4 : 3;
-        mark(c, PH_NARROW);
+        mark(c, PH_CONTACT);
         CK(cudaMemcpyAsync(c->h_counters, c->counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         const unsigned long long* h = c->h_counters;
@@ -1096,16 +1097,11 @@ extern "C" int clsn_step_host(clsn_ctx* c, const double* x_old, const double* x_
     if ((r = clsn_upload_state(c, x_old, x_new))) return r;
     if ((r = clsn_resolve(c, stats))) return r;
     const size_t n = 3 * (size_t)c->V;
-    std::vector<uint8_t> has_local;
-    uint8_t* has = has_out;
-    if (!has && vel_inout) {
-        has_local.resize(c->V);
-        has = has_local.data();
-    }
+    // scratch for avgVel / has_collsn lives in the context's pinned buffer (3V doubles + V bytes)
+    double* av = c->h_pin;
+    uint8_t* has = has_out ? has_out : reinterpret_cast<uint8_t*>(c->h_pin + n);
     // avgVel only travels back when the caller wants velocities updated
-    std::vector<double> av;
-    if (vel_inout) av.resize(n);
-    if ((r = clsn_download_state(c, x_out, vel_inout ? av.data() : nullptr, has))) return r;
+    if ((r = clsn_download_state(c, x_out, vel_inout ? av : nullptr, (has_out || vel_inout) ? has : nullptr))) return r;
     if (vel_inout)  // updateFinalVelocity, dcollid.cpp:598-624
         for (int p = 0; p < c->V; ++p)
             if (has[p])

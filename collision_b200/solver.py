@@ -48,13 +48,13 @@ class clsn_pass_stats(C.Structure):
 class clsn_step_stats(C.Structure):
     _fields_ = [("proximity", clsn_pass_stats), ("n_ccd_passes", C.c_int32), ("has_collision", C.c_int32),
                 ("still_colliding", C.c_int32), ("reserved", C.c_int32), ("ccd", clsn_pass_stats * MAX_CCD_PASSES),
-                ("ms_total", C.c_float), ("ms_phase", C.c_float * 8)]
+                ("ms_total", C.c_float), ("ms_phase", C.c_float * 10)]
 
     def as_dict(self):
         return dict(proximity=self.proximity.as_dict(), n_ccd_passes=int(self.n_ccd_passes),
                     has_collision=bool(self.has_collision), still_colliding=bool(self.still_colliding),
                     ccd=[self.ccd[i].as_dict() for i in range(int(self.n_ccd_passes))], ms_total=float(self.ms_total),
-                    ms_phase=dict(zip(("avgvel", "build", "refit", "traverse", "narrow", "reduce", "finalize", "other"),
+                    ms_phase=dict(zip(("avgvel", "build", "refit", "traverse", "cull", "roots", "contact", "reduce", "finalize", "other"),
                                       [float(v) for v in self.ms_phase])))
 
 
@@ -266,16 +266,19 @@ class CollisionSolver3d:
             self._x_old[~keep] = x[~keep]
 
     # ---- the step
-    def resolveCollision(self, x_old, x, vel):
-        """x_old: start-of-step positions; x: candidate positions on entry, final positions on return;
-        vel: updated where has_collsn (updateFinalVelocity).  Returns has_collsn (V,) uint8."""
+    def resolveCollision(self, x_old, x, vel, x_out=None):
+        """x_old: start-of-step positions; x: candidate positions on entry, final positions on return
+        (or written to x_out when given); vel: updated where has_collsn (updateFinalVelocity).
+        Returns has_collsn (V,) uint8."""
         c = self.ctx
         self._push_params()
         assert x.dtype == np.float64 and x.flags.c_contiguous and vel.dtype == np.float64 and vel.flags.c_contiguous
         xo = np.ascontiguousarray(x_old, dtype=np.float64)
         has = np.zeros(c.V, dtype=np.uint8)
         st = clsn_step_stats()
-        c.check(c.L.clsn_step_host(c.h, _dp(xo), _dp(x), _dp(x), _dp(vel), _bp(has), C.byref(st)))
+        out = x if x_out is None else x_out
+        assert out.dtype == np.float64 and out.flags.c_contiguous
+        c.check(c.L.clsn_step_host(c.h, _dp(xo), _dp(x), _dp(out), _dp(vel), _bp(has), C.byref(st)))
         self.has_collision = bool(st.has_collision)
         self.last_stats = st.as_dict()
         return has

@@ -76,7 +76,7 @@ typedef struct {
     int32_t reserved;
     clsn_pass_stats ccd[CLSN_MAX_CCD_PASSES];
     float ms_total;             /* device time of the whole step (CUDA events)                     */
-    float ms_phase[8];          /* avgvel, build, refit, traverse, narrow, reduce, finalize, other */
+    float ms_phase[10];         /* avgvel, build, refit, traverse, cull, roots, contact, reduce, finalize, other */
 } clsn_step_stats;
 
 /* Contact record for parity checks (same layout as oracle/collision_oracle.h: orc_contact). */

@@ -48,6 +48,21 @@ def main():
         .replace("smsp__thread_inst_executed_per_inst_executed.ratio", "lanes") \
         .replace("launch__registers_per_thread", "regs").replace("dram__bytes_read.sum", "dram_rd") \
         .replace("dram__bytes_write.sum", "dram_wr").replace("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%")
+    if "--traffic-json" in sys.argv:
+        # DRAM bytes (read + write) of one step per bench phase -> profiles/traffic.json
+        import json
+        steps = float(sys.argv[sys.argv.index("--traffic-json") + 2]) if len(sys.argv) > sys.argv.index("--traffic-json") + 2 else 1.0
+        phase_of = {"k_cull": "cull", "k_roots": "roots", "k_contact": "contact", "k_traverse": "traverse", "k_refit": "refit",
+                    "k_reduce_points": "reduce", "k_scatter": "reduce", "DeviceScan": "reduce", "k_reset_dirty": "reduce",
+                    "k_avg_velocity": "avgvel", "k_boundary": "finalize", "k_final_position": "finalize",
+                    "k_morton": "build", "k_hierarchy": "build", "k_scene_bounds": "build", "DeviceRadixSort": "build"}
+        out = {}
+        for name, a in agg.items():
+            for key, ph in phase_of.items():
+                if key in name:
+                    out[ph] = out.get(ph, 0) + (a.get("dram__bytes_read.sum", 0) + a.get("dram__bytes_write.sum", 0)) / steps
+                    break
+        json.dump({k: int(v) for k, v in out.items()}, open(sys.argv[sys.argv.index("--traffic-json") + 1], "w"), indent=1)
     print(f"{len(ids)} launches, {tot:.3f} ms total")
     for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["gpu__time_duration.sum"]):
         n = a["n"]
