@@ -183,3 +183,53 @@ def test_sliced_equals_whole():
     assert n_rec > 0
     for g in [whole] + parts:
         g.close()
+
+
+def test_config5_family_small():
+    """cloth stack + fast movable rigid spheres (config 5 generator, small): rigid-fabric and rigid-rigid
+    CCD with displacement per step >> edge length, re-rigidification every pass"""
+    sc = scenes.cloth_spheres(n_layers=2, n=17, n_side=2, level=1, seed=31)
+    gpu, orc = make_pair(sc)
+    x, vel = sc.x.copy(), sc.vel.copy()
+    total = 0
+    for step in range(3):
+        x, vel, stats = run_step_by_phases(gpu, orc, sc, x, vel)
+        total += sum(s["contacts"] for s in stats)
+    assert total > 0
+    gpu.close()
+
+
+def test_nan_input_is_reported_not_propagated():
+    """the reference prints and clean_up(ERROR)s on NaN/Inf average velocities (dcollid.cpp:178-184);
+    the library returns CLSN_E_NUMERIC and the host mirror raises"""
+    from collision_b200.solver import CollisionError
+    sc = scenes.two_sheets(n=8)
+    gpu, _ = make_pair(sc)
+    x = sc.x.copy()
+    xn = x + sc.dt * sc.vel
+    xn[3, 1] = np.nan
+    vel = sc.vel.copy()
+    with pytest.raises(CollisionError):
+        gpu.resolveCollision(x, xn, vel)
+    # the context stays usable
+    xn = x + sc.dt * sc.vel
+    gpu.resolveCollision(x, xn, vel)
+    assert np.isfinite(xn).all()
+    gpu.close()
+
+
+def test_zero_time_step():
+    """dt <= ROUND_EPS: avgVel = 0 (dcollid.cpp:174-177), nothing moves"""
+    sc = scenes.two_sheets(n=8)
+    sc.dt = 0.0
+    gpu, orc = make_pair(sc)
+    x, vel = sc.x.copy(), sc.vel.copy()
+    xn = x + 1e-3 * vel
+    orc.set_dt(0.0)
+    orc.set_state(x, xn)
+    vo = vel.copy()
+    orc.resolve(vo)
+    xg, vg = xn.copy(), vel.copy()
+    gpu.resolveCollision(x, xg, vg)
+    assert same_bits(xg, orc.get(port.F_X)) and same_bits(vg, vo)
+    gpu.close()
