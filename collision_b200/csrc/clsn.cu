@@ -481,6 +481,7 @@ struct clsn_ctx {
     DevBuf<Vec4> xo, xn, av;
     DevBuf<uint8_t> has, dirty;
     bool dirty_valid = false;   // dirty[] describes exactly the change between the last two CCD passes
+    bool exact_stats = false;   // count every overlapping pair in `candidates` even where the query could be pruned
     int last_detect_mode = -1;
     DevBuf<double> imp_rg;
     DevBuf<int> cnt_rg;
@@ -625,6 +626,13 @@ extern "C" int clsn_set_slice(clsn_ctx* c, int rank, int nranks)
     if (!c || nranks < 1 || rank < 0 || rank >= nranks) return CLSN_E_ARG;
     c->rank = rank;
     c->nranks = nranks;
+    return CLSN_OK;
+}
+
+extern "C" int clsn_set_exact_stats(clsn_ctx* c, int on)
+{
+    if (!c) return CLSN_E_ARG;
+    c->exact_stats = on != 0;
     return CLSN_OK;
 }
 
@@ -834,20 +842,25 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
         CK(cudaMemsetAsync(c->flags.p, 0, (size_t)N * sizeof(int), c->stream));
         CK(cudaMemsetAsync(c->cnt.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
         CK(cudaMemsetAsync(c->cnt_rg.p, 0, c->nbody * sizeof(int), c->stream));
+        // pairs whose points did not change since the previous CCD pass repeat their (hit-free) outcome
+        const bool skip_clean = moving && c->dirty_valid && c->last_detect_mode == CLSN_COLLISION;
+        // ... and an untouched query needs to visit touched subtrees only -- unless exact candidate counts are wanted
+        const bool prune = skip_clean && !c->exact_stats && !c->dbg_candidates;
         if (moving)
             k_refit<true><<<nblk(N, 128), 128, 0, c->stream>>>(c->elem.p, c->leaf_elem.p, N, c->xo.p, c->av.p, c->prm.dt,
-                                                                 c->lbox.p, c->nodes.p, c->leaf_parent.p, c->flags.p);
+                                                                 c->lbox.p, c->nodes.p, c->leaf_parent.p, c->flags.p,
+                                                                 prune ? c->dirty.p : nullptr);
         else
             k_refit<false><<<nblk(N, 128), 128, 0, c->stream>>>(c->elem.p, c->leaf_elem.p, N, c->xo.p, c->av.p, c->prm.dt,
-                                                                  c->lbox.p, c->nodes.p, c->leaf_parent.p, c->flags.p);
+                                                                  c->lbox.p, c->nodes.p, c->leaf_parent.p, c->flags.p, nullptr);
         c->launches += 1;
         mark(c, PH_REFIT);
         TraverseOut to;
         to.pairs = c->pairs.p; to.cap_pairs = (long long)c->pairs.n;
         to.dbg_cand = c->dbg_candidates ? c->dbg_cand.p : nullptr; to.cap_dbg = (long long)c->dbg_cand.n;
         to.counters = c->counters.p;
-        // pairs whose points did not change since the previous CCD pass repeat their (hit-free) outcome
-        to.dirty = (moving && c->dirty_valid && c->last_detect_mode == CLSN_COLLISION) ? c->dirty.p : nullptr;
+        to.dirty = skip_clean ? c->dirty.p : nullptr;
+        to.node_touched = prune ? c->flags.p : nullptr;
         if (q_hi > q_lo)
             k_traverse<<<nblk(q_hi - q_lo, 128), 128, 0, c->stream>>>(c->nodes.p, c->lbox.p, c->leaf_elem.p, c->elem.p, N, q_lo, q_hi, to);
         c->launches += (q_hi > q_lo) ? 1 : 0;

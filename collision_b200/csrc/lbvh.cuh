@@ -202,13 +202,19 @@ __global__ void k_hierarchy(const unsigned* __restrict__ code, int N, WideNode* 
 template <bool MOVING>
 __global__ void k_refit(const int4* __restrict__ elem, const int* __restrict__ leaf_elem, int N, const Vec4* __restrict__ xo,
                         const Vec4* __restrict__ av, double dt, double* __restrict__ lbox, WideNode* nodes,
-                        const int* __restrict__ leaf_parent, int* flags)
+                        const int* __restrict__ leaf_parent, int* flags, const uint8_t* __restrict__ vdirty)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     int4 el = __ldg(elem + __ldg(leaf_elem + i));
     double lo[3], hi[3];
     leaf_box<MOVING>(el, xo, av, dt, lo, hi);
+    // "touched" bit of the subtree (see k_traverse): does it hold a point changed by the previous pass?
+    int dbit = 1;
+    if (vdirty) {
+        dbit = vdirty[el.x] | vdirty[el.y];
+        if (el.z >= 0) dbit |= vdirty[el.z];
+    }
     double2* lb = reinterpret_cast<double2*>(lbox + 6 * (size_t)i);
     lb[0] = make_double2(lo[0], lo[1]);
     lb[1] = make_double2(lo[2], hi[0]);
@@ -230,7 +236,10 @@ __global__ void k_refit(const int4* __restrict__ elem, const int* __restrict__ l
 #pragma unroll
         for (int d = 0; d < 3; ++d) { dlo[d] = flo[d]; dhi[d] = fhi[d]; }
         __threadfence();
-        if (atomicAdd(flags + node, 1) == 0) return;  // sibling subtree not done yet
+        // arrival counter in the low byte; bit 8 / 9 = left / right child subtree is touched
+        const int old = atomicAdd(flags + node, 1 + (dbit << (left ? 8 : 9)));
+        if ((old & 0xff) == 0) return;  // sibling subtree not done yet
+        dbit |= (old >> (left ? 9 : 8)) & 1;
         __threadfence();
         const volatile float* slo = left ? nd->lo1 : nd->lo0;
         const volatile float* shi = left ? nd->hi1 : nd->hi0;
@@ -253,6 +262,9 @@ struct TraverseOut {
     long long cap_dbg;
     unsigned long long* counters;
     const uint8_t* dirty;   // non-null: drop pairs none of whose points changed since the previous CCD pass
+    const int* node_touched; // non-null (with dirty): refit's per-node flags, bit 8 / 9 = left / right subtree touched;
+                             // an untouched query then only descends into touched subtrees (its other pairs would
+                             // be dropped anyway).  `candidates` then counts only the pairs actually found.
 };
 
 #define TRAV_THREADS 128
@@ -279,6 +291,13 @@ k_traverse(const WideNode* __restrict__ nodes, const double* __restrict__ lbox, 
     __syncwarp();
     float flo[3] = {0, 0, 0}, fhi[3] = {0, 0, 0};
     int node = -1;  // -1 = this lane has finished
+    bool me_touched = true;
+    if (i < q_hi && N >= 2 && out.node_touched) {
+        const int4 el = __ldg(elem + __ldg(leaf_elem + i));
+        unsigned d = out.dirty[el.x] | out.dirty[el.y];
+        if (el.z >= 0) d |= out.dirty[el.z];
+        me_touched = d != 0;
+    }
     if (i < q_hi && N >= 2) {
         const double2* lb = reinterpret_cast<const double2*>(lbox + 6 * (size_t)i);
         const double2 b0 = __ldg(lb), b1 = __ldg(lb + 1), b2 = __ldg(lb + 2);
@@ -297,10 +316,15 @@ k_traverse(const WideNode* __restrict__ nodes, const double* __restrict__ lbox, 
             // n0 = lo0.xyz hi0.x ; n1 = hi0.yz lo1.xy ; n2 = lo1.z hi1.xyz ; n3 = c0 c1 last parent
             const int c0 = n3.x, c1 = n3.y, last = n3.z;
             const int split = c0 < 0 ? ~c0 : c0;  // last leaf of the left child
-            const bool o0 = split > i && flo[0] <= n0.w && fhi[0] >= n0.x && flo[1] <= n1.x && fhi[1] >= n0.y &&
-                            flo[2] <= n1.y && fhi[2] >= n0.z;
-            const bool o1 = last > i && flo[0] <= n2.y && fhi[0] >= n1.z && flo[1] <= n2.z && fhi[1] >= n1.w &&
-                            flo[2] <= n2.w && fhi[2] >= n2.x;
+            bool o0 = split > i && flo[0] <= n0.w && fhi[0] >= n0.x && flo[1] <= n1.x && fhi[1] >= n0.y &&
+                      flo[2] <= n1.y && fhi[2] >= n0.z;
+            bool o1 = last > i && flo[0] <= n2.y && fhi[0] >= n1.z && flo[1] <= n2.z && fhi[1] >= n1.w &&
+                      flo[2] <= n2.w && fhi[2] >= n2.x;
+            if (!me_touched && (o0 || o1)) {
+                const int tf = __ldg(out.node_touched + node);
+                o0 = o0 && ((tf >> 8) & 1);
+                o1 = o1 && ((tf >> 9) & 1);
+            }
             int next = -1;
             if (o0) {
                 if (c0 >= 0) next = c0;

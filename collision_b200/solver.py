@@ -107,6 +107,7 @@ def load_library():
     L.clsn_launch_count.argtypes = [V, I]
     L.clsn_synchronize.argtypes = [V]
     L.clsn_set_debug.argtypes = [V, I, I]
+    L.clsn_set_exact_stats.argtypes = [V, I]
     L.clsn_num_candidates.restype = C.c_int64
     L.clsn_num_candidates.argtypes = [V]
     L.clsn_get_candidates.argtypes = [V, P(C.c_int32)]
@@ -352,6 +353,10 @@ class CollisionSolver3d:
 
     def set_debug(self, candidates=True, contacts=True):
         self.ctx.check(self.ctx.L.clsn_set_debug(self.ctx.h, int(candidates), int(contacts)))
+
+    def set_exact_stats(self, on=True):
+        """full traversal in every pass so that stats['candidates'] equals the reference's callback count"""
+        self.ctx.check(self.ctx.L.clsn_set_exact_stats(self.ctx.h, int(on)))
 
     def candidates(self):
         c = self.ctx

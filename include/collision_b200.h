@@ -147,6 +147,11 @@ int clsn_import_records(clsn_ctx*, const void* d_point_records, int64_t n_point_
 
 /* ---- debug / parity readbacks (host buffers) */
 int clsn_set_debug(clsn_ctx*, int record_candidates, int record_contacts);
+/* From the second CCD pass on, pairs none of whose points was changed by the previous pass repeat their
+ * (hit-free) outcome and are skipped; queries without a changed point then only visit subtrees that hold
+ * one, and clsn_pass_stats.candidates counts only the pairs found.  on != 0 restores the full traversal so
+ * that `candidates` equals the reference's callback count in every pass (results are identical). */
+int clsn_set_exact_stats(clsn_ctx*, int on);
 int64_t clsn_num_candidates(clsn_ctx*);
 int clsn_get_candidates(clsn_ctx*, int32_t* pairs /* 2 per pair, unsorted */);
 int64_t clsn_num_contacts(clsn_ctx*);

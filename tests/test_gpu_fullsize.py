@@ -109,6 +109,7 @@ def test_sample_of_config4_matches_oracle():
         vo = vel.copy()
         st_o = orc.resolve(vo)
         xg, vg = xn.copy(), vel.copy()
+        g.set_exact_stats(True)
         g.resolveCollision(x, xg, vg)
         st = g.last_stats
         assert [p["true_pairs"] for p in st["ccd"]] == st_o[2:2 + st_o[1]]

@@ -66,6 +66,7 @@ def test_whole_step_parity(name):
     gpu.set_debug(False, False)
     x, vel = sc.x.copy(), sc.vel.copy()
     for step in range(4):
+        gpu.set_exact_stats(step % 2 == 0)   # pruned traversal on odd steps: same results, fewer candidates counted
         xn = x + sc.dt * vel
         orc.set_state(x, xn)
         vo = vel.copy()
@@ -78,7 +79,10 @@ def test_whole_step_parity(name):
         assert st["n_ccd_passes"] == st_o[1]
         assert [p["true_pairs"] for p in st["ccd"]] == st_o[2:2 + st_o[1]]
         assert st["proximity"]["candidates"] == st_o[8]
-        assert [p["candidates"] for p in st["ccd"]] == st_o[9:9 + st_o[1]]
+        if step % 2 == 0:
+            assert [p["candidates"] for p in st["ccd"]] == st_o[9:9 + st_o[1]]
+        else:
+            assert all(a <= b for a, b in zip([p["candidates"] for p in st["ccd"]], st_o[9:9 + st_o[1]]))
         assert int(st["still_colliding"]) == st_o[7]
         assert same_bits(xg, orc.get(port.F_X))
         assert same_bits(vg, vo)
