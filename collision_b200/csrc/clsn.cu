@@ -467,6 +467,7 @@ enum { PH_AVG = 0, PH_BUILD, PH_REFIT, PH_TRAVERSE, PH_CULL, PH_ROOTS, PH_CONTAC
 struct clsn_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;  // created by clsn_create; `stream` may be replaced by clsn_set_stream
     std::string err;
     clsn_params prm;
     int V = 0, T = 0, B = 0, N = 0, nbody = 0;
@@ -499,7 +500,7 @@ struct clsn_ctx {
     DevBuf<FeatRec> feats;
     DevBuf<unsigned> pair_hit;
     DevBuf<RootRec> rootrecs;
-    DevBuf<PointRec> prec;
+    DevBuf<PointRec> prec, prec_sorted;
     DevBuf<BodyRec> brec;
     DevBuf<Contact> contacts;
     DevBuf<int> cnt, offs, fill, perm, perm_sorted;
@@ -570,16 +571,17 @@ extern "C" int clsn_create(clsn_ctx** out, int device)
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return CLSN_E_CUDA;
     clsn_ctx* c = new clsn_ctx();
     c->device = device;
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
         return CLSN_E_CUDA;
     }
+    c->stream = c->own_stream;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     for (auto& e : c->ev) cudaEventCreate(&e);
     cudaEventCreate(&c->bracket[0]);
     cudaEventCreate(&c->bracket[1]);
     cudaMallocHost((void**)&c->h_counters, 64 * sizeof(unsigned long long));
-    c->counters.reserve(64);
+    c->counters.reserve(256);
     c->bounds.reserve(8);
     clsn_params p;
     p.eps = 1e-6; p.thickness = 1e-4; p.dt = 1e-3; p.k = 1000; p.m = 0.01; p.lambda = 0.02; p.cr = 0.0;
@@ -598,7 +600,7 @@ extern "C" void clsn_destroy(clsn_ctx* c)
     c->xo.release(); c->xn.release(); c->av.release(); c->has.release(); c->dirty.release(); c->imp_rg.release(); c->cnt_rg.release();
     c->stage.release(); c->code.release(); c->code_sorted.release(); c->idx.release(); c->leaf_elem.release();
     c->leaf_parent.release(); c->flags.release(); c->nodes.release(); c->lbox.release(); c->bounds.release();
-    c->cub_tmp.release(); c->pairs.release(); c->dbg_cand.release(); c->feats.release(); c->pair_hit.release(); c->rootrecs.release(); c->prec.release(); c->brec.release();
+    c->cub_tmp.release(); c->pairs.release(); c->dbg_cand.release(); c->feats.release(); c->pair_hit.release(); c->rootrecs.release(); c->prec.release(); c->prec_sorted.release(); c->brec.release();
     c->contacts.release(); c->cnt.release(); c->offs.release(); c->fill.release(); c->perm.release();
     c->perm_sorted.release(); c->skey.release(); c->counters.release(); c->acc_imp.release(); c->acc_fric.release();
     c->rigid.release();
@@ -608,7 +610,7 @@ extern "C" void clsn_destroy(clsn_ctx* c)
     for (auto& e : c->marks) cudaEventDestroy(e);
     cudaEventDestroy(c->bracket[0]);
     cudaEventDestroy(c->bracket[1]);
-    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
@@ -626,6 +628,18 @@ extern "C" int clsn_set_slice(clsn_ctx* c, int rank, int nranks)
     if (!c || nranks < 1 || rank < 0 || rank >= nranks) return CLSN_E_ARG;
     c->rank = rank;
     c->nranks = nranks;
+    return CLSN_OK;
+}
+
+// Run on the caller's stream (e.g. torch.cuda.current_stream().cuda_stream) so that the caller's own
+// device work -- the NCCL exchange of the multi-GPU step -- is ordered with the library's kernels without
+// host synchronisation.  stream == NULL restores the context's own stream.
+extern "C" int clsn_set_stream(clsn_ctx* c, void* stream)
+{
+    if (!c) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaStreamSynchronize(c->stream));
+    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
     return CLSN_OK;
 }
 
@@ -952,7 +966,7 @@ extern "C" int clsn_detect(clsn_ctx* c, int mode, clsn_pass_stats* st)
 }
 
 // group + reduce the pending records.  mode 0: apply to avgVel; mode 1: into acc arrays only.
-static int reduce_records(clsn_ctx* c, int mode)
+static int reduce_records(clsn_ctx* c, int mode, int what = 3)  // what: bit 0 point records, bit 1 body records
 {
     const int V = c->V;
     const PointRec* prec = c->prec.p;
@@ -961,12 +975,16 @@ static int reduce_records(clsn_ctx* c, int mode)
     unsigned long long* n_prec_dev = c->counters.p + CTR_PREC;
     unsigned long long* n_brec_dev = c->counters.p + CTR_BREC;
     if (c->imp_nprec >= 0) {
-        // externally gathered record set: recount per point
-        prec = c->imp_prec; brec = c->imp_brec; nprec = c->imp_nprec; nbrec = c->imp_nbrec;
-        unsigned long long hc[2] = {(unsigned long long)nprec, (unsigned long long)nbrec};
-        CK(cudaMemcpyAsync(c->counters.p + 32, hc, sizeof(hc), cudaMemcpyHostToDevice, c->stream));
         n_prec_dev = c->counters.p + 32;
         n_brec_dev = c->counters.p + 33;
+    }
+    if (c->imp_nprec >= 0) {
+        // externally gathered record set: recount per point
+        prec = c->imp_prec; brec = c->imp_brec; nprec = c->imp_nprec; nbrec = c->imp_nbrec;
+    }
+    if (c->imp_nprec >= 0 && (what & 1)) {
+        unsigned long long hc[2] = {(unsigned long long)nprec, (unsigned long long)nbrec};
+        CK(cudaMemcpyAsync(c->counters.p + 32, hc, sizeof(hc), cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemsetAsync(c->cnt.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
         CK(cudaMemsetAsync(c->cnt_rg.p, 0, c->nbody * sizeof(int), c->stream));
         if (nprec > 0 || nbrec > 0)
@@ -975,7 +993,7 @@ static int reduce_records(clsn_ctx* c, int mode)
             CK(c->perm.reserve((size_t)nprec)); CK(c->perm_sorted.reserve((size_t)nprec)); CK(c->skey.reserve((size_t)nprec));
         }
     }
-    if (nprec > 0) {
+    if (nprec > 0 && (what & 1)) {
         size_t tmp = c->cub_tmp.n;
         CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->cnt.p, c->offs.p, V + 1, c->stream));
         CK(cudaMemsetAsync(c->fill.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
@@ -990,12 +1008,12 @@ static int reduce_records(clsn_ctx* c, int mode)
                                                                   c->vflags.p, c->av.p, c->has.p, c->dirty.p, mode, c->acc_imp.p,
                                                                   c->acc_fric.p, c->counters.p);
         c->launches += 2 + 2;  // scan (init + scan), scatter, reduce
-    } else if (mode == 1) {
+    } else if (mode == 1 && (what & 1)) {
         CK(c->acc_imp.reserve(3 * (size_t)V)); CK(c->acc_fric.reserve(3 * (size_t)V));
         CK(cudaMemsetAsync(c->acc_imp.p, 0, 3 * (size_t)V * sizeof(double), c->stream));
         CK(cudaMemsetAsync(c->acc_fric.p, 0, 3 * (size_t)V * sizeof(double), c->stream));
     }
-    if (nbrec > 0 && mode == 0) {
+    if (nbrec > 0 && mode == 0 && (what & 2)) {
         const long long cap = c->imp_nprec >= 0 ? nbrec : (long long)c->brec.n;
         k_reduce_bodies<<<nblk(c->nbody, 64), 64, 0, c->stream>>>(brec, n_brec_dev, cap, c->nbody, c->imp_rg.p);
         c->launches += 1;
@@ -1004,14 +1022,18 @@ static int reduce_records(clsn_ctx* c, int mode)
     return CLSN_OK;
 }
 
-extern "C" int clsn_apply(clsn_ctx* c, int rigidify)
+// stages: bit 0 = reduce the point records into avgVel; bit 1 = body records, rigid bodies, bookkeeping.
+// The multi-GPU owner-computes path runs them separately with the avgVel exchange in between.
+static int apply_impl(clsn_ctx* c, int rigidify, int stages)
 {
-    if (!c || !c->V) return CLSN_E_ARG;
-    cudaSetDevice(c->device);
-    if (c->records_pending) {
+    if (c->records_pending && (stages & 1)) {
         k_reset_dirty<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->vflags.p, c->dirty.p);
         c->launches += 1;
-        int r = reduce_records(c, 0);
+        int r = reduce_records(c, 0, 1);
+        if (r) return r;
+    }
+    if (c->records_pending && (stages & 2)) {
+        int r = reduce_records(c, 0, 2);
         if (r) return r;
         const long long nbrec = c->imp_nprec >= 0 ? c->imp_nbrec : c->last_nbrec;
         if (nbrec > 0 || c->has_movable) {
@@ -1026,13 +1048,31 @@ extern "C" int clsn_apply(clsn_ctx* c, int rigidify)
         c->imp_nprec = -1;
         c->dirty_valid = true;
     }
-    if (rigidify && c->has_movable && c->prm.dt > 0.0) {
+    if ((stages & 2) && rigidify && c->has_movable && c->prm.dt > 0.0) {
         int r = c->rigid.rigidify(c->xo.p, c->av.p, c->vflags.p, c->prm.m, c->prm.dt, c->counters.p, c->stream);
         if (r != 0) return fail(c, CLSN_E_CUDA, "rigid-body kernels failed");
         c->launches += c->rigid.nlists ? 2 : 0;
     }
     CK(cudaGetLastError());
     mark(c, PH_REDUCE);
+    return CLSN_OK;
+}
+
+extern "C" int clsn_apply(clsn_ctx* c, int rigidify)
+{
+    if (!c || !c->V) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    return apply_impl(c, rigidify, 3);
+}
+
+extern "C" int clsn_apply_stage(clsn_ctx* c, int stage, int rigidify)
+{
+    if (!c || !c->V || (stage != 1 && stage != 2)) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    int r = apply_impl(c, rigidify, stage);
+    if (r) return r;
+    // the caller exchanges state next: on its own stream unless it shares one with us (clsn_set_stream)
+    if (c->stream == c->own_stream) CK(cudaStreamSynchronize(c->stream));
     return CLSN_OK;
 }
 
@@ -1165,6 +1205,42 @@ extern "C" int clsn_export_records(clsn_ctx* c, void** d_prec, int64_t* n_prec, 
     if (d_brec) *d_brec = c->brec.p;
     if (n_brec) *n_brec = c->last_nbrec;
     if (true_pairs) *true_pairs = (int64_t)c->h_counters[CTR_TRUE];
+    return CLSN_OK;
+}
+
+extern "C" int clsn_bucket_records(clsn_ctx* c, int nranks, int64_t* counts, void** d_sorted)
+{
+    if (!c || !c->records_pending || nranks < 1 || nranks > 64 || !counts || !d_sorted) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    const long long n = c->last_nprec;
+    const int per_rank = (c->V + nranks - 1) / nranks;
+    CK(c->prec_sorted.reserve((size_t)(n > 0 ? n : 1)));
+    unsigned long long* cnt = c->counters.p + 40;  // 64 bucket counters, then 64 cursors
+    CK(cudaMemsetAsync(cnt, 0, 128 * sizeof(unsigned long long), c->stream));
+    unsigned long long h[64] = {0};
+    if (n > 0) {
+        k_owner_count<<<c->sm_count * 4, 256, 0, c->stream>>>(c->prec.p, n, per_rank, cnt);
+        CK(cudaMemcpyAsync(h, cnt, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        unsigned long long cur[64], acc = 0;
+        for (int r = 0; r < 64; ++r) { cur[r] = acc; acc += h[r]; }
+        CK(cudaMemcpyAsync(cnt + 64, cur, 64 * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+        k_owner_scatter<<<c->sm_count * 4, 256, 0, c->stream>>>(c->prec.p, n, per_rank, cnt + 64, c->prec_sorted.p);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(c->stream));
+        c->launches += 2;
+    }
+    for (int r = 0; r < nranks; ++r) counts[r] = (int64_t)h[r];
+    *d_sorted = c->prec_sorted.p;
+    return CLSN_OK;
+}
+
+extern "C" int clsn_state_device_ptrs(clsn_ctx* c, void** av, void** has, void** dirty)
+{
+    if (!c || !c->V) return CLSN_E_ARG;
+    if (av) *av = c->av.p;
+    if (has) *has = c->has.p;
+    if (dirty) *dirty = c->dirty.p;
     return CLSN_OK;
 }
 

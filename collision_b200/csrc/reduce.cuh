@@ -38,6 +38,49 @@ __global__ void k_count_records(const PointRec* __restrict__ prec, long long npr
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < nbrec; r += stride) atomicAdd(cnt_rg + brec[r].body, 1);
 }
 
+// Multi-GPU owner-computes exchange: bucket this rank's point records by the rank that owns the point
+// (contiguous vertex ranges of `per_rank` vertices).  Two passes: histogram, then scatter with one
+// running offset per bucket (order inside a bucket is free -- the reduction sorts by key anyway).
+__global__ void k_owner_count(const PointRec* __restrict__ rec, long long n, int per_rank, unsigned long long* counts)
+{
+    __shared__ unsigned s_c[64];
+    if (threadIdx.x < 64) s_c[threadIdx.x] = 0;
+    __syncthreads();
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&s_c[rec[r].point / per_rank], 1u);
+    __syncthreads();
+    if (threadIdx.x < 64 && s_c[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_c[threadIdx.x]);
+}
+__global__ void k_owner_scatter(const PointRec* __restrict__ rec, long long n, int per_rank, unsigned long long* cursor,
+                                PointRec* __restrict__ out)
+{
+    // one global atomic per (tile, owner): ranks inside the tile come from shared-memory counters
+    __shared__ unsigned s_c[64];
+    __shared__ unsigned long long s_base[64];
+    for (long long tile = (long long)blockIdx.x * blockDim.x; tile < n; tile += (long long)gridDim.x * blockDim.x) {
+        if (threadIdx.x < 64) s_c[threadIdx.x] = 0;
+        __syncthreads();
+        const long long r = tile + threadIdx.x;
+        ulonglong2 a, b, c2, d;
+        int owner = 0;
+        unsigned local = 0;
+        if (r < n) {
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(rec + r);
+            a = src[0]; b = src[1]; c2 = src[2]; d = src[3];
+            owner = (int)(unsigned)a.y / per_rank;
+            local = atomicAdd(&s_c[owner], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 64 && s_c[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], (unsigned long long)s_c[threadIdx.x]);
+        __syncthreads();
+        if (r < n) {
+            ulonglong2* dst = reinterpret_cast<ulonglong2*>(out + (s_base[owner] + local));
+            dst[0] = a; dst[1] = b; dst[2] = c2; dst[3] = d;
+        }
+        __syncthreads();
+    }
+}
+
 // One warp per point.  Rank the point's keys (all-pairs compare, keys are unique), store the
 // records in rank order, then lanes 0..5 each sum one of imp.xyz / fric.xyz sequentially.
 // mode 0: apply to avgVel (updateAverageVelocity :707-724); mode 1: write the sums to acc arrays.

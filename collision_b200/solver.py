@@ -101,6 +101,10 @@ def load_library():
     L.clsn_set_slice.argtypes = [V, I, I]
     L.clsn_export_records.argtypes = [V, P(V), P(C.c_int64), P(V), P(C.c_int64), P(C.c_int64)]
     L.clsn_import_records.argtypes = [V, V, C.c_int64, V, C.c_int64]
+    L.clsn_bucket_records.argtypes = [V, I, P(C.c_int64), P(V)]
+    L.clsn_set_stream.argtypes = [V, V]
+    L.clsn_apply_stage.argtypes = [V, I, I]
+    L.clsn_state_device_ptrs.argtypes = [V, P(V), P(V), P(V)]
     L.clsn_timer_start.argtypes = [V]
     L.clsn_timer_stop.argtypes = [V, P(C.c_float)]
     L.clsn_launch_count.restype = C.c_int64

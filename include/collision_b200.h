@@ -142,6 +142,17 @@ int clsn_export_records(clsn_ctx*, void** d_point_records, int64_t* n_point_reco
 /* replace the record set to be reduced by clsn_apply with externally gathered ones (device ptrs) */
 int clsn_import_records(clsn_ctx*, const void* d_point_records, int64_t n_point_records,
                         const void* d_body_records, int64_t n_body_records);
+/* owner-computes variant: vertex v belongs to rank v / ceil(V/nranks).  clsn_bucket_records groups this
+ * rank's point records by owner (counts[r] records for rank r, contiguous in *d_sorted) for an
+ * all-to-all; each rank imports what it received, runs clsn_apply_stage(1) (reduce -> avgVel of its own
+ * vertices), the ranks all-gather their avgVel / has_collsn / touched slices (clsn_state_device_ptrs:
+ * 32-byte Vec4 per vertex, 1 byte, 1 byte), then clsn_apply_stage(2) (body records, rigid bodies). */
+int clsn_bucket_records(clsn_ctx*, int nranks, int64_t* counts, void** d_sorted);
+/* run on the caller's CUDA stream (cudaStream_t passed as void*; NULL = the context's own stream; for the
+ * legacy default stream pass cudaStreamLegacy, i.e. (void*)0x1) */
+int clsn_set_stream(clsn_ctx*, void* cuda_stream);
+int clsn_apply_stage(clsn_ctx*, int stage, int rigidify);
+int clsn_state_device_ptrs(clsn_ctx*, void** d_avgvel_vec4, void** d_has_collsn, void** d_touched);
 #define CLSN_POINT_RECORD_BYTES 64
 #define CLSN_BODY_RECORD_BYTES 48
 

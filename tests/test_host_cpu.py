@@ -99,6 +99,14 @@ exp = torch.cat([(torch.arange(m, dtype=torch.int64) %% 251 + r).to(torch.uint8)
 assert torch.equal(out, exp), (rank, out.shape)
 empty = gather_varlen(torch.empty(0, dtype=torch.uint8))
 assert empty.numel() == 0
+# owner-computes all-to-all: rank r sends (r+1)*(d+1)*64 bytes of value 10*r+d to rank d
+from collision_b200.dist import exchange_by_owner
+counts = [(rank + 1) * (d + 1) * 64 for d in range(3)]
+send = torch.cat([torch.full((n,), 10 * rank + d, dtype=torch.uint8) for d, n in enumerate(counts)])
+recv, rc = exchange_by_owner(send, counts)
+assert rc == [(s + 1) * (rank + 1) * 64 for s in range(3)], rc
+exp = torch.cat([torch.full(((s + 1) * (rank + 1) * 64,), 10 * s + rank, dtype=torch.uint8) for s in range(3)])
+assert torch.equal(recv, exp)
 dist.destroy_process_group()
 print("ok", rank)
 """
