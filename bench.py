@@ -85,7 +85,7 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
-    def stop(self):
+    def stop(self, first_timed: int = 0):
         if self.proc:
             self.proc.terminate()
             try:
@@ -94,7 +94,13 @@ class ClockSampler:
                 pass
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        # a very short timed region can fall between two nvidia-smi samples: then use every sample taken
+        # since the sampler started (the untimed spin-up steps run the same step under the same load)
+        window = "timed"
+        lines = self.lines[first_timed:]
+        if len(lines) < 3:
+            lines, window = self.lines, "spin-up + timed (timed region shorter than 3 samples)"
+        for ln in lines:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -107,8 +113,9 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": window}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 # ----------------------------------------------------------------------------- reference arm
@@ -249,10 +256,11 @@ def run_b200(args):
         st = one_step()
     sampler = ClockSampler(local)
     sampler.start()
-    for _ in range(3):       # keep the GPU under load while nvidia-smi spins up; untimed
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 0.8:   # keep the GPU under load while nvidia-smi spins up; untimed
         one_step()
     barrier()
-    sampler.lines.clear()    # only samples taken during the timed region count
+    n_before = len(sampler.lines)  # samples from here on fall inside the timed region
     solver.launch_count(reset=True)
     solver.timer_start()
     t0 = time.perf_counter()
@@ -266,7 +274,7 @@ def run_b200(args):
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
     launches = solver.launch_count()
-    clocks = sampler.stop()
+    clocks = sampler.stop(n_before)
 
     # ---- e2e through the drop-in call with pinned host buffers (N = 1: the C ABI call; N > 1: host
     # upload + distributed step + host download)
