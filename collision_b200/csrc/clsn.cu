@@ -423,6 +423,7 @@ k_contact(const FeatRec* __restrict__ feats, const RootRec* __restrict__ rootrec
             nq = base;
             __syncwarp();
         }
+        __syncwarp();  // every lane has read s_n[w] before lane 0 rewrites it
         if (lane == 0) s_n[w] = nq;
         __syncwarp();
         if (done) break;

@@ -399,6 +399,7 @@ k_traverse(const WideNode* __restrict__ nodes, const double* __restrict__ lbox, 
             nq = base;
             __syncwarp();
         }
+        __syncwarp();  // every lane has read s_n[w] before lane 0 rewrites it
         if (lane == 0) s_n[w] = nq;
         __syncwarp();
     }
