@@ -80,8 +80,9 @@ __device__ __forceinline__ FBox fbox_union(const FBox& a, const FBox& b)
 // only if, at some t in [0, dt], the point lies within h of the triangle's hull inflated by the
 // barycentric slack eps (PointToTri :911-919), resp. the two segments come within h (EdgeToEdge :747).
 // Every position used by the test lies in the swept boxes, so a gap larger than
-// margin = 2h + (3 eps + 1e-2) * extent along any axis means "the reference returns false" -- the
-// 1e-2 * extent term dwarfs every rounding error of the test itself (DESIGN.md "exact culls").
+// margin = 1.001 h + (3 eps + 2e-3) * extent along any axis means "the reference returns false" -- the
+// 2e-3 * extent term covers the rounding of the test itself, including the barycentric coordinates of
+// nearly degenerate triangles (DESIGN.md "exact culls").
 // FP32 with directed rounding: the gap is rounded down, the margin up, so the cull stays conservative.
 __device__ __forceinline__ bool boxes_far(const FBox& a, const FBox& b, float h2, float rel)
 {
@@ -117,8 +118,11 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
     const int tid = threadIdx.x, lane = tid & 31, wb = tid & ~31;
     long long n_pairs = (long long)counters[CTR_PAIRS];
     if (n_pairs > cap_pairs) n_pairs = cap_pairs;
-    const float h2 = __double2float_ru(2.0 * (MOVING ? P.eps : P.thickness));
-    const float rel = __double2float_ru(3.0 * P.eps + 1e-2);
+    // contact distance with 0.1 % head-room (covers the rounding of the distance itself), and the relative
+    // slack: 3 eps for the barycentric tolerance + 2e-3 for the error of the barycentric coordinates of a
+    // nearly degenerate triangle (cond <= L^4 / (1000 MACH_EPS), i.e. <= 4.5e-4 for L <= 1)
+    const float h2 = __double2float_ru(1.001 * (MOVING ? P.eps : P.thickness));
+    const float rel = __double2float_ru(3.0 * P.eps + 2e-3);
     unsigned long long n_box = 0;
     for (long long base = (long long)blockIdx.x * CULL_THREADS; base < n_pairs; base += (long long)gridDim.x * CULL_THREADS) {
         const long long pi = base + tid;
