@@ -137,11 +137,18 @@ def time_reference(scene, steps, warmup):
             r.set_state(x0, xn0, v0)
             r.assemble(scene.dt)
             r.record(False)
+            # exactly the work clsn_resolve does: resolveCollision (dcollid.cpp:317-362) without reduceSuperelast and
+            # without the computeImpactZone fail-safe that the reference enters after 5 unresolved CCD passes
             t0 = time.perf_counter()
             r.phase(ref.PH_AVG_VELOCITY)
-            r.phase(ref.PH_DETECT_PROXIMITY)
+            r.phase(ref.PH_PROXIMITY_DETECT)
+            r.phase(ref.PH_APPLY)
             n_prox = r.num_callbacks()
-            r.phase(ref.PH_DETECT_COLLISION)
+            for _ in range(5):                       # MAX_ITER, dcollid.cpp:433
+                n_true = r.phase(ref.PH_COLLISION_DETECT)
+                r.phase(ref.PH_APPLY)
+                if n_true == 0:
+                    break
             r.phase(ref.PH_BOUNDARY)
             r.phase(ref.PH_FINAL_POSITION)
             r.phase(ref.PH_FINAL_VELOCITY)
