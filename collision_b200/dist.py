@@ -90,6 +90,7 @@ class DistributedSolver:
         self.s = solver
         self.group = group
         self.mode = mode
+        self.small_pass_records = 65536   # passes with fewer records (all ranks together) skip the all-to-all
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         c = solver.ctx
@@ -127,12 +128,31 @@ class DistributedSolver:
         allh = torch.empty((G, G + 2), dtype=torch.int64, device=self.device)
         dist.all_gather_into_tensor(allh, hdr, group=self.group)
         allh = allh.cpu()
+        n_true = int(allh[:, G + 1].sum())
+        per_rank_total = [int(allh[src, :G].sum()) for src in range(G)]
+        if sum(per_rank_total) <= self.small_pass_records and int(allh[:, G].sum()) == 0:
+            # small pass (late CCD passes, contact-free proximity): cheaper to all-gather the few records and let
+            # every rank reduce all of them -- one collective instead of two, no state exchange
+            mx = max(per_rank_total) * POINT_RECORD_BYTES
+            allp = torch.empty(0, dtype=torch.uint8, device=self.device)
+            if mx > 0:
+                nb = npr.value * POINT_RECORD_BYTES
+                mine = torch.zeros(mx, dtype=torch.uint8, device=self.device)
+                mine[:nb] = torch.as_tensor(_DevPtr(pp.value, nb), device=self.device)[:nb]
+                full = torch.empty((G, mx), dtype=torch.uint8, device=self.device)
+                dist.all_gather_into_tensor(full, mine, group=self.group)
+                allp = torch.cat([full[r, : per_rank_total[r] * POINT_RECORD_BYTES] for r in range(G)])
+            self._keep = (allp,)
+            c.check(c.L.clsn_import_records(c.h, allp.data_ptr() if allp.numel() else None, allp.numel() // POINT_RECORD_BYTES,
+                                            None, 0))
+            c.check(c.L.clsn_apply_stage(c.h, 1, 0))
+            c.check(c.L.clsn_apply_stage(c.h, 2, 1 if rigidify else 0))
+            return n_true
         send_b = [int(counts[r]) * POINT_RECORD_BYTES for r in range(G)]
         recv_b = [int(allh[src, self.rank]) * POINT_RECORD_BYTES for src in range(G)]
         send = torch.as_tensor(_DevPtr(ps.value, sum(send_b)), device=self.device)[: sum(send_b)]
         recv = torch.empty(sum(recv_b), dtype=torch.uint8, device=self.device)
         dist.all_to_all_single(recv, send, output_split_sizes=recv_b, input_split_sizes=send_b, group=self.group)
-        n_true = int(allh[:, G + 1].sum())
         allb = torch.empty(0, dtype=torch.uint8, device=self.device)
         if int(allh[:, G].sum()) > 0:
             # body records (rigid-rigid contacts) are few: all-gather, every rank reduces them identically
