@@ -1,0 +1,203 @@
+// The coplanarity cubic of the CCD tests: coefficients, the trig-free classifier and the correctly
+// rounded solve (reference: isCoplanar, dcollid3d.cpp:371-482).  Pure FP64 arithmetic, no CUDA intrinsics:
+// the file is __host__ __device__ so that tests/cubic_check.cpp can fuzz exactly this code on the CPU
+// against the oracle (tests/test_host_cpu.py::test_cubic_path_matches_oracle_on_host).
+#pragma once
+#include <math.h>
+#include "crmath.cuh"
+
+#if defined(__CUDACC__)
+#define CLSN_HD __host__ __device__ __forceinline__
+#else
+#define CLSN_HD static inline
+#endif
+
+namespace clsn {
+
+#define CLSN_MACH_EPS 2.220446049250313e-16 /* DBL_EPSILON */
+#define CLSN_ROUND_EPS 1e-10                /* collid.h:17 */
+
+// the four points of one feature test
+struct Quad {
+    int id[4];
+    int flags[4];   // CLSN_VFLAG_*
+    int body[4];
+    double xo[4][3];  // x_old
+    double av[4][3];  // avgVel
+};
+
+
+// Coefficients of the coplanarity cubic a t^3 + b t^2 + c t + d (dcollid3d.cpp:382-422), in the
+// reference's exact operation order.
+CLSN_HD void coplanar_coeffs(const Quad& q, double& a, double& b, double& c, double& d)
+{
+    double v[4][3], x[4][3];
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            v[i][j] = q.av[i][j] - q.av[0][j];
+            x[i][j] = q.xo[i][j] - q.xo[0][j];
+        }
+    double vv[3], vx[3], xx[3];
+    vv[0] = v[1][1] * v[2][2] - v[1][2] * v[2][1];
+    vv[1] = v[1][0] * v[2][2] - v[1][2] * v[2][0];
+    vv[2] = v[1][0] * v[2][1] - v[1][1] * v[2][0];
+    vx[0] = v[1][1] * x[2][2] - v[1][2] * x[2][1] - v[2][1] * x[1][2] + v[2][2] * x[1][1];
+    vx[1] = v[1][0] * x[2][2] - v[1][2] * x[2][0] - v[2][0] * x[1][2] + v[2][2] * x[1][0];
+    vx[2] = v[1][0] * x[2][1] - v[1][1] * x[2][0] - v[2][0] * x[1][1] + v[2][1] * x[1][0];
+    xx[0] = x[1][1] * x[2][2] - x[1][2] * x[2][1];
+    xx[1] = x[1][0] * x[2][2] - x[1][2] * x[2][0];
+    xx[2] = x[1][0] * x[2][1] - x[1][1] * x[2][0];
+    a = v[3][0] * vv[0] - v[3][1] * vv[1] + v[3][2] * vv[2];
+    b = x[3][0] * vv[0] - x[3][1] * vv[1] + x[3][2] * vv[2] + v[3][0] * vx[0] - v[3][1] * vx[1] + v[3][2] * vx[2];
+    c = x[3][0] * vx[0] - x[3][1] * vx[1] + x[3][2] * vx[2] + v[3][0] * xx[0] - v[3][1] * xx[1] + v[3][2] * xx[2];
+    d = x[3][0] * xx[0] - x[3][1] * xx[1] + x[3][2] * xx[2];
+}
+
+// Rigorous, trig-free classifier: can isCoplanar produce a root that survives its "-MACH_EPS, keep
+// [0, dt]" filter?  "false" is exact (the reference's isCoplanar returns false); "true" sends the
+// feature to the correctly rounded solve.  (a, b, c, d) as returned by coplanar_coeffs.
+//
+// Three-real-root branch (R^2 < Q^3): the reference's roots are -2 sqrt(Q) cos(phi_k) - a/3 with
+// phi_k = (acos(x) + 2 pi k)/3, x = R / sqrt(Q^3); cos(phi_k) are the three solutions of the
+// triple-angle identity T3(c) = 4c^3 - 3c = x.  A computed root is valid only if its cosine lies in
+// [u, v] = [-(dt + a/3)/S, -(a/3)/S] (S = 2 sqrt(Q)) up to the rounding of the root formula, so no
+// root is valid when x is outside T3([u - delta, v + delta]) -- two polynomial evaluations, no acos/cos.
+// delta covers: correctly rounded acos/cos (<= 1 ulp total in phi and cos), the rounding of 2*pi,
+// of the sum and of /3 (<= 1e-15), and the two roundings of the root formula (eta).  DESIGN.md.
+// One-real-root branch: root = A + B - a/3 with A = -sgn * pow(u, 1/3); cbrt() is within 1.5e-14
+// relative of the correctly rounded pow over the whole double range, covered by a 1e-13 guard.
+// Returns 0 = no valid root possible, 1 = maybe (three-real-root / trig branch), 2 = maybe (other branches).
+CLSN_HD int coplanar_maybe(double a, double b, double c, double d, double dt)
+{
+    if (fabs(a) > CLSN_MACH_EPS) {
+        b /= a; c /= a; d /= a;
+        a = b; b = c; c = d;
+        const double Q = (a * a - 3 * b) / 9;
+        const double R = (2 * a * a * a - 9 * a * b + 27 * c) / 54;
+        const double Q3 = Q * Q * Q, R2 = R * R;
+        if (R2 < Q3) {
+            const double S = 2 * sqrt(Q);
+            const double x = R / sqrt(Q3);
+            if (!(fabs(x) <= 1.0) || !(S > 0.0)) return 1;  // acos domain edge / NaN: let the exact path decide
+            const double A3 = a / 3;
+            const double eta = 4e-16 * (2 * S + fabs(A3) + dt) + 2 * CLSN_MACH_EPS;
+            double u = -(dt + A3 + eta) / S;
+            double v = -(A3 - eta) / S;
+            const double delta = 4e-15 + 4e-16 * (fabs(u) + fabs(v));
+            u -= delta;
+            v += delta;
+            if (u > 1.0 || v < -1.0) return 0;  // the cosines live in [-1, 1]
+            u = fmax(u, -1.0);
+            v = fmin(v, 1.0);
+            const double tu = u * (4 * u * u - 3), tv = v * (4 * v * v - 3);
+            double tmin = fmin(tu, tv), tmax = fmax(tu, tv);
+            if (u <= -0.5 && v >= -0.5) tmax = 1.0;   // interior maximum of T3 at c = -1/2
+            if (u <= 0.5 && v >= 0.5) tmin = -1.0;    // interior minimum at c = +1/2
+            return !(x < tmin - 4e-14 || x > tmax + 4e-14) ? 1 : 0;
+        }
+        const double sgn = (R > 0) ? 1.0 : -1.0;
+        const double A = -sgn * cbrt(fabs(R) + sqrt(R2 - Q3));
+        if (!(fabs(fabs(A) - CLSN_ROUND_EPS) > 1e-20)) return 2;  // the |A| < 1e-10 switch could flip
+        const double Bv = (fabs(A) < CLSN_ROUND_EPS) ? 0.0 : Q / A;
+        const double g = (fabs(A) + fabs(Bv) + fabs(a)) * 1e-13;
+        const double r0 = (A + Bv) - a / 3.0;
+        bool maybe = !(r0 < -g || r0 > dt + g);
+        if (!(fabs(A - Bv) > 2 * CLSN_ROUND_EPS)) {  // the double-root branch (|A-B| < 1e-10) may be taken
+            const double rr = -0.5 * (A + Bv) - a / 3.0;
+            maybe = maybe || !(rr < -g || rr > dt + g);
+        }
+        return maybe ? 2 : 0;
+    }
+    // quadratic / linear fall-backs use IEEE operations only: evaluate them as the reference does
+    a = b; b = c; c = d;
+    const double delta = b * b - 4.0 * a * c;
+    double r0 = -1.0, r1 = -1.0;
+    if (fabs(a) > CLSN_ROUND_EPS && delta > 0) {
+        const double ds = sqrt(delta);
+        r0 = (-b + ds) / (2.0 * a);
+        r1 = (-b - ds) / (2.0 * a);
+    } else if (fabs(a) < CLSN_ROUND_EPS && fabs(b) > CLSN_ROUND_EPS) {
+        r0 = -c / b;
+    }
+    r0 -= CLSN_MACH_EPS;
+    r1 -= CLSN_MACH_EPS;
+    const bool ok0 = !(r0 < 0 || r0 > dt), ok1 = !(r1 < 0 || r1 > dt);
+    return (ok0 || ok1) ? 2 : 0;
+}
+
+// isCoplanar, dcollid3d.cpp:371-482.  Returns true iff some root > MACH_EPS; roots[0..2] sorted.
+// CLASSIFY = false when the caller has already run coplanar_maybe() on this feature (k_cull).
+template <bool CLASSIFY>
+CLSN_HD bool is_coplanar(const Quad& q, double dt, double* roots)
+{
+    double a, b, c, d;
+    coplanar_coeffs(q, a, b, c, d);
+    if (CLASSIFY && !coplanar_maybe(a, b, c, d, dt)) return false;  // every root provably outside [0, dt]
+    if (fabs(a) > CLSN_MACH_EPS) {
+        b /= a; c /= a; d /= a;
+        a = b; b = c; c = d;
+        double Q = (a * a - 3 * b) / 9;
+        double R = (2 * a * a * a - 9 * a * b + 27 * c) / 54;
+        double Q3 = Q * Q * Q, R2 = R * R;
+        if (R2 < Q3) {
+            double Qsqrt = sqrt(Q);
+            const double arg = R / sqrt(Q3);
+            const double two_pi = 2 * 3.14159265358979323846;
+            // Which of the three roots can survive the [0, dt] filter?  Root k is -S cos(phi_k) - a/3 with
+            // phi_0 in [0, pi/3], phi_1 in [2pi/3, pi], phi_2 in [-2pi/3, -pi/3], i.e. its cosine lies in
+            // [1/2, 1], [-1, -1/2], [-1/2, 1/2] respectively, and a valid root has its cosine in the (tiny)
+            // interval [u, v] derived in coplanar_maybe().  Only the overlapping k are evaluated (correctly
+            // rounded); the others get -1, which is what the filter below would turn them into anyway.
+            const double S = 2 * Qsqrt, A3 = a / 3;
+            bool need0 = true, need1 = true, need2 = true;
+            if (S > 0.0 && fabs(arg) <= 1.0) {
+                const double eta = 4e-16 * (2 * S + fabs(A3) + dt) + 2 * CLSN_MACH_EPS;
+                double u = -(dt + A3 + eta) / S;
+                double v = -(A3 - eta) / S;
+                const double delta = 4e-15 + 4e-16 * (fabs(u) + fabs(v));
+                u -= delta;
+                v += delta;
+                const double e = 1e-14;
+                need0 = !(v < 0.5 - e);                      // overlaps [1/2, 1]
+                need1 = !(u > -0.5 + e);                     // overlaps [-1, -1/2]
+                need2 = !(v < -0.5 - e || u > 0.5 + e);      // overlaps [-1/2, 1/2]
+            }
+            if (need0 || need1 || need2) {
+                const double theta = crm::acos_cr(arg);
+                if (need0) roots[0] = -2 * Qsqrt * crm::cos_cr(theta / 3) - a / 3;
+                if (need1) roots[1] = -2 * Qsqrt * crm::cos_cr((theta + two_pi) / 3) - a / 3;
+                if (need2) roots[2] = -2 * Qsqrt * crm::cos_cr((theta - two_pi) / 3) - a / 3;
+            }
+        } else {
+            double sgn = (R > 0) ? 1.0 : -1.0;
+            double A = -sgn * crm::pow13_cr(fabs(R) + sqrt(R2 - Q3));
+            double Bv = (fabs(A) < CLSN_ROUND_EPS) ? 0.0 : Q / A;
+            roots[0] = (A + Bv) - a / 3.0;
+            if (fabs(A - Bv) < CLSN_ROUND_EPS) roots[1] = roots[2] = -0.5 * (A + Bv) - a / 3.0;
+        }
+    } else {
+        a = b; b = c; c = d;
+        double delta = b * b - 4.0 * a * c;
+        if (fabs(a) > CLSN_ROUND_EPS && delta > 0) {
+            double ds = sqrt(delta);
+            roots[0] = (-b + ds) / (2.0 * a);
+            roots[1] = (-b - ds) / (2.0 * a);
+        } else if (fabs(a) < CLSN_ROUND_EPS && fabs(b) > CLSN_ROUND_EPS) {
+            roots[0] = -c / b;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        roots[i] = roots[i] - CLSN_MACH_EPS;
+        if (roots[i] < 0 || roots[i] > dt) roots[i] = -1;
+    }
+    double t;
+    if (roots[0] > roots[1]) { t = roots[0]; roots[0] = roots[1]; roots[1] = t; }
+    if (roots[0] > roots[2]) { t = roots[0]; roots[0] = roots[2]; roots[2] = t; }
+    if (roots[1] > roots[2]) { t = roots[1]; roots[1] = roots[2]; roots[2] = t; }
+    return roots[0] > CLSN_MACH_EPS || roots[1] > CLSN_MACH_EPS || roots[2] > CLSN_MACH_EPS;
+}
+
+} // namespace clsn

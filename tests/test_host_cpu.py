@@ -120,3 +120,18 @@ def test_record_exchange_gloo_world3():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 3
+
+
+def test_cubic_path_matches_oracle_on_host():
+    """collision_b200/csrc/cubic.cuh -- the CUDA path's isCoplanar (coefficients, trig-free classifier,
+    selective correctly rounded solve) -- compiled for the host and fuzzed against the oracle's
+    is_coplanar (binary128 libm flavour): identical return value and root bits on every case, and no
+    cubic that the classifier rejects has a root the oracle keeps.  (48 M cases were run once by hand.)"""
+    from oracle import port
+    so = port.build()
+    exe = "/tmp/clsn_cubic_check"
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-mfma", "-x", "c++", "-I", os.path.join(ROOT, "collision_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "cubic_check.cpp"), "-o", exe, "-ldl", "-lm"])
+    n, bad, rejected, rejected_wrong, oracle_true = map(int, subprocess.check_output([exe, so, "2000000", "7"], text=True).split())
+    assert n == 2000000 and bad == 0 and rejected_wrong == 0
+    assert rejected > n // 4 and oracle_true > n // 4   # both outcomes are well represented
