@@ -118,3 +118,58 @@ def test_sample_of_config4_matches_oracle():
         g.close()
     finally:
         port.set_libm(port.LIBM_NATIVE)
+
+
+def test_config1_string_string_200_steps():
+    """Config 1 (in-string_string restated: two crossing strings of 192 bonds): 200 steps, every step the
+    drop-in call against the oracle's resolve, bit for bit; the strings must actually meet."""
+    sc = scenes.string_string(dt=0.01, gap=0.01)
+    port.set_libm(port.LIBM_CR)
+    try:
+        orc = port.OracleSolver(sc)
+        g = _solver(sc)
+        x, vel = sc.x.copy(), sc.vel.copy()
+        hits = 0
+        for step in range(200):
+            xn = x + sc.dt * vel
+            orc.set_state(x, xn)
+            vo = vel.copy()
+            st_o = orc.resolve(vo)
+            xg, vg = xn.copy(), vel.copy()
+            g.resolveCollision(x, xg, vg)
+            assert same_bits(xg, orc.get(port.F_X)) and same_bits(vg, vo), f"step {step}"
+            hits += sum(st_o[2:2 + st_o[1]])
+            x, vel = xg, vg
+        assert hits > 0
+        g.close()
+    finally:
+        port.set_libm(port.LIBM_NATIVE)
+
+
+def test_config3_full_size_step_matches_oracle():
+    """Config 3 at full size (256 x 256 sheet on a static level-5 icosphere, 150 530 triangles): four whole
+    steps of the drape against the oracle, bit for bit."""
+    sc = scenes.drape(256, 5)
+    assert sc.T == 150_530
+    port.set_libm(port.LIBM_CR)
+    try:
+        orc = port.OracleSolver(sc)
+        g = _solver(sc)
+        g.set_exact_stats(True)
+        x, vel = sc.x.copy(), sc.vel.copy()
+        for step in range(4):
+            xn = x + sc.dt * vel
+            orc.set_state(x, xn)
+            vo = vel.copy()
+            st_o = orc.resolve(vo)
+            xg, vg = xn.copy(), vel.copy()
+            has = g.resolveCollision(x, xg, vg)
+            st = g.last_stats
+            assert [p["true_pairs"] for p in st["ccd"]] == st_o[2:2 + st_o[1]] and sum(st_o[2:2 + st_o[1]]) > 0
+            assert [p["candidates"] for p in st["ccd"]] == st_o[9:9 + st_o[1]]
+            assert same_bits(xg, orc.get(port.F_X)) and same_bits(vg, vo)
+            assert np.array_equal(has, orc.geti(port.I_HAS_COLLSN))
+            x, vel = xg, vg
+        g.close()
+    finally:
+        port.set_libm(port.LIBM_NATIVE)
