@@ -37,6 +37,9 @@ struct orc_ctx {
     /* union-find lists of createImpZoneForRG (dcollid3d.cpp:54-68), topology only */
     int *uf_root, *uf_next, *uf_tail, *uf_weight;
     int uf_ready;
+    int det_imp_zone;  /* s_detImpZone, dcollid.cpp:28 */
+    int impact_zones;  /* run computeImpactZone from orc_resolve when passes are exhausted */
+    unsigned char* sorted;
     /* results of the last detect */
     int* cand; long n_cand, cap_cand;
     int* truep; long n_true, cap_true;
@@ -463,6 +466,21 @@ static int elem_rigid(const orc_ctx* c, const int* pts, int n) /* isRigidBody(CD
     return 0;
 }
 
+static void uf_merge(orc_ctx* c, int X, int Y);
+static void uf_build(orc_ctx* c);
+/* createImpZone(pts, 4, first = NO), dcollid.cpp:473-484: movable-rigid points never join a zone */
+static void create_imp_zone(orc_ctx* c, const int* p)
+{
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < i; ++j) {
+            if (is_movable(c, p[i]) || is_movable(c, p[j])) continue;
+            uf_merge(c, p[i], p[j]);
+        }
+}
+/* `if (status && is_detImpZone) createImpZone(pts,4)` after every Moving* feature test
+ * (dcollid3d.cpp:222-240, :268, :301, :320): status is sticky within the element pair */
+#define ZONE_HOOK() do { if (status && moving && c->det_imp_zone) create_imp_zone(c, p); } while (0)
+
 /* TriToTri (dcollid3d.cpp:570-627) / MovingTriToTri (:274-325) */
 static int tri_tri(orc_ctx* c, int moving, const int* A, const int* Bt, double h, tag_t* tag)
 {
@@ -478,11 +496,13 @@ static int tri_tri(orc_ctx* c, int moving, const int* A, const int* Bt, double h
             const int* other = moving ? (k == 0 ? Bt : A) : (k == 0 ? A : Bt);
             p[0] = tri[0]; p[1] = tri[1]; p[2] = tri[2]; p[3] = other[i];
             if (feature_test(c, moving, 0, p, h, tag)) status = 1;
+            ZONE_HOOK();
         }
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) {
             p[0] = A[i]; p[1] = A[(i + 1) % 3]; p[2] = Bt[j]; p[3] = Bt[(j + 1) % 3];
             if (feature_test(c, moving, 1, p, h, tag)) status = 1;
+            ZONE_HOOK();
         }
     return status;
 }
@@ -496,12 +516,15 @@ static int tri_bond(orc_ctx* c, int moving, const int* tri, const int* bd, doubl
     p[0] = tri[0]; p[1] = tri[1]; p[2] = tri[2];
     p[3] = bd[0];
     if (feature_test(c, moving, 0, p, h, tag)) status = 1;
+    ZONE_HOOK();
     p[3] = bd[1];
     if (feature_test(c, moving, 0, p, h, tag)) status = 1;
+    ZONE_HOOK();
     p[2] = bd[0]; p[3] = bd[1];
     for (int i = 0; i < 3; ++i) {
         p[0] = tri[i]; p[1] = tri[(i + 1) % 3];
         if (feature_test(c, moving, 1, p, h, tag)) status = 1;
+        ZONE_HOOK();
     }
     return status;
 }
@@ -513,7 +536,9 @@ static int bond_bond(orc_ctx* c, int moving, const int* b1, const int* b2, doubl
     for (int i = 0; i < 4; ++i)
         for (int j = i + 1; j < 4; ++j)
             if (p[i] == p[j]) return 0;
-    return feature_test(c, moving, 1, p, h, tag);
+    int status = feature_test(c, moving, 1, p, h, tag);
+    ZONE_HOOK();
+    return status;
 }
 
 /* isProximity / isCollision, dcollid.cpp:753-836: dispatch + same-surface rigid filter */
@@ -661,6 +686,7 @@ static void broad_phase(orc_ctx* c, int moving)
 long orc_detect(orc_ctx* c, int mode)
 {
     int moving = mode == ORC_COLLISION;
+    if (c->det_imp_zone && !c->uf_ready) uf_build(c);
     broad_phase(c, moving);
     c->n_con = 0;
     c->n_true = 0;
@@ -685,6 +711,7 @@ long orc_detect(orc_ctx* c, int mode)
 long orc_detect_ordered(orc_ctx* c, int mode, const int* pairs, long n)
 {
     int moving = mode == ORC_COLLISION;
+    if (c->det_imp_zone && !c->uf_ready) uf_build(c);
     c->n_con = 0;
     c->n_true = 0;
     for (long q = 0; q < n; ++q) {
@@ -853,6 +880,51 @@ void orc_apply(orc_ctx* c, int rigidify)
     }
 }
 
+/* updateImpactZoneVelocity, dcollid.cpp:290-309: every union-find set with more than one point
+ * (impact zones and movable bodies alike) is made to move rigidly; returns the number of sets */
+int orc_zone_velocity(orc_ctx* c)
+{
+    int zones = 0;
+    if (!c->uf_ready) uf_build(c);
+    memset(c->sorted, 0, (size_t)c->V);
+    for (int e = 0; e < c->N; ++e) {
+        const int* pts = e < c->T ? c->tri + 3 * e : c->bond + 2 * (e - c->T);
+        int n = e < c->T ? 3 : 2;
+        for (int i = 0; i < n; ++i) {
+            int p = pts[i], r = uf_find(c, p);
+            if (c->sorted[p] || c->uf_weight[r] == 1) continue;
+            for (int q = r; q >= 0; q = c->uf_next[q]) c->sorted[q] = 1;
+            if (c->dt > 0.0) rigidify_list(c, r);
+            zones++;
+        }
+    }
+    return zones;
+}
+
+void orc_set_imp_zone(orc_ctx* c, int on) { c->det_imp_zone = on; } /* turnOn/OffImpZone, dcollid.cpp:222-223 */
+void orc_enable_impact_zones(orc_ctx* c, int on) { c->impact_zones = on; }
+
+/* computeImpactZone, dcollid.cpp:227-265.  out[0] iterations, out[1] zones in the last iteration,
+ * out[2] true pairs summed over the iterations.  The reference loops without bound; `max_iter`
+ * (<= 0: 100000) only guards the test harness, hitting it sets the error flag. */
+void orc_impact_zone(orc_ctx* c, int max_iter, long* out)
+{
+    int is_collision = 1, zones = 0;
+    long it = 0, pairs = 0;
+    if (max_iter <= 0) max_iter = 100000;
+    c->det_imp_zone = 1;
+    while (is_collision) {
+        long n = orc_detect(c, ORC_COLLISION);
+        is_collision = n > 0;
+        pairs += n;
+        orc_apply(c, 1);
+        zones = orc_zone_velocity(c);
+        if (++it >= max_iter && is_collision) { c->error = 1; break; }
+    }
+    c->det_imp_zone = 0;
+    if (out) { out[0] = it; out[1] = zones; out[2] = pairs; }
+}
+
 /* detectDomainBoundaryCollision, dcollid.cpp:116-158 -- once per unique point */
 void orc_boundary(orc_ctx* c)
 {
@@ -893,7 +965,7 @@ void orc_final_velocity(orc_ctx* c, double* vel) /* dcollid.cpp:598-624 */
 /* resolveCollision, dcollid.cpp:317-362, with detectProximity :390-406 and detectCollision :430-468 */
 void orc_resolve(orc_ctx* c, double* vel, long* stats)
 {
-    for (int i = 0; i < 14; ++i) stats[i] = 0;
+    for (int i = 0; i < 16; ++i) stats[i] = 0;
     orc_avg_velocity(c);
     stats[0] = orc_detect(c, ORC_PROXIMITY);
     stats[8] = c->n_cand;
@@ -909,7 +981,12 @@ void orc_resolve(orc_ctx* c, double* vel, long* stats)
         if (++niter > MAX_ITER) break;
     }
     stats[1] = cd;
-    stats[7] = is_collision; /* the reference would now enter computeImpactZone (out of scope) */
+    stats[7] = is_collision; /* the reference now enters computeImpactZone (dcollid.cpp:466) */
+    if (is_collision && c->impact_zones) {
+        long z[3];
+        orc_impact_zone(c, 0, z);
+        stats[14] = z[0]; stats[15] = z[1];
+    }
     orc_boundary(c);
     orc_final_position(c);
     orc_final_velocity(c, vel);
@@ -949,6 +1026,7 @@ orc_ctx* orc_create(int V, int T, const int* tri_idx, const int* tri_surf, int B
     c->uf_next = (int*)malloc((size_t)(V + 1) * sizeof(int));
     c->uf_tail = (int*)malloc((size_t)(V + 1) * sizeof(int));
     c->uf_weight = (int*)malloc((size_t)(V + 1) * sizeof(int));
+    c->sorted = (unsigned char*)calloc((size_t)V + 1, 1);
     return c;
 }
 
@@ -957,7 +1035,7 @@ void orc_destroy(orc_ctx* c)
     if (!c) return;
     free(c->tri); free(c->tri_surf); free(c->bond); free(c->flags); free(c->vhs); free(c->hs_mass);
     free(c->xo); free(c->x); free(c->av); free(c->imp); free(c->fric); free(c->cnt); free(c->has);
-    free(c->imp_rg); free(c->cnt_rg); free(c->uf_root); free(c->uf_next); free(c->uf_tail); free(c->uf_weight);
+    free(c->imp_rg); free(c->cnt_rg); free(c->uf_root); free(c->uf_next); free(c->uf_tail); free(c->uf_weight); free(c->sorted);
     free(c->cand); free(c->truep); free(c->con);
     free(c);
 }
@@ -981,6 +1059,7 @@ void orc_set_state(orc_ctx* c, const double* x_old, const double* x_new)
     memset(c->fric, 0, n * sizeof(double));
     memset(c->cnt, 0, (size_t)c->V * sizeof(int));
     memset(c->has, 0, (size_t)c->V); /* recordOriginPosition clears has_collsn, dcollid.cpp:100 */
+    c->uf_ready = 0;                 /* makeSet in assembleFromInterface, dcollid3d.cpp:44 */
 }
 void orc_set_avgvel(orc_ctx* c, const double* av) { memcpy(c->av, av, (size_t)3 * c->V * sizeof(double)); }
 

@@ -65,8 +65,16 @@ void orc_final_velocity(orc_ctx*, double* vel);  /* dcollid.cpp:598-624, vel upd
 /* whole step (dcollid.cpp:317-362 minus reduceSuperelast and the impact-zone fail-safe).
  * stats[0] proximity pairs true, stats[1] #CCD passes, stats[2..6] true pairs per CCD pass,
  * stats[7] 1 if still colliding after MAX_ITER passes, stats[8] candidates proximity,
- * stats[9..13] candidates per CCD pass */
+ * stats[9..13] candidates per CCD pass, stats[14] impact-zone iterations, stats[15] zones (16 longs) */
 void orc_resolve(orc_ctx*, double* vel, long* stats);
+
+/* Impact-zone fail-safe (computeImpactZone, dcollid.cpp:227-265; createImpZone :473-484;
+ * updateImpactZoneVelocity :290-309).  orc_enable_impact_zones makes orc_resolve enter it when
+ * MAX_ITER passes leave collisions; the pieces are exposed for phase-by-phase pinning. */
+void orc_enable_impact_zones(orc_ctx*, int on);
+void orc_set_imp_zone(orc_ctx*, int on);            /* turnOnImpZone / turnOffImpZone */
+int orc_zone_velocity(orc_ctx*);                    /* updateImpactZoneVelocity -> number of zones */
+void orc_impact_zone(orc_ctx*, int max_iter, long* out3);
 
 /* readbacks */
 void orc_get_f64(orc_ctx*, int field, double* out); /* 0 x_old 1 x 2 avgVel 3 imp 4 fric (3V each) */

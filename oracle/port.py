@@ -71,6 +71,11 @@ def lib():
         L.orc_final_position.argtypes = [V]
         L.orc_final_velocity.argtypes = [V, P(D)]
         L.orc_resolve.argtypes = [V, P(D), P(C.c_long)]
+        L.orc_enable_impact_zones.argtypes = [V, I]
+        L.orc_set_imp_zone.argtypes = [V, I]
+        L.orc_zone_velocity.argtypes = [V]
+        L.orc_zone_velocity.restype = I
+        L.orc_impact_zone.argtypes = [V, I, P(C.c_long)]
         L.orc_get_f64.argtypes = [V, I, P(D)]
         L.orc_get_i32.argtypes = [V, I, P(I)]
         L.orc_get_body.argtypes = [V, P(D), P(I)]
@@ -164,9 +169,23 @@ class OracleSolver:
 
     def resolve(self, vel):
         assert vel.dtype == np.float64 and vel.flags.c_contiguous
-        stats = (C.c_long * 14)()
+        stats = (C.c_long * 16)()
         lib().orc_resolve(self.h, _dp(vel), stats)
         return list(stats)
+
+    def enable_impact_zones(self, on=True):
+        lib().orc_enable_impact_zones(self.h, 1 if on else 0)
+
+    def set_imp_zone(self, on):
+        lib().orc_set_imp_zone(self.h, 1 if on else 0)
+
+    def zone_velocity(self) -> int:
+        return int(lib().orc_zone_velocity(self.h))
+
+    def impact_zone(self, max_iter=0):
+        out = (C.c_long * 3)()
+        lib().orc_impact_zone(self.h, int(max_iter), out)
+        return list(out)
 
     def get(self, field) -> np.ndarray:
         out = np.empty((self.V, 3), dtype=np.float64)

@@ -17,7 +17,8 @@ LIB_PATH = os.path.join(_HERE, "_ref", "libcollision_ref.so")
 F_X_OLD, F_COORDS, F_VEL, F_AVGVEL, F_IMP, F_FRIC, F_IMP_RG = range(7)
 I_CNT, I_CNT_RG, I_HAS_COLLSN = range(3)
 (PH_AVG_VELOCITY, PH_PROXIMITY_DETECT, PH_APPLY, PH_COLLISION_DETECT, PH_BOUNDARY, PH_FINAL_POSITION,
- PH_STRAIN_LIMIT, PH_FINAL_VELOCITY, PH_DETECT_PROXIMITY, PH_DETECT_COLLISION) = range(10)
+ PH_STRAIN_LIMIT, PH_FINAL_VELOCITY, PH_DETECT_PROXIMITY, PH_DETECT_COLLISION,
+ PH_IMPZONE_ON, PH_IMPZONE_OFF, PH_ZONE_VELOCITY, PH_COMPUTE_IMPACT_ZONE) = range(14)
 K_ISCOPLANAR, K_POINT_TO_TRI, K_EDGE_TO_EDGE, K_MOVING_POINT_TO_TRI, K_MOVING_EDGE_TO_EDGE = range(5)
 
 _lib = None

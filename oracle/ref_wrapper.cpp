@@ -488,6 +488,10 @@ int clsn_ref_phase(void* h, int phase)
             s->detectCollision();
             ret = s->hasCollision() ? 1 : 0;
             break;
+        case 10: s->turnOnImpZone(); break;
+        case 11: s->turnOffImpZone(); break;
+        case 12: s->updateImpactZoneVelocity(ret); break;
+        case 13: s->computeImpactZone(); break;
         default: return -2;
         }
     } catch (const clsn_ref_abort&) {

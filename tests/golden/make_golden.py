@@ -118,6 +118,10 @@ SCENES = {
     "mixed": (lambda: scenes.mixed(), 3),
     "ball_plane": (lambda: scenes.ball_plane(level=2, gap=2e-4), 2),
     "sheet_wall": (lambda: scenes.sheet_wall(n=10), 2),
+    # scenes that leave collisions after the 5 CCD passes and enter computeImpactZone
+    "mixed_zone": (lambda: scenes.mixed(), 4),
+    "layered_zone": (lambda: scenes.layered_cloth(4, 13, speed=3.0), 1),
+    "sheets_zone": (lambda: scenes.two_sheets(n=10, speed=10.0), 1),
 }
 
 
@@ -131,6 +135,8 @@ def make_scene(name, path):
         xn = x + sc.dt * vel
         r.set_state(x, xn, vel)
         r.assemble(sc.dt)
+        if name.endswith("_zone"):  # recordOriginPosition clears has_collsn every step (dcollid.cpp:100)
+            r.puti(ref.I_HAS_COLLSN, np.zeros(sc.V, np.int32))
         r.phase(ref.PH_AVG_VELOCITY)
         out[f"s{step}_x_old"] = x.copy()
         out[f"s{step}_avgvel0"] = r.get(ref.F_AVGVEL)
@@ -152,6 +158,24 @@ def make_scene(name, path):
             if ps > 0 and n == 0:
                 break
         out[f"s{step}_npass"] = np.int32(npass)
+        nzone = 0
+        if name.endswith("_zone") and n > 0:  # computeImpactZone, dcollid.cpp:227-265, phase by phase
+            r.phase(ref.PH_IMPZONE_ON)
+            while True:
+                r.record(True)
+                n = r.phase(ref.PH_COLLISION_DETECT)
+                k = f"s{step}_z{nzone}_"
+                out[k + "pairs"] = r.pairs()
+                out[k + "count"] = np.int64(n)
+                r.phase(ref.PH_APPLY)
+                out[k + "avgvel"] = r.get(ref.F_AVGVEL)
+                out[k + "zones"] = np.int32(r.phase(ref.PH_ZONE_VELOCITY))
+                out[k + "zvel"] = r.get(ref.F_AVGVEL)
+                nzone += 1
+                if n == 0:
+                    break
+            r.phase(ref.PH_IMPZONE_OFF)
+        out[f"s{step}_nzone"] = np.int32(nzone)
         r.phase(ref.PH_BOUNDARY)
         r.phase(ref.PH_FINAL_POSITION)
         r.phase(ref.PH_FINAL_VELOCITY)
@@ -166,6 +190,9 @@ def make_scene(name, path):
 if __name__ == "__main__":
     if not ref.available():
         raise SystemExit("oracle/_ref/libcollision_ref.so missing: run `make -C oracle ref` (needs /root/reference)")
-    make_features(os.path.join(HERE, "features.npz"))
+    if not sys.argv[1:]:
+        make_features(os.path.join(HERE, "features.npz"))
+    only = sys.argv[1:]
     for name in SCENES:
-        make_scene(name, os.path.join(HERE, f"scene_{name}.npz"))
+        if not only or name in only:
+            make_scene(name, os.path.join(HERE, f"scene_{name}.npz"))

@@ -100,6 +100,85 @@ def test_scene_replay_bit_exact(name):
         assert total_true > 0
 
 
+ZONE_SCENES = {
+    "mixed_zone": lambda: scenes.mixed(),
+    "layered_zone": lambda: scenes.layered_cloth(4, 13, speed=3.0),
+    "sheets_zone": lambda: scenes.two_sheets(n=10, speed=10.0),
+}
+
+
+@pytest.mark.parametrize("name", list(ZONE_SCENES))
+def test_impact_zone_replay_bit_exact(name):
+    """Scenes that still collide after the 5 CCD passes: the restatement of computeImpactZone
+    (createImpZone merges inside the narrow phase, updateImpactZoneVelocity) replays the reference's
+    callback sequence and must reproduce avgVel after every iteration, the zone counts and the final
+    state bit for bit."""
+    sc = ZONE_SCENES[name]()
+    d = np.load(os.path.join(G, f"scene_{name}.npz"))
+    o = port.OracleSolver(sc)
+    vel = sc.vel.copy()
+    zone_iters = 0
+    for step in range(int(d["n_steps"])):
+        x = d[f"s{step}_x_old"]
+        o.set_state(x, x + sc.dt * vel)
+        o.avg_velocity()
+        assert same_bits(o.get(port.F_AVGVEL), d[f"s{step}_avgvel0"])
+        for ps in range(int(d[f"s{step}_npass"])):
+            k = f"s{step}_p{ps}_"
+            n_true = o.detect_ordered(port.PROXIMITY if ps == 0 else port.COLLISION, d[k + "pairs"])
+            assert n_true == int(d[k + "count"])
+            assert same_bits(o.get(port.F_IMP), d[k + "imp"]) and same_bits(o.get(port.F_FRIC), d[k + "fric"])
+            assert np.array_equal(o.geti(port.I_CNT), d[k + "cnt"])
+            o.apply(True)
+            assert same_bits(o.get(port.F_AVGVEL), d[k + "avgvel"]), f"{k}: avgVel"
+        nz = int(d[f"s{step}_nzone"])
+        if nz:
+            o.set_imp_zone(True)
+            for it in range(nz):
+                k = f"s{step}_z{it}_"
+                assert o.detect_ordered(port.COLLISION, d[k + "pairs"]) == int(d[k + "count"])
+                o.apply(True)
+                assert same_bits(o.get(port.F_AVGVEL), d[k + "avgvel"]), f"{k}: avgVel before the zones"
+                assert o.zone_velocity() == int(d[k + "zones"])
+                assert same_bits(o.get(port.F_AVGVEL), d[k + "zvel"]), f"{k}: avgVel after updateImpactZoneVelocity"
+            assert int(d[f"s{step}_z{nz - 1}_count"]) == 0      # the loop ends on a collision-free pass
+            o.set_imp_zone(False)
+            zone_iters += nz
+        o.boundary()
+        o.final_position()
+        o.final_velocity(vel)
+        assert same_bits(o.get(port.F_X), d[f"s{step}_x"])
+        assert np.array_equal(o.geti(port.I_HAS_COLLSN), d[f"s{step}_has"])
+        assert same_bits(vel, d[f"s{step}_vel"])
+    assert zone_iters >= 2
+
+
+def test_impact_zone_loop_in_resolve():
+    """orc_resolve with the fail-safe enabled == the phase-by-phase loop, and it ends collision free."""
+    sc = scenes.layered_cloth(4, 13, speed=3.0)
+    o1, o2 = port.OracleSolver(sc), port.OracleSolver(sc)
+    o1.enable_impact_zones(True)
+    v1, v2 = sc.vel.copy(), sc.vel.copy()
+    o1.set_state(sc.x, sc.x + sc.dt * sc.vel)
+    st = o1.resolve(v1)
+    assert st[7] == 1 and st[14] >= 2 and st[15] >= 1
+    o2.set_state(sc.x, sc.x + sc.dt * sc.vel)
+    o2.avg_velocity()
+    o2.detect(port.PROXIMITY)
+    o2.apply(True)
+    for _ in range(5):
+        n = o2.detect(port.COLLISION)
+        o2.apply(True)
+    assert n > 0
+    out = o2.impact_zone()
+    assert out[0] == st[14] and out[1] == st[15]
+    o2.boundary(); o2.final_position(); o2.final_velocity(v2)
+    assert same_bits(o1.get(port.F_X), o2.get(port.F_X)) and same_bits(v1, v2)
+    o2.set_state(o2.get(port.F_X_OLD), o2.get(port.F_X))
+    o2.avg_velocity()
+    assert o2.detect(port.COLLISION) == 0
+
+
 def test_canonical_order_is_order_independent_for_sets():
     """canonical (a<b sorted) evaluation finds the same candidate set and, for point-triangle-only
     contacts (static sphere), the same per-point sums up to summation order (<= 1e-12 relative)."""
