@@ -18,6 +18,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "narrow.cuh"
@@ -483,6 +484,14 @@ struct clsn_ctx {
     DevBuf<int> vbody;
     DevBuf<double> body_mass;
     RigidTopo rigid;
+    // impact zones (host fail-safe): host topology + union-find, device lists
+    std::vector<int> h_tri, h_tri_surf, h_bond;
+    std::vector<uint8_t> h_vflags;
+    HostUF zone_uf;
+    bool zone_uf_ready = false, zone_lists_stale = true;
+    RigidTopo zone_lists;
+    bool impact_zones = false;
+    int zone_max_iter = 0;
     // state
     DevBuf<Vec4> xo, xn, av;
     DevBuf<uint8_t> has, dirty;
@@ -608,7 +617,7 @@ extern "C" void clsn_destroy(clsn_ctx* c)
     c->cub_tmp.release(); c->pairs.release(); c->dbg_cand.release(); c->feats.release(); c->pair_hit.release(); c->rootrecs.release(); c->prec.release(); c->prec_sorted.release(); c->brec.release();
     c->contacts.release(); c->cnt.release(); c->offs.release(); c->fill.release(); c->perm.release();
     c->perm_sorted.release(); c->skey.release(); c->counters.release(); c->acc_imp.release(); c->acc_fric.release();
-    c->rigid.release();
+    c->rigid.release(); c->zone_lists.release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     for (auto& e : c->ev) cudaEventDestroy(e);
@@ -727,6 +736,11 @@ extern "C" int clsn_set_topology(clsn_ctx* c, int V, int T, const int32_t* tri_i
     if (c->brec.n == 0) CK(c->brec.reserve(4096));
     c->tree_built = false;
     c->records_pending = false;
+    c->h_tri.assign(tri_idx, tri_idx + 3 * (size_t)T);
+    c->h_tri_surf.assign(tri_surf, tri_surf + T);
+    c->h_bond.assign(bond_idx, bond_idx + 2 * (size_t)B);
+    c->h_vflags.assign(vflags, vflags + V);
+    c->zone_uf_ready = false;
     // host-side restatement of createImpZoneForRG's union-find lists (topology only)
     int r = c->rigid.build(V, T, tri_idx, tri_surf, vflags);
     if (r != 0) return fail(c, CLSN_E_CUDA, "rigid-body topology upload failed");
@@ -747,6 +761,7 @@ static int begin_step(clsn_ctx* c)
     c->records_pending = false;
     c->dirty_valid = false;
     c->last_detect_mode = -1;
+    c->zone_uf_ready = false;  // makeSet: the impact zones live for one step (dcollid3d.cpp:44)
     return CLSN_OK;
 }
 
@@ -1104,6 +1119,142 @@ extern "C" int clsn_final_position(clsn_ctx* c)
     return CLSN_OK;
 }
 
+// ------------------------------------------------------------------ impact zones
+// computeImpactZone, dcollid.cpp:227-265: the fail-safe the reference enters when MAX_ITER CCD passes
+// leave collisions.  Every iteration is one full CCD pass + updateAverageVelocity on the GPU, plus
+//   * createImpZone (dcollid.cpp:473-484) for every feature test of a pair from its first hit on
+//     (`status` is sticky inside Moving*To*, dcollid3d.cpp:203-325): the hits come back as contact
+//     records, the host replays the merges in canonical order (pairs by (a,b), features in loop
+//     order) on the reference's union-find, whose list order is part of the result;
+//   * updateImpactZoneVelocity (dcollid.cpp:290-309): every set of more than one point -- zones and
+//     movable bodies alike -- is made to move rigidly by the same kernels as rigid.cuh's bodies.
+// Host work is O(contacts) per iteration (+ one O(elements) list flattening when a merge happened).
+static int pair_features(int T, int ea, int eb) { return ea < T && eb < T ? 15 : (ea < T ? 5 : 1); }
+
+static void feature_points(const clsn_ctx* c, int ea, int eb, int f, int p[4])
+{
+    const int T = c->T;
+    const int* A = ea < T ? &c->h_tri[3 * (size_t)ea] : &c->h_bond[2 * (size_t)(ea - T)];
+    const int* B = eb < T ? &c->h_tri[3 * (size_t)eb] : &c->h_bond[2 * (size_t)(eb - T)];
+    if (ea < T && eb < T) {  // MovingTriToTri, dcollid3d.cpp:274-325
+        if (f < 3) { p[0] = A[0]; p[1] = A[1]; p[2] = A[2]; p[3] = B[f]; }
+        else if (f < 6) { p[0] = B[0]; p[1] = B[1]; p[2] = B[2]; p[3] = A[f - 3]; }
+        else {
+            const int i = (f - 6) / 3, j = (f - 6) % 3;
+            p[0] = A[i]; p[1] = A[(i + 1) % 3]; p[2] = B[j]; p[3] = B[(j + 1) % 3];
+        }
+    } else if (ea < T) {     // MovingTriToBond, :203-244 (triangles precede bonds in hseList)
+        if (f < 2) { p[0] = A[0]; p[1] = A[1]; p[2] = A[2]; p[3] = B[f]; }
+        else { const int i = f - 2; p[0] = A[i]; p[1] = A[(i + 1) % 3]; p[2] = B[0]; p[3] = B[1]; }
+    } else {                 // MovingBondToBond, :246-272
+        p[0] = A[0]; p[1] = A[1]; p[2] = B[0]; p[3] = B[1];
+    }
+}
+
+// all sets of more than one point, in order of first appearance in hseList (updateImpactZoneVelocity)
+static int upload_zone_lists(clsn_ctx* c)
+{
+    HostUF& uf = c->zone_uf;
+    std::vector<int> offs(1, 0), pts, pt_list;
+    std::vector<uint8_t> seen((size_t)c->V, 0);
+    auto visit = [&](int p) {
+        const int r = uf.find(p);
+        if (seen[r] || uf.weight[r] == 1) return;
+        seen[r] = 1;
+        for (int q = r; q >= 0; q = uf.next[q]) {
+            pts.push_back(q);
+            pt_list.push_back((int)offs.size() - 1);
+        }
+        offs.push_back((int)pts.size());
+    };
+    for (size_t i = 0; i < c->h_tri.size(); ++i) visit(c->h_tri[i]);
+    for (size_t i = 0; i < c->h_bond.size(); ++i) visit(c->h_bond[i]);
+    if (c->zone_lists.upload(offs, pts, pt_list) != 0) return fail(c, CLSN_E_NOMEM, "impact-zone list upload failed");
+    c->zone_lists_stale = false;
+    return CLSN_OK;
+}
+
+extern "C" int clsn_compute_impact_zone(clsn_ctx* c, int max_iter, clsn_zone_stats* out)
+{
+    if (!c || !c->V) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    if (c->nranks != 1) return fail(c, CLSN_E_UNSUPPORTED, "impact zones need the whole pair set (not a sliced context)");
+    if (max_iter <= 0) max_iter = 100000;
+    clsn_zone_stats zs;
+    memset(&zs, 0, sizeof(zs));
+    if (!c->zone_uf_ready) {  // makeSet + createImpZoneForRG, once per step (dcollid3d.cpp:44-45)
+        c->zone_uf.reset(c->V);
+        c->zone_uf.merge_movable_bodies(c->T, c->h_tri.data(), c->h_tri_surf.data(), c->h_vflags.data());
+        c->zone_uf_ready = true;
+        c->zone_lists_stale = true;
+    }
+    const bool dbg_saved = c->dbg_contacts;
+    if (c->contacts.n == 0) CK(c->contacts.reserve((size_t)c->N / 8 + 4096));
+    c->dbg_contacts = true;
+    std::vector<Contact> con;
+    std::vector<unsigned long long> order;
+    bool is_collision = true;
+    int r = CLSN_OK;
+    while (is_collision) {
+        clsn_pass_stats st;
+        if ((r = run_detect(c, CLSN_COLLISION, &st, false, 0))) break;
+        is_collision = st.true_pairs > 0;
+        zs.true_pairs += st.true_pairs;
+        const size_t n = (size_t)c->n_contacts;
+        con.resize(n);
+        if (n) {
+            cudaError_t e = cudaMemcpyAsync(con.data(), c->contacts.p, n * sizeof(Contact), cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) { c->err = cudaGetErrorString(e); r = CLSN_E_CUDA; break; }
+        }
+        // first hit of every true pair, pairs in canonical order
+        std::sort(con.begin(), con.end(), [](const Contact& a, const Contact& b) {
+            return a.ea != b.ea ? a.ea < b.ea : (a.eb != b.eb ? a.eb < b.eb : a.feature < b.feature);
+        });
+        for (size_t i = 0; i < n; ++i) {
+            if (i && con[i].ea == con[i - 1].ea && con[i].eb == con[i - 1].eb) continue;
+            const int ea = con[i].ea, eb = con[i].eb, nf = pair_features(c->T, ea, eb);
+            for (int f = con[i].feature; f < nf; ++f) {
+                int p[4];
+                feature_points(c, ea, eb, f, p);
+                for (int a = 0; a < 4; ++a)      // createImpZone(pts, 4, first = NO)
+                    for (int b = 0; b < a; ++b) {
+                        if ((c->h_vflags[p[a]] & 2) || (c->h_vflags[p[b]] & 2)) continue;
+                        if (c->zone_uf.merge(p[a], p[b])) { c->zone_lists_stale = true; ++zs.merges; }
+                    }
+            }
+        }
+        if ((r = clsn_apply(c, 1))) break;
+        if (c->zone_lists_stale && (r = upload_zone_lists(c))) break;
+        if (c->prm.dt > 0.0 && c->zone_lists.nlists) {
+            if (c->zone_lists.rigidify(c->xo.p, c->av.p, c->vflags.p, c->prm.m, c->prm.dt, c->counters.p, c->stream, c->dirty.p) != 0) {
+                r = fail(c, CLSN_E_CUDA, "impact-zone kernels failed");
+                break;
+            }
+            c->launches += 2;
+        }
+        mark(c, PH_REDUCE);
+        zs.zones = c->zone_lists.nlists;
+        zs.zone_points = c->zone_lists.npts;
+        if (++zs.iterations >= max_iter && is_collision) {
+            r = fail(c, CLSN_E_NUMERIC, "impact zones did not converge within max_iter iterations");
+            break;
+        }
+    }
+    c->dbg_contacts = dbg_saved;
+    zs.converged = (r == CLSN_OK && !is_collision) ? 1 : 0;
+    if (out) *out = zs;
+    return r;
+}
+
+extern "C" int clsn_set_impact_zones(clsn_ctx* c, int on, int max_iter)
+{
+    if (!c) return CLSN_E_ARG;
+    c->impact_zones = on != 0;
+    c->zone_max_iter = max_iter;
+    return CLSN_OK;
+}
+
 // resolveCollision, dcollid.cpp:317-362 (detectProximity :390-406, detectCollision :430-468)
 extern "C" int clsn_resolve(clsn_ctx* c, clsn_step_stats* stats)
 {
@@ -1131,6 +1282,12 @@ extern "C" int clsn_resolve(clsn_ctx* c, clsn_step_stats* stats)
     }
     s.n_ccd_passes = cd;
     s.still_colliding = is_collision ? 1 : 0;
+    if (is_collision && c->impact_zones) {  // detectCollision's tail, dcollid.cpp:464-467
+        clsn_zone_stats zs;
+        if ((r = clsn_compute_impact_zone(c, c->zone_max_iter, &zs))) return r;
+        s.zone_iterations = zs.iterations;
+        s.zones = zs.zones;
+    }
     if ((r = clsn_boundary(c))) return r;
     if ((r = clsn_final_position(c))) return r;
     CK(cudaEventRecord(c->ev[1], c->stream));

@@ -89,12 +89,14 @@ __global__ void k_rigid_sums(int nlists, const int* __restrict__ list_offs, cons
 // dcollid3d.cpp:140-198: avgVel of every non-static point of the list from the rigid motion
 __global__ void k_rigid_apply(int npts, const int* __restrict__ list_pts, const int* __restrict__ pt_list,
                               const RigidBodyState* __restrict__ st, const Vec4* __restrict__ xo, Vec4* av,
-                              const uint8_t* __restrict__ vflags, double dt, unsigned long long* counters)
+                              const uint8_t* __restrict__ vflags, double dt, unsigned long long* counters,
+                              uint8_t* dirty)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= npts) return;
     const int p = list_pts[t];
     if (vflags[p] & 1) return;
+    if (dirty) dirty[p] = 1;  // impact zones: avgVel changes outside the impulse reduction
     const RigidBodyState s = st[pt_list[t]];
     const Vec4 x = ldg_vec4(xo + p);
     const double xs[3] = {x.x, x.y, x.z};
@@ -122,6 +124,54 @@ __global__ void k_rigid_apply(int npts, const int* __restrict__ list_pts, const 
     av[p] = o;
 }
 
+// The reference's union-find with per-set point lists (dcollid.cpp:995-1059): weighted union, the
+// lighter list is appended to the heavier one (ties: X's list goes behind Y's).  The list order
+// decides the summation order of updateImpactListVelocity, so it is restated exactly.
+struct HostUF {
+    std::vector<int> root, next, tail, weight;
+
+    void reset(int V)  // makeSet, dcollid.cpp:1015-1031
+    {
+        root.resize(V); tail.resize(V);
+        next.assign(V, -1); weight.assign(V, 1);
+        for (int v = 0; v < V; ++v) root[v] = tail[v] = v;
+    }
+    int find(int p)  // findSet :1033-1037 (iterative; compression does not change any list)
+    {
+        int r = p;
+        while (root[r] != r) r = root[r];
+        while (root[p] != r) { int n = root[p]; root[p] = r; p = n; }
+        return r;
+    }
+    bool merge(int X, int Y)  // mergePoint :1039-1059
+    {
+        int PX = find(X), PY = find(Y);
+        if (PX == PY) return false;
+        if (weight[PX] > weight[PY]) {
+            weight[PX] += weight[PY]; root[PY] = PX; next[tail[PX]] = PY; tail[PX] = tail[PY];
+        } else {
+            weight[PY] += weight[PX]; root[PX] = PY; next[tail[PY]] = PX; tail[PY] = tail[PX];
+        }
+        return true;
+    }
+    // createImpZoneForRG, dcollid3d.cpp:54-68: every triangle of a movable body, first = YES
+    bool merge_movable_bodies(int T, const int* tri, const int* tri_surf, const uint8_t* vflags)
+    {
+        bool any = false;
+        int t = 0;
+        while (t < T) {
+            const int s = tri_surf[t], t0 = t;
+            while (t < T && tri_surf[t] == s) ++t;
+            if (!(vflags[tri[3 * t0]] & 2)) continue;  // first_tri's point 0 decides (dcollid3d.cpp:62)
+            any = true;
+            for (int q = t0; q < t; ++q)
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < i; ++j) merge(tri[3 * q + i], tri[3 * q + j]);
+        }
+        return any;
+    }
+};
+
 struct RigidTopo {
     int nlists = 0, npts = 0;
     int* d_offs = nullptr;
@@ -144,33 +194,10 @@ struct RigidTopo {
     int build(int V, int T, const int* tri, const int* tri_surf, const uint8_t* vflags)
     {
         release();
-        std::vector<int> root(V), next(V, -1), tail(V), weight(V, 1);
-        for (int v = 0; v < V; ++v) root[v] = tail[v] = v;
-        auto find = [&](int p) {
-            int r = p;
-            while (root[r] != r) r = root[r];
-            while (root[p] != r) { int n = root[p]; root[p] = r; p = n; }  // path compression
-            return r;
-        };
-        bool any = false;
-        int t = 0;
-        while (t < T) {
-            const int s = tri_surf[t], t0 = t;
-            while (t < T && tri_surf[t] == s) ++t;
-            if (!(vflags[tri[3 * t0]] & 2)) continue;  // first_tri's point 0 decides (dcollid3d.cpp:62)
-            any = true;
-            for (int q = t0; q < t; ++q)
-                for (int i = 0; i < 3; ++i)
-                    for (int j = 0; j < i; ++j) {
-                        int PX = find(tri[3 * q + i]), PY = find(tri[3 * q + j]);
-                        if (PX == PY) continue;
-                        if (weight[PX] > weight[PY]) {
-                            weight[PX] += weight[PY]; root[PY] = PX; next[tail[PX]] = PY; tail[PX] = tail[PY];
-                        } else {
-                            weight[PY] += weight[PX]; root[PX] = PY; next[tail[PY]] = PX; tail[PY] = tail[PX];
-                        }
-                    }
-        }
+        HostUF uf;
+        uf.reset(V);
+        const bool any = uf.merge_movable_bodies(T, tri, tri_surf, vflags);
+        const std::vector<int>&root = uf.root, &next = uf.next, &weight = uf.weight;
         if (!any) return 0;
         std::vector<int> offs(1, 0), pts, pt_list;
         for (int v = 0; v < V; ++v) {
@@ -182,9 +209,16 @@ struct RigidTopo {
             }
             offs.push_back((int)pts.size());
         }
+        return upload(offs, pts, pt_list);
+    }
+
+    // flat lists -> device (also used for the impact zones, which change from iteration to iteration)
+    int upload(const std::vector<int>& offs, const std::vector<int>& pts, const std::vector<int>& pt_list)
+    {
+        release();
         nlists = (int)offs.size() - 1;
         npts = (int)pts.size();
-        if (nlists == 0) return 0;
+        if (nlists <= 0) { nlists = npts = 0; return 0; }
         if (cudaMalloc((void**)&d_offs, offs.size() * sizeof(int)) != cudaSuccess) return -1;
         if (cudaMalloc((void**)&d_pts, pts.size() * sizeof(int)) != cudaSuccess) return -1;
         if (cudaMalloc((void**)&d_pt_list, pts.size() * sizeof(int)) != cudaSuccess) return -1;
@@ -195,11 +229,12 @@ struct RigidTopo {
         return 0;
     }
 
-    int rigidify(const Vec4* xo, Vec4* av, const uint8_t* vflags, double m, double dt, unsigned long long* counters, cudaStream_t st)
+    int rigidify(const Vec4* xo, Vec4* av, const uint8_t* vflags, double m, double dt, unsigned long long* counters, cudaStream_t st,
+                 uint8_t* dirty = nullptr)
     {
         if (nlists == 0) return 0;
         k_rigid_sums<<<(nlists + 31) / 32, 32, 0, st>>>(nlists, d_offs, d_pts, xo, av, m, dt, d_state);
-        k_rigid_apply<<<(npts + 255) / 256, 256, 0, st>>>(npts, d_pts, d_pt_list, d_state, xo, av, vflags, dt, counters);
+        k_rigid_apply<<<(npts + 255) / 256, 256, 0, st>>>(npts, d_pts, d_pt_list, d_state, xo, av, vflags, dt, counters, dirty);
         return cudaGetLastError() == cudaSuccess ? 0 : -1;
     }
 };

@@ -40,8 +40,22 @@ CollisionSolver::CollisionSolver(int dim) : has_collision(false), m_dim(dim), m_
 {
     for (int i = 0; i < 3; ++i) { Boundary[i][0] = -1e30; Boundary[i][1] = 1e30; }
     std::memset(&m_stats, 0, sizeof(m_stats));
+    std::memset(&m_zone_stats, 0, sizeof(m_zone_stats));
     int rc = clsn_create(&m_ctx, 0);
     if (rc != CLSN_OK || !m_ctx) throw std::runtime_error("collision_b200: no usable CUDA device (there is no CPU fallback)");
+    clsn_set_impact_zones(m_ctx, 1, 0);
+}
+
+void CollisionSolver::setImpactZones(bool on, int max_iter)
+{
+    int rc = clsn_set_impact_zones(m_ctx, on ? 1 : 0, max_iter);
+    if (rc != CLSN_OK) fail(rc, "clsn_set_impact_zones");
+}
+
+void CollisionSolver::computeImpactZone()  // dcollid.cpp:227-265, on the state resident on the GPU
+{
+    int rc = clsn_compute_impact_zone(m_ctx, 0, &m_zone_stats);
+    if (rc != CLSN_OK) fail(rc, "clsn_compute_impact_zone");
 }
 
 CollisionSolver::~CollisionSolver()

@@ -161,6 +161,7 @@ protected:
     std::vector<double> m_xold, m_xnew, m_xout, m_vel;
     std::vector<uint8_t> m_has;
     clsn_step_stats m_stats;
+    clsn_zone_stats m_zone_stats;
     bool m_topology_dirty;
     void clearHseList();
     void gatherTopology(const INTERFACE*);
@@ -183,7 +184,11 @@ public:
     static double getPointMass();
     static void setRestitutionCoef(double);
     static double getRestitutionCoef();
-    static bool getImpZoneStatus() { return false; }  // the impact-zone fail-safe is host-side and not part of this path
+    static bool getImpZoneStatus() { return false; }  // s_detImpZone only lives inside the library's fail-safe loop
+    // computeImpactZone (dcollid.cpp:227-265): entered by resolveCollision when MAX_ITER passes leave
+    // collisions, like the reference's detectCollision (:464-467).  On by default; max_iter <= 0 = unbounded.
+    void setImpactZones(bool on, int max_iter = 0);
+    void computeImpactZone();
 
     virtual void assembleFromInterface(const INTERFACE*, double dt) = 0;
     virtual void createImpZoneForRG(const INTERFACE*) = 0;
@@ -195,7 +200,8 @@ public:
     double getDomainBoundary(int dir, int side) { return Boundary[dir][side]; }
     bool hasCollision() { return has_collision; }
     const clsn_step_stats& lastStats() const { return m_stats; }
-    bool stillColliding() const { return m_stats.still_colliding != 0; }  // the reference would enter computeImpactZone
+    bool stillColliding() const { return m_stats.still_colliding != 0; }  // MAX_ITER passes were not enough
+    const clsn_zone_stats& lastZoneStats() const { return m_zone_stats; }
     static void printDebugVariable() {}
 };
 

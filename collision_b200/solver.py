@@ -47,15 +47,24 @@ class clsn_pass_stats(C.Structure):
 
 class clsn_step_stats(C.Structure):
     _fields_ = [("proximity", clsn_pass_stats), ("n_ccd_passes", C.c_int32), ("has_collision", C.c_int32),
-                ("still_colliding", C.c_int32), ("reserved", C.c_int32), ("ccd", clsn_pass_stats * MAX_CCD_PASSES),
-                ("ms_total", C.c_float), ("ms_phase", C.c_float * 10)]
+                ("still_colliding", C.c_int32), ("zone_iterations", C.c_int32), ("ccd", clsn_pass_stats * MAX_CCD_PASSES),
+                ("ms_total", C.c_float), ("ms_phase", C.c_float * 10), ("zones", C.c_int32)]
 
     def as_dict(self):
         return dict(proximity=self.proximity.as_dict(), n_ccd_passes=int(self.n_ccd_passes),
                     has_collision=bool(self.has_collision), still_colliding=bool(self.still_colliding),
+                    zone_iterations=int(self.zone_iterations), zones=int(self.zones),
                     ccd=[self.ccd[i].as_dict() for i in range(int(self.n_ccd_passes))], ms_total=float(self.ms_total),
                     ms_phase=dict(zip(("avgvel", "build", "refit", "traverse", "cull", "roots", "contact", "reduce", "finalize", "other"),
                                       [float(v) for v in self.ms_phase])))
+
+
+class clsn_zone_stats(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("zones", C.c_int32), ("zone_points", C.c_int32), ("converged", C.c_int32),
+                ("true_pairs", C.c_int64), ("merges", C.c_int64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
 CONTACT_DTYPE = np.dtype([("ea", "<i4"), ("eb", "<i4"), ("feature", "<i4"), ("kind", "<i4"), ("p", "<i4", (4,)),
@@ -120,6 +129,8 @@ def load_library():
     L.clsn_get_contacts.argtypes = [V, V]
     L.clsn_get_accumulators.argtypes = [V, P(D), P(D), P(C.c_int32), P(D), P(C.c_int32)]
     L.clsn_set_body_accumulators.argtypes = [V, P(D), P(C.c_int32)]
+    L.clsn_set_impact_zones.argtypes = [V, I, I]
+    L.clsn_compute_impact_zone.argtypes = [V, I, P(clsn_zone_stats)]
     _lib = L
     return L
 
@@ -177,8 +188,12 @@ class CollisionSolver3d:
     s_lambda = 0.02
     s_cr = 0.0
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, impact_zones: bool = True, max_zone_iterations: int = 0):
+        """impact_zones: enter computeImpactZone when MAX_ITER CCD passes leave collisions, as the
+        reference's detectCollision does (dcollid.cpp:464-467); max_zone_iterations <= 0 keeps the
+        reference's unbounded loop (guarded at 100000)."""
         self.ctx = Context(device)
+        self.setImpactZones(impact_zones, max_zone_iterations)
         self.scene = None
         self.has_collision = False
         self.last_stats = None
@@ -231,6 +246,17 @@ class CollisionSolver3d:
 
     def hasCollision(self):
         return self.has_collision
+
+    def setImpactZones(self, on=True, max_iterations=0):
+        self.ctx.check(self.ctx.L.clsn_set_impact_zones(self.ctx.h, 1 if on else 0, int(max_iterations)))
+        self.impact_zones = bool(on)
+
+    def computeImpactZone(self, max_iterations=0):
+        """The fail-safe loop alone, on the resident state (dcollid.cpp:227-265)."""
+        self._push_params()
+        zs = clsn_zone_stats()
+        self.ctx.check(self.ctx.L.clsn_compute_impact_zone(self.ctx.h, int(max_iterations), C.byref(zs)))
+        return zs.as_dict()
 
     # ---- assembly
     def assembleFromInterface(self, scene, dt):

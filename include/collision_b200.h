@@ -71,13 +71,24 @@ typedef struct {
     clsn_pass_stats proximity;
     int32_t n_ccd_passes;
     int32_t has_collision;      /* hasCollision(): first CCD pass found something (dcollid.cpp:456) */
-    int32_t still_colliding;    /* MAX_ITER passes did not resolve: the reference would enter
-                                   computeImpactZone (host fail-safe, out of scope)                */
-    int32_t reserved;
+    int32_t still_colliding;    /* MAX_ITER passes did not resolve: the reference enters computeImpactZone
+                                   (dcollid.cpp:464-467); run here when clsn_set_impact_zones is on   */
+    int32_t zone_iterations;    /* iterations of that fail-safe (0: not entered)                    */
     clsn_pass_stats ccd[CLSN_MAX_CCD_PASSES];
     float ms_total;             /* device time of the whole step (CUDA events)                     */
     float ms_phase[10];         /* avgvel, build, refit, traverse, cull, roots, contact, reduce, finalize, other */
+    int32_t zones;              /* sets of more than one point after the last fail-safe iteration  */
 } clsn_step_stats;
+
+/* computeImpactZone (dcollid.cpp:227-265). */
+typedef struct {
+    int32_t iterations;   /* CCD pass + updateAverageVelocity + updateImpactZoneVelocity rounds      */
+    int32_t zones;        /* numZones of the last round: union-find sets with more than one point     */
+    int32_t zone_points;  /* points in those sets                                                     */
+    int32_t converged;    /* 1: the last round found no collision                                     */
+    int64_t true_pairs;   /* colliding pairs summed over the rounds                                   */
+    int64_t merges;       /* successful mergePoint calls (dcollid.cpp:1039-1059)                      */
+} clsn_zone_stats;
 
 /* Contact record for parity checks (same layout as oracle/collision_oracle.h: orc_contact). */
 typedef struct {
@@ -108,6 +119,16 @@ int clsn_set_topology(clsn_ctx*, int V, int T, const int32_t* tri_idx, const int
 /* x_old[3V], x_new[3V] = Coords as the spring solver left them; clears per-step accumulators */
 int clsn_upload_state(clsn_ctx*, const double* x_old, const double* x_new);
 int clsn_resolve(clsn_ctx*, clsn_step_stats* stats); /* resolveCollision() minus strain limiting */
+/* The fail-safe the reference enters when MAX_ITER passes leave collisions (detectCollision,
+ * dcollid.cpp:464-467 -> computeImpactZone :227-265, createImpZone :473-484,
+ * updateImpactZoneVelocity :290-309).  clsn_set_impact_zones(on) makes clsn_resolve / clsn_step_host
+ * run it like the reference does (default off: it is outside the timed hot loop); max_iter <= 0
+ * means the reference's unbounded loop (guarded at 100000 -> CLSN_E_NUMERIC).
+ * clsn_compute_impact_zone is the loop alone, for a caller driving the phases itself.  The CCD passes
+ * and the rigid projection of the zones run on the GPU; the union-find merges are replayed on the
+ * host in canonical order from the contact records.  Whole-mesh contexts only (not clsn_set_slice). */
+int clsn_set_impact_zones(clsn_ctx*, int on, int max_iter);
+int clsn_compute_impact_zone(clsn_ctx*, int max_iter, clsn_zone_stats* out);
 /* any pointer may be NULL.  x[3V] final Coords, avgvel[3V], has_collsn[V] */
 int clsn_download_state(clsn_ctx*, double* x, double* avgvel, uint8_t* has_collsn);
 /* upload + resolve + download + "vel = avgVel where has_collsn" (updateFinalVelocity) in one call */

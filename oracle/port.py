@@ -103,7 +103,9 @@ def set_libm(mode: int):
 class OracleSolver:
     """The C restatement driven on a collision_b200.scenes.Scene."""
 
-    def __init__(self, scene):
+    def __init__(self, scene, impact_zones=True):
+        """impact_zones: resolve() enters computeImpactZone when the CCD passes are exhausted, like the
+        reference's detectCollision (dcollid.cpp:464-467)."""
         L = lib()
         self.scene = scene
         self.V, self.T, self.B = scene.V, scene.T, scene.B
@@ -119,6 +121,7 @@ class OracleSolver:
         hi = np.ascontiguousarray(scene.hi, dtype=np.float64)
         L.orc_set_domain(self.h, _dp(lo), _dp(hi))
         L.orc_set_dt(self.h, scene.dt)
+        L.orc_enable_impact_zones(self.h, 1 if impact_zones else 0)
 
     def close(self):
         if self.h:

@@ -84,6 +84,7 @@ def test_whole_step_parity(name):
         else:
             assert all(a <= b for a, b in zip([p["candidates"] for p in st["ccd"]], st_o[9:9 + st_o[1]]))
         assert int(st["still_colliding"]) == st_o[7]
+        assert st["zone_iterations"] == st_o[14] and st["zones"] == st_o[15]   # the impact-zone fail-safe, when entered
         assert same_bits(xg, orc.get(port.F_X))
         assert same_bits(vg, vo)
         assert np.array_equal(has, orc.geti(port.I_HAS_COLLSN))
@@ -237,3 +238,77 @@ def test_zero_time_step():
     gpu.resolveCollision(x, xg, vg)
     assert same_bits(xg, orc.get(port.F_X)) and same_bits(vg, vo)
     gpu.close()
+
+
+ZONE_SCENES = {
+    "layered_fast": lambda: scenes.layered_cloth(4, 13, speed=3.0),
+    "sheets_fast": lambda: scenes.two_sheets(n=10, speed=10.0),
+    "mixed": lambda: scenes.mixed(),
+}
+
+
+@pytest.mark.parametrize("name", list(ZONE_SCENES))
+def test_impact_zone_failsafe_matches_oracle(name):
+    """Scenes that still collide after the 5 CCD passes: the drop-in call enters computeImpactZone
+    (dcollid.cpp:227-265) like the reference; zone iterations, zone counts and the final state equal
+    the oracle's bit for bit, and the fail-safe really ran."""
+    sc = ZONE_SCENES[name]()
+    gpu, orc = make_pair(sc)
+    gpu.set_debug(False, False)
+    x, vel = sc.x.copy(), sc.vel.copy()
+    iters = 0
+    for step in range(5 if name == "mixed" else 2):
+        xn = x + sc.dt * vel
+        orc.set_state(x, xn)
+        vo = vel.copy()
+        st_o = orc.resolve(vo)
+        xg, vg = xn.copy(), vel.copy()
+        has = gpu.resolveCollision(x, xg, vg)
+        st = gpu.last_stats
+        assert [p["true_pairs"] for p in st["ccd"]] == st_o[2:2 + st_o[1]]
+        assert int(st["still_colliding"]) == st_o[7]
+        assert (st["zone_iterations"], st["zones"]) == (st_o[14], st_o[15]), f"step {step}"
+        assert same_bits(xg, orc.get(port.F_X)) and same_bits(vg, vo), f"step {step}"
+        assert np.array_equal(has, orc.geti(port.I_HAS_COLLSN))
+        iters += st["zone_iterations"]
+        x, vel = xg, vg
+    assert iters >= 2, "the fail-safe never ran: the test would be vacuous"
+    gpu.close()
+
+
+def test_impact_zone_loop_alone_and_disabled():
+    """clsn_compute_impact_zone on a caller-driven phase sequence == the oracle's loop (avgVel bit for
+    bit, the state ends collision free); with the fail-safe off the step stops after the CCD passes."""
+    sc = scenes.layered_cloth(4, 13, speed=3.0)
+    gpu, orc = make_pair(sc)
+    gpu.set_debug(False, False)
+    x, vel = sc.x.copy(), sc.vel.copy()
+    xn = x + sc.dt * vel
+    orc.set_state(x, xn)
+    orc.avg_velocity()
+    gpu.upload(x, xn)
+    gpu.avg_velocity()
+    for ps in range(6):
+        mode = port.PROXIMITY if ps == 0 else port.COLLISION
+        n_o = orc.detect(mode)
+        assert gpu.detect(mode)["true_pairs"] == n_o
+        orc.apply(True)
+        gpu.apply(True)
+    assert n_o > 0
+    z_o = orc.impact_zone()
+    z = gpu.computeImpactZone()
+    assert (z["iterations"], z["zones"], z["true_pairs"]) == tuple(z_o) and z["converged"] == 1 and z["merges"] > 0
+    assert same_bits(gpu.download()[1], orc.get(port.F_AVGVEL))
+    assert gpu.detect(port.COLLISION)["true_pairs"] == 0
+    gpu.close()
+    # fail-safe off: identical to an oracle that stops after MAX_ITER passes, and still colliding
+    off = CollisionSolver3d(impact_zones=False)
+    off.assembleFromInterface(sc, sc.dt)
+    o2 = port.OracleSolver(sc, impact_zones=False)
+    o2.set_state(x, xn)
+    vo, xg, vg = vel.copy(), xn.copy(), vel.copy()
+    st_o = o2.resolve(vo)
+    off.resolveCollision(x, xg, vg)
+    assert off.last_stats["still_colliding"] and off.last_stats["zone_iterations"] == 0 and st_o[14] == 0
+    assert same_bits(xg, o2.get(port.F_X)) and same_bits(vg, vo)
+    off.close()
