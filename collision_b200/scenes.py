@@ -73,6 +73,22 @@ class Scene:
     def n_curve(self) -> int:
         return int(self.bond_curve.max()) + 1 if self.B else 0
 
+    def rest_lengths(self, x=None):
+        """TRI::side_length0[3] / BOND::length0 -- the application's data in the reference, set from the
+        unstretched mesh; here from `x` (default: the scene's initial positions).  Edge j of a
+        triangle joins its points j and (j+1)%3.  Same operation order as FronTier's
+        distance_between_positions: sqrt(((dx^2 + dy^2) + dz^2))."""
+        x = self.x if x is None else x
+
+        def dist(a, b):
+            d = x[a] - x[b]
+            return np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2])
+
+        t = self.tri_idx
+        tri_len0 = np.stack([dist(t[:, j], t[:, (j + 1) % 3]) for j in range(3)], axis=1) if self.T else np.zeros((0, 3))
+        bond_len0 = dist(self.bond_idx[:, 0], self.bond_idx[:, 1]) if self.B else np.zeros(0)
+        return np.ascontiguousarray(tri_len0, dtype=np.float64), np.ascontiguousarray(bond_len0, dtype=np.float64)
+
     def x_new(self) -> np.ndarray:
         """Candidate end-of-step positions, as the driver's spring solver leaves them
         (test.cpp:226-258): x_old + dt * vel."""

@@ -40,6 +40,9 @@ struct orc_ctx {
     int det_imp_zone;  /* s_detImpZone, dcollid.cpp:28 */
     int impact_zones;  /* run computeImpactZone from orc_resolve when passes are exhausted */
     unsigned char* sorted;
+    double* tri_len0;  /* TRI::side_length0[3] */
+    double* bond_len0; /* BOND::length0 */
+    int have_len0, strain_limiting;
     /* results of the last detect */
     int* cand; long n_cand, cap_cand;
     int* truep; long n_true, cap_true;
@@ -955,6 +958,73 @@ void orc_final_position(orc_ctx* c) /* dcollid.cpp:562-584 */
     for (int i = 0; i < 3 * c->V; ++i) c->x[i] = c->xo[i] + c->av[i] * c->dt;
 }
 
+/* reduceSuperelastOnce, dcollid.cpp:485-560: one Gauss-Seidel sweep over the edges of every
+ * non-rigid element in hseList order (a shared edge is visited once per adjacent triangle);
+ * an edge whose strain or strain rate exceeds 10 % gets both end points the mean avgVel. */
+static double dist3(const double* p, const double* q) /* distance_between_positions */
+{
+    double s = 0.0;
+    for (int i = 0; i < 3; ++i) s += (p[i] - q[i]) * (p[i] - q[i]);
+    return sqrt(s);
+}
+int orc_strain_limit_once(orc_ctx* c, long* num_edges)
+{
+    const double tol = 0.10, dt = c->dt;
+    int has = 0;
+    *num_edges = 0;
+    for (int e = 0; e < c->N; ++e) {
+        const int* pts = e < c->T ? c->tri + 3 * e : c->bond + 2 * (e - c->T);
+        int np = e < c->T ? 3 : 2;
+        if (elem_rigid(c, pts, np)) continue;
+        for (int j = 0; j < (np == 2 ? 1 : np); ++j) {
+            int p0 = pts[j % np], p1 = pts[(j + 1) % np];
+            double* a0 = c->av + 3 * p0;
+            double* a1 = c->av + 3 * p1;
+            const double *x0 = c->xo + 3 * p0, *x1 = c->xo + 3 * p1;
+            double c0[3], c1[3];
+            for (int k = 0; k < 3; ++k) { c0[k] = x0[k] + dt * a0[k]; c1[k] = x1[k] + dt * a1[k]; }
+            double len_new = dist3(c0, c1), len_old = dist3(x0, x1);
+            double len0 = e < c->T ? c->tri_len0[3 * e + j] : c->bond_len0[e - c->T];
+            int fix;
+            if (len_old > ROUND_EPS && len_new > ROUND_EPS) {
+                double strain_rate = (len_new - len_old) / len_old;
+                double strain = (len_new - len0) / len0;
+                fix = fabs(strain) > tol || fabs(strain_rate) > tol;
+            } else
+                fix = 1;
+            if (fix) {
+                for (int k = 0; k < 3; ++k) {
+                    double v = 0.5 * (a0[k] + a1[k]);
+                    a0[k] = v; a1[k] = v;
+                }
+                ++*num_edges;
+                has = 1;
+            }
+        }
+    }
+    return has;
+}
+
+/* reduceSuperelast, dcollid.cpp:586-596: at most 10 sweeps; returns the number of sweeps run */
+int orc_strain_limit(orc_ctx* c, long* num_edges)
+{
+    int has = 1, niter = 0;
+    long n = 0;
+    if (!c->have_len0) { c->error = 1; return -1; }
+    while (has && niter++ < 10) has = orc_strain_limit_once(c, &n);
+    if (niter > 10) niter = 10; /* the reference's post-increment leaves 11 after ten sweeps */
+    if (num_edges) *num_edges = n;
+    return niter;
+}
+
+void orc_set_rest_lengths(orc_ctx* c, const double* tri_len0, const double* bond_len0)
+{
+    memcpy(c->tri_len0, tri_len0, (size_t)3 * c->T * sizeof(double));
+    memcpy(c->bond_len0, bond_len0, (size_t)c->B * sizeof(double));
+    c->have_len0 = 1;
+}
+void orc_enable_strain_limiting(orc_ctx* c, int on) { c->strain_limiting = on; }
+
 void orc_final_velocity(orc_ctx* c, double* vel) /* dcollid.cpp:598-624 */
 {
     for (int p = 0; p < c->V; ++p)
@@ -965,7 +1035,7 @@ void orc_final_velocity(orc_ctx* c, double* vel) /* dcollid.cpp:598-624 */
 /* resolveCollision, dcollid.cpp:317-362, with detectProximity :390-406 and detectCollision :430-468 */
 void orc_resolve(orc_ctx* c, double* vel, long* stats)
 {
-    for (int i = 0; i < 16; ++i) stats[i] = 0;
+    for (int i = 0; i < 20; ++i) stats[i] = 0;
     orc_avg_velocity(c);
     stats[0] = orc_detect(c, ORC_PROXIMITY);
     stats[8] = c->n_cand;
@@ -989,6 +1059,11 @@ void orc_resolve(orc_ctx* c, double* vel, long* stats)
     }
     orc_boundary(c);
     orc_final_position(c);
+    if (c->strain_limiting) { /* reduceSuperelast sits between the final positions and velocities (:355) */
+        long ne = 0;
+        stats[16] = orc_strain_limit(c, &ne);
+        stats[17] = ne;
+    }
     orc_final_velocity(c, vel);
 }
 
@@ -1027,6 +1102,8 @@ orc_ctx* orc_create(int V, int T, const int* tri_idx, const int* tri_surf, int B
     c->uf_tail = (int*)malloc((size_t)(V + 1) * sizeof(int));
     c->uf_weight = (int*)malloc((size_t)(V + 1) * sizeof(int));
     c->sorted = (unsigned char*)calloc((size_t)V + 1, 1);
+    c->tri_len0 = (double*)calloc((size_t)3 * T + 1, sizeof(double));
+    c->bond_len0 = (double*)calloc((size_t)B + 1, sizeof(double));
     return c;
 }
 
@@ -1035,7 +1112,7 @@ void orc_destroy(orc_ctx* c)
     if (!c) return;
     free(c->tri); free(c->tri_surf); free(c->bond); free(c->flags); free(c->vhs); free(c->hs_mass);
     free(c->xo); free(c->x); free(c->av); free(c->imp); free(c->fric); free(c->cnt); free(c->has);
-    free(c->imp_rg); free(c->cnt_rg); free(c->uf_root); free(c->uf_next); free(c->uf_tail); free(c->uf_weight); free(c->sorted);
+    free(c->imp_rg); free(c->cnt_rg); free(c->uf_root); free(c->uf_next); free(c->uf_tail); free(c->uf_weight); free(c->sorted); free(c->tri_len0); free(c->bond_len0);
     free(c->cand); free(c->truep); free(c->con);
     free(c);
 }

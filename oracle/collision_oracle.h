@@ -65,7 +65,8 @@ void orc_final_velocity(orc_ctx*, double* vel);  /* dcollid.cpp:598-624, vel upd
 /* whole step (dcollid.cpp:317-362 minus reduceSuperelast and the impact-zone fail-safe).
  * stats[0] proximity pairs true, stats[1] #CCD passes, stats[2..6] true pairs per CCD pass,
  * stats[7] 1 if still colliding after MAX_ITER passes, stats[8] candidates proximity,
- * stats[9..13] candidates per CCD pass, stats[14] impact-zone iterations, stats[15] zones (16 longs) */
+ * stats[9..13] candidates per CCD pass, stats[14] impact-zone iterations, stats[15] zones,
+ * stats[16] strain-limiting sweeps, stats[17] edges averaged in the last sweep (20 longs) */
 void orc_resolve(orc_ctx*, double* vel, long* stats);
 
 /* Impact-zone fail-safe (computeImpactZone, dcollid.cpp:227-265; createImpZone :473-484;
@@ -75,6 +76,14 @@ void orc_enable_impact_zones(orc_ctx*, int on);
 void orc_set_imp_zone(orc_ctx*, int on);            /* turnOnImpZone / turnOffImpZone */
 int orc_zone_velocity(orc_ctx*);                    /* updateImpactZoneVelocity -> number of zones */
 void orc_impact_zone(orc_ctx*, int max_iter, long* out3);
+
+/* Strain limiting (reduceSuperelast, dcollid.cpp:485-596).  Rest lengths are the caller's data in the
+ * reference (TRI::side_length0[3], BOND::length0).  orc_enable_strain_limiting makes orc_resolve run it
+ * between the final positions and the final velocities like resolveCollision (:355). */
+void orc_set_rest_lengths(orc_ctx*, const double* tri_len0, const double* bond_len0);
+void orc_enable_strain_limiting(orc_ctx*, int on);
+int orc_strain_limit_once(orc_ctx*, long* num_edges);
+int orc_strain_limit(orc_ctx*, long* num_edges);
 
 /* readbacks */
 void orc_get_f64(orc_ctx*, int field, double* out); /* 0 x_old 1 x 2 avgVel 3 imp 4 fric (3V each) */

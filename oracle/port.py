@@ -76,6 +76,10 @@ def lib():
         L.orc_zone_velocity.argtypes = [V]
         L.orc_zone_velocity.restype = I
         L.orc_impact_zone.argtypes = [V, I, P(C.c_long)]
+        L.orc_set_rest_lengths.argtypes = [V, P(D), P(D)]
+        L.orc_enable_strain_limiting.argtypes = [V, I]
+        L.orc_strain_limit_once.argtypes = [V, P(C.c_long)]
+        L.orc_strain_limit.argtypes = [V, P(C.c_long)]
         L.orc_get_f64.argtypes = [V, I, P(D)]
         L.orc_get_i32.argtypes = [V, I, P(I)]
         L.orc_get_body.argtypes = [V, P(D), P(I)]
@@ -103,9 +107,10 @@ def set_libm(mode: int):
 class OracleSolver:
     """The C restatement driven on a collision_b200.scenes.Scene."""
 
-    def __init__(self, scene, impact_zones=True):
+    def __init__(self, scene, impact_zones=True, strain_limiting=False):
         """impact_zones: resolve() enters computeImpactZone when the CCD passes are exhausted, like the
-        reference's detectCollision (dcollid.cpp:464-467)."""
+        reference's detectCollision (dcollid.cpp:464-467).  strain_limiting: resolve() runs
+        reduceSuperelast (:355) with the scene's rest lengths."""
         L = lib()
         self.scene = scene
         self.V, self.T, self.B = scene.V, scene.T, scene.B
@@ -122,6 +127,8 @@ class OracleSolver:
         L.orc_set_domain(self.h, _dp(lo), _dp(hi))
         L.orc_set_dt(self.h, scene.dt)
         L.orc_enable_impact_zones(self.h, 1 if impact_zones else 0)
+        self.set_rest_lengths(*scene.rest_lengths())
+        L.orc_enable_strain_limiting(self.h, 1 if strain_limiting else 0)
 
     def close(self):
         if self.h:
@@ -172,9 +179,23 @@ class OracleSolver:
 
     def resolve(self, vel):
         assert vel.dtype == np.float64 and vel.flags.c_contiguous
-        stats = (C.c_long * 16)()
+        stats = (C.c_long * 20)()
         lib().orc_resolve(self.h, _dp(vel), stats)
         return list(stats)
+
+    def set_rest_lengths(self, tri_len0, bond_len0):
+        a = np.ascontiguousarray(tri_len0, dtype=np.float64)
+        b = np.ascontiguousarray(bond_len0, dtype=np.float64)
+        lib().orc_set_rest_lengths(self.h, _dp(a), _dp(b))
+
+    def enable_strain_limiting(self, on=True):
+        lib().orc_enable_strain_limiting(self.h, 1 if on else 0)
+
+    def strain_limit(self):
+        """reduceSuperelast: (sweeps run, edges averaged in the last sweep)"""
+        n = C.c_long()
+        it = lib().orc_strain_limit(self.h, C.byref(n))
+        return int(it), int(n.value)
 
     def enable_impact_zones(self, on=True):
         lib().orc_enable_impact_zones(self.h, 1 if on else 0)

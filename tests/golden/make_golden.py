@@ -23,6 +23,9 @@ sys.path.insert(0, ROOT)
 from collision_b200 import scenes  # noqa: E402
 from oracle import ref  # noqa: E402
 
+sys.path.insert(0, os.path.dirname(HERE))
+from parity_util import STRAIN_SCENES, strain_inputs  # noqa: E402
+
 PARAMS = np.array([1e-6, 1e-4, 1000.0, 0.01, 0.02, 0.0])
 
 
@@ -187,11 +190,31 @@ def make_scene(name, path):
     print(f"scene_{name}.npz: {nsteps} steps, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def make_strain(path):
+    """reduceSuperelast (dcollid.cpp:485-596) of the compiled reference on kicked velocity fields."""
+    out = {}
+    for name, mk in STRAIN_SCENES.items():
+        sc = mk()
+        r = ref.RefSolver(sc)
+        r.set_rest_lengths(sc.x)
+        r.set_state(sc.x, sc.x + sc.dt * sc.vel, sc.vel)
+        r.assemble(sc.dt)
+        for case in range(3):
+            av = strain_inputs(sc, case)
+            r.put(ref.F_AVGVEL, av)
+            r.phase(ref.PH_STRAIN_LIMIT)
+            out[f"{name}_{case}_out"] = r.get(ref.F_AVGVEL)
+    np.savez_compressed(path, **out)
+    print(f"strain.npz: {len(out)} cases, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     if not ref.available():
         raise SystemExit("oracle/_ref/libcollision_ref.so missing: run `make -C oracle ref` (needs /root/reference)")
     if not sys.argv[1:]:
         make_features(os.path.join(HERE, "features.npz"))
+    if not sys.argv[1:] or "strain" in sys.argv[1:]:
+        make_strain(os.path.join(HERE, "strain.npz"))
     only = sys.argv[1:]
     for name in SCENES:
         if not only or name in only:

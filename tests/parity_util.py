@@ -2,6 +2,7 @@
 phases from identical inputs and compare bit for bit."""
 import numpy as np
 
+from collision_b200 import scenes
 from oracle import port
 
 
@@ -104,3 +105,22 @@ def run_step_by_phases(gpu, orc, scene, x, vel, max_passes=5):
     vg[has != 0] = av[has != 0]
     assert same_bits(vg, vo)
     return xg, vg, stats
+
+
+# ---- strain limiting (reduceSuperelast): shared by the golden generator, the oracle test and the GPU test
+STRAIN_SCENES = {
+    "two_sheets": lambda: scenes.two_sheets(n=10),
+    "mixed": lambda: scenes.mixed(),
+    "layered": lambda: scenes.layered_cloth(4, 13, speed=3.0),
+    "string_string": lambda: scenes.string_string(dt=0.01, gap=0.003),
+}
+
+
+def strain_inputs(sc, case):
+    """avgVel fed to reduceSuperelast: the step's own average velocity, kicked on 5 % of the points
+    (case 0: no kick, nothing over the limit)."""
+    rng = np.random.default_rng(100 + case)
+    av = np.repeat(sc.vel[None], 1, 0)[0].copy()
+    if case:
+        av = av + rng.normal(0, 30.0 * case, (sc.V, 3)) * (rng.random((sc.V, 1)) < 0.05)
+    return av

@@ -179,6 +179,26 @@ def test_impact_zone_loop_in_resolve():
     assert o2.detect(port.COLLISION) == 0
 
 
+def test_strain_limiting_matches_reference_golden():
+    """reduceSuperelast restated (sequential Gauss-Seidel sweeps over the edges in hseList order) against
+    the compiled reference's output on kicked velocity fields, bit for bit; sweeps run 1..10 times."""
+    from parity_util import STRAIN_SCENES, strain_inputs
+    d = np.load(os.path.join(G, "strain.npz"))
+    sweeps = set()
+    for name, mk in STRAIN_SCENES.items():
+        sc = mk()
+        o = port.OracleSolver(sc)
+        o.set_state(sc.x, sc.x + sc.dt * sc.vel)
+        for case in range(3):
+            av = strain_inputs(sc, case)
+            o.set_avgvel(av)
+            it, _ = o.strain_limit()
+            sweeps.add(it)
+            assert same_bits(o.get(port.F_AVGVEL), d[f"{name}_{case}_out"]), (name, case)
+            assert (case == 0) == (it == 1)
+    assert 10 in sweeps and len(sweeps) >= 3
+
+
 def test_canonical_order_is_order_independent_for_sets():
     """canonical (a<b sorted) evaluation finds the same candidate set and, for point-triangle-only
     contacts (static sphere), the same per-point sums up to summation order (<= 1e-12 relative)."""
@@ -222,13 +242,14 @@ def test_whole_step_matches_reference_when_available():
         pytest.skip("oracle/_ref not built here")
     sc = scenes.drape(n=24, level=2)
     r = ref.RefSolver(sc)
-    o = port.OracleSolver(sc)
+    r.set_rest_lengths(sc.x)
+    o = port.OracleSolver(sc, impact_zones=True, strain_limiting=True)
     x, vel = sc.x.copy(), sc.vel.copy()
     for step in range(3):
         xn = x + sc.dt * vel
         r.set_state(x, xn, vel)
         r.assemble(sc.dt)
-        r.resolve(False)
+        r.resolve(True)      # resolveCollision() verbatim: impact zones and strain limiting included
         o.set_state(x, xn)
         vo = vel.copy()
         o.resolve(vo)
