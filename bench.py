@@ -159,7 +159,7 @@ def time_reference(scene, steps, warmup):
     else:
         kind = "port"
         port.set_libm(port.LIBM_NATIVE)
-        o = port.OracleSolver(scene, impact_zones=False)
+        o = port.OracleSolver(scene, impact_zones=False, strain_limiting=False)
         for it in range(warmup + steps):
             o.set_state(x0, xn0)
             v = v0.copy()
@@ -241,7 +241,7 @@ def run_b200(args):
     scene, desc = workload(args.workload)
     # the timed step is resolveCollision's hot loop; the impact-zone fail-safe (host-assisted, only entered when
     # 5 CCD passes leave collisions) is excluded on both arms, like strain limiting -- see config.scope
-    solver = CollisionSolver3d(device=local, impact_zones=False)
+    solver = CollisionSolver3d(device=local, impact_zones=False, strain_limiting=False)
     CollisionSolver3d.set_params_from(scene.params)
     solver.assembleFromInterface(scene, scene.dt)
     x_old = np.ascontiguousarray(scene.x)

@@ -25,6 +25,7 @@
 #include "lbvh.cuh"
 #include "reduce.cuh"
 #include "rigid.cuh"
+#include "strain.cuh"
 
 using namespace clsn;
 
@@ -492,6 +493,9 @@ struct clsn_ctx {
     RigidTopo zone_lists;
     bool impact_zones = false;
     int zone_max_iter = 0;
+    // strain limiting
+    StrainTopo strain;
+    bool strain_limiting = false, strain_pending = false;
     // state
     DevBuf<Vec4> xo, xn, av;
     DevBuf<uint8_t> has, dirty;
@@ -617,7 +621,7 @@ extern "C" void clsn_destroy(clsn_ctx* c)
     c->cub_tmp.release(); c->pairs.release(); c->dbg_cand.release(); c->feats.release(); c->pair_hit.release(); c->rootrecs.release(); c->prec.release(); c->prec_sorted.release(); c->brec.release();
     c->contacts.release(); c->cnt.release(); c->offs.release(); c->fill.release(); c->perm.release();
     c->perm_sorted.release(); c->skey.release(); c->counters.release(); c->acc_imp.release(); c->acc_fric.release();
-    c->rigid.release(); c->zone_lists.release();
+    c->rigid.release(); c->zone_lists.release(); c->strain.release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     for (auto& e : c->ev) cudaEventDestroy(e);
@@ -741,6 +745,8 @@ extern "C" int clsn_set_topology(clsn_ctx* c, int V, int T, const int32_t* tri_i
     c->h_bond.assign(bond_idx, bond_idx + 2 * (size_t)B);
     c->h_vflags.assign(vflags, vflags + V);
     c->zone_uf_ready = false;
+    c->strain.release_schedule();  // rest lengths belong to the old elements: clsn_set_rest_lengths again
+    c->strain.have_len0 = false;
     // host-side restatement of createImpZoneForRG's union-find lists (topology only)
     int r = c->rigid.build(V, T, tri_idx, tri_surf, vflags);
     if (r != 0) return fail(c, CLSN_E_CUDA, "rigid-body topology upload failed");
@@ -1255,6 +1261,63 @@ extern "C" int clsn_set_impact_zones(clsn_ctx* c, int on, int max_iter)
     return CLSN_OK;
 }
 
+// ------------------------------------------------------------------ strain limiting
+extern "C" int clsn_set_rest_lengths(clsn_ctx* c, const double* tri_len0, const double* bond_len0)
+{
+    if (!c || !c->V || (c->T > 0 && !tri_len0) || (c->B > 0 && !bond_len0)) return CLSN_E_ARG;
+    c->strain.h_tri_len0.assign(tri_len0, tri_len0 + 3 * (size_t)c->T);
+    c->strain.h_bond_len0.assign(bond_len0, bond_len0 + c->B);
+    c->strain.have_len0 = true;
+    c->strain.release_schedule();
+    return CLSN_OK;
+}
+
+extern "C" int clsn_set_strain_limiting(clsn_ctx* c, int on)
+{
+    if (!c) return CLSN_E_ARG;
+    c->strain_limiting = on != 0;
+    return CLSN_OK;
+}
+
+// enqueue reduceSuperelast on the resident avgVel; strain_finish() reads the outcome after a stream sync
+static int strain_enqueue(clsn_ctx* c)
+{
+    if (!c->strain.have_len0) return fail(c, CLSN_E_ARG, "strain limiting needs clsn_set_rest_lengths (TRI::side_length0 / BOND::length0)");
+    if (!c->strain.built) {
+        cudaSetDevice(c->device);
+        int r = c->strain.build(c->V, c->T, c->B, c->h_tri.data(), c->h_bond.data(), c->h_vflags.data());
+        if (r == -2) return fail(c, CLSN_E_ARG, "too many edges for the 32-bit strain-limiting schedule");
+        if (r != 0) return fail(c, CLSN_E_NOMEM, "strain-limiting schedule upload failed");
+    }
+    if (c->strain.run(c->xo.p, c->av.p, c->prm.dt, c->sm_count, c->stream, &c->launches) != 0)
+        return fail(c, CLSN_E_CUDA, "strain-limiting kernels failed to launch");
+    c->strain_pending = true;
+    c->dirty_valid = false;
+    mark(c, PH_FINAL);
+    return CLSN_OK;
+}
+
+static void strain_finish(clsn_ctx* c, int32_t* sweeps, int32_t* edges_last)
+{
+    const StrainResult& r = *c->strain.h_res;
+    int n = c->strain.M > 0 ? r.sweeps : 1;
+    if (n < 1) n = 1;
+    if (sweeps) *sweeps = n;
+    if (edges_last) *edges_last = c->strain.M > 0 && r.any ? r.viol[n - 1] : 0;
+    c->strain_pending = false;
+}
+
+extern "C" int clsn_strain_limit(clsn_ctx* c, int32_t* sweeps, int32_t* edges_last)
+{
+    if (!c || !c->V) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    int r = strain_enqueue(c);
+    if (r) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    strain_finish(c, sweeps, edges_last);
+    return CLSN_OK;
+}
+
 // resolveCollision, dcollid.cpp:317-362 (detectProximity :390-406, detectCollision :430-468)
 extern "C" int clsn_resolve(clsn_ctx* c, clsn_step_stats* stats)
 {
@@ -1290,11 +1353,13 @@ extern "C" int clsn_resolve(clsn_ctx* c, clsn_step_stats* stats)
     }
     if ((r = clsn_boundary(c))) return r;
     if ((r = clsn_final_position(c))) return r;
+    if (c->strain_limiting && (r = strain_enqueue(c))) return r;  // reduceSuperelast, dcollid.cpp:355
     CK(cudaEventRecord(c->ev[1], c->stream));
     CK(cudaMemcpyAsync(c->h_counters, c->counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (c->h_counters[CTR_ERROR]) return fail(c, CLSN_E_NUMERIC, "NaN/Inf in the collision step (reference: clean_up(ERROR))");
     CK(cudaEventElapsedTime(&s.ms_total, c->ev[0], c->ev[1]));
+    if (c->strain_pending) strain_finish(c, &s.strain_sweeps, &s.strain_edges);
     c->timing = false;
     for (size_t i = 1; i < c->n_marks; ++i) {
         float ms = 0.f;

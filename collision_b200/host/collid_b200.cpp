@@ -44,6 +44,13 @@ CollisionSolver::CollisionSolver(int dim) : has_collision(false), m_dim(dim), m_
     int rc = clsn_create(&m_ctx, 0);
     if (rc != CLSN_OK || !m_ctx) throw std::runtime_error("collision_b200: no usable CUDA device (there is no CPU fallback)");
     clsn_set_impact_zones(m_ctx, 1, 0);
+    clsn_set_strain_limiting(m_ctx, 1);
+}
+
+void CollisionSolver::setStrainLimiting(bool on)
+{
+    int rc = clsn_set_strain_limiting(m_ctx, on ? 1 : 0);
+    if (rc != CLSN_OK) fail(rc, "clsn_set_strain_limiting");
 }
 
 void CollisionSolver::setImpactZones(bool on, int max_iter)
@@ -100,6 +107,7 @@ void CollisionSolver::gatherTopology(const INTERFACE* intfc)
     std::unordered_map<const HYPER_SURF*, int> body_of;
     std::vector<double> body_mass;
     std::vector<int32_t> tri, tri_surf, bond, body;
+    std::vector<double> tri_len0, bond_len0;  // TRI::side_length0 / BOND::length0, read by reduceSuperelastOnce (dcollid.cpp:514-517)
     std::vector<uint8_t> flags;
     auto pid = [&](POINT* p) {
         auto it = ids.find(p);
@@ -120,6 +128,7 @@ void CollisionSolver::gatherTopology(const INTERFACE* intfc)
     for (CD_HSE* h : hseList) {
         if (CD_TRI* t = dynamic_cast<CD_TRI*>(h)) {
             for (int i = 0; i < 3; ++i) tri.push_back(pid(t->m_tri->pts[i]));
+            for (int i = 0; i < 3; ++i) tri_len0.push_back(t->m_tri->side_length0[i]);
             auto s = surf_id.emplace(t->m_tri->surf, (int)surf_id.size()).first;
             tri_surf.push_back(s->second);
         }
@@ -128,18 +137,30 @@ void CollisionSolver::gatherTopology(const INTERFACE* intfc)
         if (CD_BOND* b = dynamic_cast<CD_BOND*>(h)) {
             bond.push_back(pid(b->m_bond->start));
             bond.push_back(pid(b->m_bond->end));
+            bond_len0.push_back(b->m_bond->length0);
         }
     }
     (void)intfc;
     const bool same = points == m_points && tri == m_tri && bond == m_bond && flags == m_flags && body == m_body &&
                       tri_surf == m_tri_surf && body_mass == m_body_mass;
-    if (same && !m_topology_dirty) return;
+    const bool same_len0 = tri_len0 == m_tri_len0 && bond_len0 == m_bond_len0;
+    if (same && !m_topology_dirty) {
+        if (!same_len0) {
+            m_tri_len0.swap(tri_len0); m_bond_len0.swap(bond_len0);
+            int rc = clsn_set_rest_lengths(m_ctx, m_tri_len0.data(), m_bond_len0.data());
+            if (rc != CLSN_OK) fail(rc, "clsn_set_rest_lengths");
+        }
+        return;
+    }
     m_points.swap(points); m_point_id.swap(ids); m_tri.swap(tri); m_tri_surf.swap(tri_surf); m_bond.swap(bond);
     m_flags.swap(flags); m_body.swap(body); m_body_mass.swap(body_mass);
     const int V = (int)m_points.size();
     int rc = clsn_set_topology(m_ctx, V, (int)m_tri_surf.size(), m_tri.data(), m_tri_surf.data(), (int)m_bond.size() / 2,
                                m_bond.data(), m_flags.data(), m_body.data(), (int)m_body_mass.size(), m_body_mass.data());
     if (rc != CLSN_OK) fail(rc, "clsn_set_topology");
+    m_tri_len0.swap(tri_len0); m_bond_len0.swap(bond_len0);
+    rc = clsn_set_rest_lengths(m_ctx, m_tri_len0.data(), m_bond_len0.data());
+    if (rc != CLSN_OK) fail(rc, "clsn_set_rest_lengths");
     m_xold.resize(3 * (size_t)V); m_xnew.resize(3 * (size_t)V); m_xout.resize(3 * (size_t)V); m_vel.resize(3 * (size_t)V);
     m_has.resize(V);
     m_topology_dirty = false;

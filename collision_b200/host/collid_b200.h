@@ -162,6 +162,7 @@ protected:
     std::vector<uint8_t> m_has;
     clsn_step_stats m_stats;
     clsn_zone_stats m_zone_stats;
+    std::vector<double> m_tri_len0, m_bond_len0;
     bool m_topology_dirty;
     void clearHseList();
     void gatherTopology(const INTERFACE*);
@@ -189,6 +190,8 @@ public:
     // collisions, like the reference's detectCollision (:464-467).  On by default; max_iter <= 0 = unbounded.
     void setImpactZones(bool on, int max_iter = 0);
     void computeImpactZone();
+    // reduceSuperelast (dcollid.cpp:586-596) runs inside resolveCollision like the reference's (:355); on by default.
+    void setStrainLimiting(bool on);
 
     virtual void assembleFromInterface(const INTERFACE*, double dt) = 0;
     virtual void createImpZoneForRG(const INTERFACE*) = 0;

@@ -2,6 +2,7 @@
 // reads a flat scene file written by tests/test_gpu_host_cpp.py, builds the POINT/TRI/BOND mesh, runs
 // `steps` x { spring solver stand-in; assembleFromInterface; setFrictionConstant; resolveCollision },
 // writes final coords + vel.  Usage: host_check scene.bin out.bin steps
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -15,6 +16,14 @@ static std::vector<T> rd(FILE* f, size_t n)
     std::vector<T> v(n);
     if (n && fread(v.data(), sizeof(T), n, f) != n) { fprintf(stderr, "short read\n"); exit(2); }
     return v;
+}
+
+// what the application stores in TRI::side_length0 / BOND::length0 from the unstretched mesh
+static double rest_length(const double* p, const double* q)
+{
+    double s = 0.0;
+    for (int i = 0; i < 3; ++i) s += (p[i] - q[i]) * (p[i] - q[i]);
+    return std::sqrt(s);
 }
 
 int main(int argc, char** argv)
@@ -53,6 +62,7 @@ int main(int argc, char** argv)
     for (int t = 0; t < T; ++t) {
         for (int i = 0; i < 3; ++i) tris[t].pts[i] = &pt[tri[3 * t + i]];
         tris[t].next = nullptr; tris[t].surf = &surf[tsurf[t]];
+        for (int i = 0; i < 3; ++i) tris[t].side_length0[i] = rest_length(&x[3 * tri[3 * t + i]], &x[3 * tri[3 * t + (i + 1) % 3]]);
         if (last[tsurf[t]]) last[tsurf[t]]->next = &tris[t]; else surf[tsurf[t]].first_tri = &tris[t];
         last[tsurf[t]] = &tris[t];
     }
@@ -61,7 +71,8 @@ int main(int argc, char** argv)
     std::vector<BOND*> blast(NC, nullptr);
     for (int c = 0; c < NC; ++c) { cur[c].first = nullptr; cur[c].is_string = true; cur[c].hs = &hs[NS + c]; }
     for (int b = 0; b < B; ++b) {
-        bonds[b].start = &pt[bond[2 * b]]; bonds[b].end = &pt[bond[2 * b + 1]]; bonds[b].next = nullptr; bonds[b].length0 = 0;
+        bonds[b].start = &pt[bond[2 * b]]; bonds[b].end = &pt[bond[2 * b + 1]]; bonds[b].next = nullptr;
+        bonds[b].length0 = rest_length(&x[3 * bond[2 * b]], &x[3 * bond[2 * b + 1]]);
         if (blast[bcur[b]]) blast[bcur[b]]->next = &bonds[b]; else cur[bcur[b]].first = &bonds[b];
         blast[bcur[b]] = &bonds[b];
     }

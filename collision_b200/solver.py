@@ -48,12 +48,14 @@ class clsn_pass_stats(C.Structure):
 class clsn_step_stats(C.Structure):
     _fields_ = [("proximity", clsn_pass_stats), ("n_ccd_passes", C.c_int32), ("has_collision", C.c_int32),
                 ("still_colliding", C.c_int32), ("zone_iterations", C.c_int32), ("ccd", clsn_pass_stats * MAX_CCD_PASSES),
-                ("ms_total", C.c_float), ("ms_phase", C.c_float * 10), ("zones", C.c_int32)]
+                ("ms_total", C.c_float), ("ms_phase", C.c_float * 10), ("zones", C.c_int32),
+                ("strain_sweeps", C.c_int32), ("strain_edges", C.c_int32), ("reserved", C.c_int32)]
 
     def as_dict(self):
         return dict(proximity=self.proximity.as_dict(), n_ccd_passes=int(self.n_ccd_passes),
                     has_collision=bool(self.has_collision), still_colliding=bool(self.still_colliding),
                     zone_iterations=int(self.zone_iterations), zones=int(self.zones),
+                    strain_sweeps=int(self.strain_sweeps), strain_edges=int(self.strain_edges),
                     ccd=[self.ccd[i].as_dict() for i in range(int(self.n_ccd_passes))], ms_total=float(self.ms_total),
                     ms_phase=dict(zip(("avgvel", "build", "refit", "traverse", "cull", "roots", "contact", "reduce", "finalize", "other"),
                                       [float(v) for v in self.ms_phase])))
@@ -130,6 +132,9 @@ def load_library():
     L.clsn_get_accumulators.argtypes = [V, P(D), P(D), P(C.c_int32), P(D), P(C.c_int32)]
     L.clsn_set_body_accumulators.argtypes = [V, P(D), P(C.c_int32)]
     L.clsn_set_impact_zones.argtypes = [V, I, I]
+    L.clsn_set_rest_lengths.argtypes = [V, P(D), P(D)]
+    L.clsn_set_strain_limiting.argtypes = [V, I]
+    L.clsn_strain_limit.argtypes = [V, P(C.c_int32), P(C.c_int32)]
     L.clsn_compute_impact_zone.argtypes = [V, I, P(clsn_zone_stats)]
     _lib = L
     return L
@@ -188,12 +193,15 @@ class CollisionSolver3d:
     s_lambda = 0.02
     s_cr = 0.0
 
-    def __init__(self, device: int = 0, impact_zones: bool = True, max_zone_iterations: int = 0):
+    def __init__(self, device: int = 0, impact_zones: bool = True, max_zone_iterations: int = 0,
+                 strain_limiting: bool = True):
         """impact_zones: enter computeImpactZone when MAX_ITER CCD passes leave collisions, as the
         reference's detectCollision does (dcollid.cpp:464-467); max_zone_iterations <= 0 keeps the
-        reference's unbounded loop (guarded at 100000)."""
+        reference's unbounded loop (guarded at 100000).  strain_limiting: run reduceSuperelast
+        between the final positions and velocities, as resolveCollision does (:355)."""
         self.ctx = Context(device)
         self.setImpactZones(impact_zones, max_zone_iterations)
+        self.setStrainLimiting(strain_limiting)
         self.scene = None
         self.has_collision = False
         self.last_stats = None
@@ -251,6 +259,24 @@ class CollisionSolver3d:
         self.ctx.check(self.ctx.L.clsn_set_impact_zones(self.ctx.h, 1 if on else 0, int(max_iterations)))
         self.impact_zones = bool(on)
 
+    def setStrainLimiting(self, on=True):
+        self.ctx.check(self.ctx.L.clsn_set_strain_limiting(self.ctx.h, 1 if on else 0))
+        self.strain_limiting = bool(on)
+
+    def setRestLengths(self, tri_len0, bond_len0):
+        """TRI::side_length0[3] / BOND::length0 (the application's data in the reference)."""
+        a = np.ascontiguousarray(tri_len0, dtype=np.float64)
+        b = np.ascontiguousarray(bond_len0, dtype=np.float64)
+        assert a.size == 3 * self.scene.T and b.size == self.scene.B
+        self.ctx.check(self.ctx.L.clsn_set_rest_lengths(self.ctx.h, _dp(a), _dp(b)))
+
+    def reduceSuperelast(self):
+        """Strain limiting alone on the resident avgVel (dcollid.cpp:586-596): (sweeps, edges in the last)."""
+        self._push_params()
+        n, e = C.c_int32(), C.c_int32()
+        self.ctx.check(self.ctx.L.clsn_strain_limit(self.ctx.h, C.byref(n), C.byref(e)))
+        return int(n.value), int(e.value)
+
     def computeImpactZone(self, max_iterations=0):
         """The fail-safe loop alone, on the resident state (dcollid.cpp:227-265)."""
         self._push_params()
@@ -276,6 +302,7 @@ class CollisionSolver3d:
                                           _ip(vb), len(mass), _dp(mass)))
             c.V, c.nbody = scene.V, len(mass)
             self.scene = scene
+            self.setRestLengths(*scene.rest_lengths())
         self.setDomainBoundary(scene.lo, scene.hi)
 
     def _push_params(self):

@@ -78,6 +78,9 @@ typedef struct {
     float ms_total;             /* device time of the whole step (CUDA events)                     */
     float ms_phase[10];         /* avgvel, build, refit, traverse, cull, roots, contact, reduce, finalize, other */
     int32_t zones;              /* sets of more than one point after the last fail-safe iteration  */
+    int32_t strain_sweeps;      /* reduceSuperelastOnce sweeps run (0: strain limiting off)          */
+    int32_t strain_edges;       /* edges averaged in the last of them (the reference's num_edges)   */
+    int32_t reserved;
 } clsn_step_stats;
 
 /* computeImpactZone (dcollid.cpp:227-265). */
@@ -127,6 +130,16 @@ int clsn_resolve(clsn_ctx*, clsn_step_stats* stats); /* resolveCollision() minus
  * clsn_compute_impact_zone is the loop alone, for a caller driving the phases itself.  The CCD passes
  * and the rigid projection of the zones run on the GPU; the union-find merges are replayed on the
  * host in canonical order from the contact records.  Whole-mesh contexts only (not clsn_set_slice). */
+/* Strain limiting (reduceSuperelast, dcollid.cpp:485-596; called from resolveCollision :355 between the
+ * final positions and the final velocities, so it only changes avgVel -> vel).  Rest lengths are the
+ * application's data in the reference: tri_len0[3T] = TRI::side_length0 (edge j joins points j and
+ * (j+1)%3), bond_len0[B] = BOND::length0; set them again after clsn_set_topology.
+ * clsn_set_strain_limiting(on) makes clsn_resolve / clsn_step_host run it (default off: outside the
+ * timed hot loop); clsn_strain_limit runs it alone on the resident avgVel.  The reference's sequential
+ * sweep order is kept exactly through a wavefront schedule of the edge visits (csrc/strain.cuh). */
+int clsn_set_rest_lengths(clsn_ctx*, const double* tri_len0, const double* bond_len0);
+int clsn_set_strain_limiting(clsn_ctx*, int on);
+int clsn_strain_limit(clsn_ctx*, int32_t* sweeps, int32_t* edges_last);
 int clsn_set_impact_zones(clsn_ctx*, int on, int max_iter);
 int clsn_compute_impact_zone(clsn_ctx*, int max_iter, clsn_zone_stats* out);
 /* any pointer may be NULL.  x[3V] final Coords, avgvel[3V], has_collsn[V] */

@@ -107,7 +107,7 @@ def set_libm(mode: int):
 class OracleSolver:
     """The C restatement driven on a collision_b200.scenes.Scene."""
 
-    def __init__(self, scene, impact_zones=True, strain_limiting=False):
+    def __init__(self, scene, impact_zones=True, strain_limiting=True):
         """impact_zones: resolve() enters computeImpactZone when the CCD passes are exhausted, like the
         reference's detectCollision (dcollid.cpp:464-467).  strain_limiting: resolve() runs
         reduceSuperelast (:355) with the scene's rest lengths."""

@@ -25,7 +25,7 @@ def main():
                      ("spheres", scenes.cloth_spheres(n_layers=2, n=17, n_side=2, level=1, seed=31))):
         for mode in ("owner", "gather"):
             CollisionSolver3d.set_params_from(sc.params)
-            one = CollisionSolver3d(device=local, impact_zones=False)  # DistributedSolver stops after the CCD passes
+            one = CollisionSolver3d(device=local, impact_zones=False, strain_limiting=False)  # DistributedSolver stops after the CCD passes
             one.assembleFromInterface(sc, sc.dt)
             many = CollisionSolver3d(device=local)
             many.assembleFromInterface(sc, sc.dt)

@@ -20,8 +20,8 @@ def big():
     return scenes.layered_cloth(8, 251)
 
 
-def _solver(sc, impact_zones=True):
-    g = CollisionSolver3d(impact_zones=impact_zones)
+def _solver(sc, impact_zones=True, strain_limiting=True):
+    g = CollisionSolver3d(impact_zones=impact_zones, strain_limiting=strain_limiting)
     CollisionSolver3d.set_params_from(sc.params)
     g.assembleFromInterface(sc, sc.dt)
     return g
@@ -30,7 +30,7 @@ def _solver(sc, impact_zones=True):
 def test_config4_deterministic_and_sane(big):
     sc = big
     assert sc.T == 1_000_000
-    g = _solver(sc, impact_zones=False)   # the hot loop alone, as benchmarked
+    g = _solver(sc, impact_zones=False, strain_limiting=False)   # the hot loop alone, as benchmarked
     outs = []
     for rep in range(2):
         x, vel = sc.x.copy(), sc.vel.copy()
@@ -93,6 +93,37 @@ def test_config4_slices_equal_whole_first_pass(big):
     _, av, has = part.download()
     assert same_bits(av, avw) and np.array_equal(has, hasw)
     part.close()
+
+
+def test_config4_strain_limiting_full_size(big):
+    """reduceSuperelast at 1 M triangles (3 M edge visits per sweep, ten sweeps): the wavefront schedule
+    against the oracle's sequential sweeps, bit for bit, on the step's own average velocities with 5 %
+    of the points kicked."""
+    import time
+    from parity_util import strain_inputs
+    sc = big
+    g = _solver(sc)
+    orc = port.OracleSolver(sc)
+    xn = sc.x + sc.dt * sc.vel
+    g.upload(sc.x, xn)
+    orc.set_state(sc.x, xn)
+    for case in (1, 0):
+        av = strain_inputs(sc, case)
+        g.set_avgvel(av)
+        orc.set_avgvel(av)
+        g.reduceSuperelast() if case == 1 else None      # first call builds the schedule: time the second
+        g.set_avgvel(av)
+        g.synchronize()
+        t0 = time.perf_counter()
+        r_g = g.reduceSuperelast()
+        dt_g = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        r_o = orc.strain_limit()
+        dt_o = time.perf_counter() - t0
+        print(f"strain limiting 1M tris case {case}: sweeps/edges {r_g}, GPU {dt_g * 1e3:.2f} ms, oracle {dt_o * 1e3:.0f} ms")
+        assert r_g == r_o
+        assert same_bits(g.download()[1], orc.get(port.F_AVGVEL))
+    g.close()
 
 
 def test_sample_of_config4_matches_oracle():

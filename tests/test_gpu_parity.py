@@ -85,6 +85,7 @@ def test_whole_step_parity(name):
             assert all(a <= b for a, b in zip([p["candidates"] for p in st["ccd"]], st_o[9:9 + st_o[1]]))
         assert int(st["still_colliding"]) == st_o[7]
         assert st["zone_iterations"] == st_o[14] and st["zones"] == st_o[15]   # the impact-zone fail-safe, when entered
+        assert (st["strain_sweeps"], st["strain_edges"]) == (st_o[16], st_o[17])   # reduceSuperelast
         assert same_bits(xg, orc.get(port.F_X))
         assert same_bits(vg, vo)
         assert np.array_equal(has, orc.geti(port.I_HAS_COLLSN))
@@ -302,9 +303,9 @@ def test_impact_zone_loop_alone_and_disabled():
     assert gpu.detect(port.COLLISION)["true_pairs"] == 0
     gpu.close()
     # fail-safe off: identical to an oracle that stops after MAX_ITER passes, and still colliding
-    off = CollisionSolver3d(impact_zones=False)
+    off = CollisionSolver3d(impact_zones=False, strain_limiting=False)
     off.assembleFromInterface(sc, sc.dt)
-    o2 = port.OracleSolver(sc, impact_zones=False)
+    o2 = port.OracleSolver(sc, impact_zones=False, strain_limiting=False)
     o2.set_state(x, xn)
     vo, xg, vg = vel.copy(), xn.copy(), vel.copy()
     st_o = o2.resolve(vo)
@@ -312,3 +313,29 @@ def test_impact_zone_loop_alone_and_disabled():
     assert off.last_stats["still_colliding"] and off.last_stats["zone_iterations"] == 0 and st_o[14] == 0
     assert same_bits(xg, o2.get(port.F_X)) and same_bits(vg, vo)
     off.close()
+
+
+@pytest.mark.parametrize("name", ["two_sheets", "mixed", "layered", "string_string"])
+def test_strain_limiting_matches_oracle(name):
+    """reduceSuperelast (dcollid.cpp:485-596) alone on kicked velocity fields: the wavefront-scheduled
+    kernel reproduces the sequential Gauss-Seidel sweeps bit for bit -- same sweep count (1..10), same
+    number of edges averaged in the last sweep, same avgVel."""
+    from parity_util import STRAIN_SCENES, strain_inputs
+    sc = STRAIN_SCENES[name]()
+    gpu, orc = make_pair(sc)
+    gpu.set_debug(False, False)
+    xn = sc.x + sc.dt * sc.vel
+    orc.set_state(sc.x, xn)
+    gpu.upload(sc.x, xn)
+    sweeps = []
+    for case in range(3):
+        av = strain_inputs(sc, case)
+        orc.set_avgvel(av)
+        gpu.set_avgvel(av)
+        r_o = orc.strain_limit()
+        r_g = gpu.reduceSuperelast()
+        assert r_g == r_o, (case, r_g, r_o)
+        assert same_bits(gpu.download()[1], orc.get(port.F_AVGVEL)), case
+        sweeps.append(r_o[0])
+    assert sweeps[0] == 1 and max(sweeps) > 1
+    gpu.close()

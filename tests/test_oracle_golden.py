@@ -172,7 +172,7 @@ def test_impact_zone_loop_in_resolve():
     assert n > 0
     out = o2.impact_zone()
     assert out[0] == st[14] and out[1] == st[15]
-    o2.boundary(); o2.final_position(); o2.final_velocity(v2)
+    o2.boundary(); o2.final_position(); o2.strain_limit(); o2.final_velocity(v2)
     assert same_bits(o1.get(port.F_X), o2.get(port.F_X)) and same_bits(v1, v2)
     o2.set_state(o2.get(port.F_X_OLD), o2.get(port.F_X))
     o2.avg_velocity()
