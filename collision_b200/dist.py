@@ -225,7 +225,20 @@ class DistributedSolver:
                 break
         stats["n_ccd_passes"] = cd
         stats["still_colliding"] = is_collision
+        stats["zone_iterations"] = stats["zones"] = stats["strain_sweeps"] = stats["strain_edges"] = 0
+        if is_collision and s.impact_zones:
+            # computeImpactZone (dcollid.cpp:227-265) needs every pair's first hit in canonical order: the state is
+            # replicated, so each rank runs the fail-safe on the whole mesh (identical results, no exchange)
+            c = s.ctx
+            c.check(c.L.clsn_set_slice(c.h, 0, 1))
+            try:
+                zs = s.computeImpactZone(s.max_zone_iterations)
+            finally:
+                c.check(c.L.clsn_set_slice(c.h, self.rank, self.world))
+            stats["zone_iterations"], stats["zones"] = zs["iterations"], zs["zones"]
         s.boundary()
         s.final_position()
+        if s.strain_limiting:   # reduceSuperelast (dcollid.cpp:355), replicated like the state it works on
+            stats["strain_sweeps"], stats["strain_edges"] = s.reduceSuperelast()
         s.synchronize()
         return stats

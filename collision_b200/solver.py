@@ -258,6 +258,7 @@ class CollisionSolver3d:
     def setImpactZones(self, on=True, max_iterations=0):
         self.ctx.check(self.ctx.L.clsn_set_impact_zones(self.ctx.h, 1 if on else 0, int(max_iterations)))
         self.impact_zones = bool(on)
+        self.max_zone_iterations = int(max_iterations)
 
     def setStrainLimiting(self, on=True):
         self.ctx.check(self.ctx.L.clsn_set_strain_limiting(self.ctx.h, 1 if on else 0))

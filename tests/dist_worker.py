@@ -25,13 +25,14 @@ def main():
                      ("spheres", scenes.cloth_spheres(n_layers=2, n=17, n_side=2, level=1, seed=31))):
         for mode in ("owner", "gather"):
             CollisionSolver3d.set_params_from(sc.params)
-            one = CollisionSolver3d(device=local, impact_zones=False, strain_limiting=False)  # DistributedSolver stops after the CCD passes
+            one = CollisionSolver3d(device=local)   # impact zones and strain limiting on, on both sides
             one.assembleFromInterface(sc, sc.dt)
             many = CollisionSolver3d(device=local)
             many.assembleFromInterface(sc, sc.dt)
             stepper = DistributedSolver(many, mode=mode)
             x, vel = sc.x.copy(), sc.vel.copy()
             contacts = 0
+            zone_iters = 0
             for step in range(3):
                 xn = x + sc.dt * vel
                 xg, vg = xn.copy(), vel.copy()
@@ -45,9 +46,13 @@ def main():
                 assert same_bits(vm, vg), (name, mode, step, "velocities")
                 assert st["n_ccd_passes"] == one.last_stats["n_ccd_passes"]
                 assert [p["true_pairs"] for p in st["ccd"]] == [p["true_pairs"] for p in one.last_stats["ccd"]]
+                for k in ("zone_iterations", "zones", "strain_sweeps", "strain_edges"):
+                    assert st[k] == one.last_stats[k], (name, mode, step, k)
+                zone_iters += st["zone_iterations"]
                 contacts += sum(p["true_pairs"] for p in st["ccd"])
                 x, vel = xg, vg
             assert contacts > 0
+            assert name != "mixed" or zone_iters > 0   # the mixed scene enters the impact-zone fail-safe in step 2
             one.close()
             many.close()
     dist.barrier()
