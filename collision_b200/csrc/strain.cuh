@@ -48,11 +48,11 @@ __device__ __forceinline__ double dist3(const double* p, const double* q)  // di
     return sqrt(s);
 }
 
-// one edge visit of reduceSuperelastOnce (dcollid.cpp:495-556); returns whether the edge was averaged
+// one edge visit of reduceSuperelastOnce (dcollid.cpp:495-556); returns whether the edge was averaged.
+// Everything but avgVel is constant during the sweeps and may have been fetched ahead of time.
 template <bool WRITE>
-__device__ __forceinline__ bool strain_visit(int2 e, double len0, const Vec4* __restrict__ xo, Vec4* av, double dt)
+__device__ __forceinline__ bool strain_visit(int2 e, double len0, const Vec4& X0, const Vec4& X1, Vec4* av, double dt)
 {
-    const Vec4 X0 = ldg_vec4(xo + e.x), X1 = ldg_vec4(xo + e.y);
     const double x0[3] = {X0.x, X0.y, X0.z}, x1[3] = {X1.x, X1.y, X1.z};
     double a0[3], a1[3], c0[3], c1[3];
     load_cg3(av + e.x, a0);
@@ -84,7 +84,11 @@ __global__ void k_strain_check(int M, const int2* __restrict__ visits, const dou
                                const Vec4* __restrict__ xo, Vec4* av, double dt, StrainResult* res)
 {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
-    bool fix = v < M && strain_visit<false>(visits[v], len0[v], xo, av, dt);
+    bool fix = false;
+    if (v < M) {
+        const int2 e = visits[v];
+        fix = strain_visit<false>(e, len0[v], ldg_vec4(xo + e.x), ldg_vec4(xo + e.y), av, dt);
+    }
     if (__any_sync(0xffffffffu, fix) && (threadIdx.x & 31) == 0) res->any = 1;
 }
 
@@ -102,11 +106,36 @@ __global__ void __launch_bounds__(256) k_strain_wavefront(int nlev, const int* _
     }
     const int gtid = (int)grid.thread_rank(), gsize = (int)grid.size();
     int sweep_done = 0;
+    // The critical path is one level = barrier + dependent loads.  Only avgVel depends on the previous
+    // level, so a thread fetches the schedule entry, the edge, its rest length and x_old of its first visit
+    // of the NEXT level before it enters the barrier; after the barrier one round trip (avgVel) is left.
+    int lo = lev_off[0], hi = lev_off[1];
+    int2 pe = make_int2(0, 0);
+    double plen = 0.0;
+    Vec4 pX0 = {0, 0, 0, 0}, pX1 = {0, 0, 0, 0};
+    int ps = 0;
+    auto prefetch = [&](int i) {
+        const unsigned g = sched[i];
+        ps = (int)(g / (unsigned)M);
+        const int v = (int)(g - (unsigned)ps * (unsigned)M);
+        pe = visits[v];
+        plen = len0[v];
+        pX0 = ldg_vec4(xo + pe.x);
+        pX1 = ldg_vec4(xo + pe.y);
+    };
+    if (lo + gtid < hi) prefetch(lo + gtid);
     for (int lev = 0; lev < nlev; ++lev) {
-        for (int i = lev_off[lev] + gtid; i < lev_off[lev + 1]; i += gsize) {
+        if (lo + gtid < hi && strain_visit<true>(pe, plen, pX0, pX1, av, dt)) atomicAdd(&res->viol[ps], 1);
+        for (int i = lo + gtid + gsize; i < hi; i += gsize) {  // levels wider than the grid (rare)
             const unsigned g = sched[i];
             const int s = (int)(g / (unsigned)M), v = (int)(g - (unsigned)s * (unsigned)M);
-            if (strain_visit<true>(visits[v], len0[v], xo, av, dt)) atomicAdd(&res->viol[s], 1);
+            const int2 e = visits[v];
+            if (strain_visit<true>(e, len0[v], ldg_vec4(xo + e.x), ldg_vec4(xo + e.y), av, dt)) atomicAdd(&res->viol[s], 1);
+        }
+        if (lev + 1 < nlev) {
+            lo = hi;
+            hi = lev_off[lev + 2];
+            if (lo + gtid < hi) prefetch(lo + gtid);
         }
         grid.sync();
         bool stop = false;
