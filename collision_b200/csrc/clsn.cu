@@ -1319,15 +1319,9 @@ extern "C" int clsn_strain_limit(clsn_ctx* c, int32_t* sweeps, int32_t* edges_la
 }
 
 // resolveCollision, dcollid.cpp:317-362 (detectProximity :390-406, detectCollision :430-468)
-extern "C" int clsn_resolve(clsn_ctx* c, clsn_step_stats* stats)
+static int resolve_impl(clsn_ctx* c, clsn_step_stats& s)
 {
-    if (!c || !c->V) return CLSN_E_ARG;
-    cudaSetDevice(c->device);
-    clsn_step_stats s;
-    memset(&s, 0, sizeof(s));
     int r;
-    c->timing = true;
-    c->n_marks = 0;
     CK(cudaEventRecord(c->ev[0], c->stream));
     mark(c, PH_OTHER);
     if ((r = clsn_avg_velocity(c))) return r;
@@ -1360,13 +1354,26 @@ extern "C" int clsn_resolve(clsn_ctx* c, clsn_step_stats* stats)
     if (c->h_counters[CTR_ERROR]) return fail(c, CLSN_E_NUMERIC, "NaN/Inf in the collision step (reference: clean_up(ERROR))");
     CK(cudaEventElapsedTime(&s.ms_total, c->ev[0], c->ev[1]));
     if (c->strain_pending) strain_finish(c, &s.strain_sweeps, &s.strain_edges);
-    c->timing = false;
     for (size_t i = 1; i < c->n_marks; ++i) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, c->marks[i - 1], c->marks[i]) == cudaSuccess) s.ms_phase[c->mark_phase[i]] += ms;
     }
-    if (stats) *stats = s;
     return CLSN_OK;
+}
+
+extern "C" int clsn_resolve(clsn_ctx* c, clsn_step_stats* stats)
+{
+    if (!c || !c->V) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    clsn_step_stats s;
+    memset(&s, 0, sizeof(s));
+    c->timing = true;   // phase marks are only recorded inside a whole step
+    c->n_marks = 0;
+    const int r = resolve_impl(c, s);
+    c->timing = false;  // also on the error paths: a failed step must not leave the marks armed
+    c->strain_pending = false;
+    if (r == CLSN_OK && stats) *stats = s;
+    return r;
 }
 
 extern "C" int clsn_step_host(clsn_ctx* c, const double* x_old, const double* x_new, double* x_out, double* vel_inout,
