@@ -16,6 +16,7 @@
 #include <cub/cub.cuh>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <algorithm>
@@ -110,7 +111,7 @@ template <bool MOVING>
 __global__ void __launch_bounds__(CULL_THREADS, CULL_MIN_BLOCKS)
 k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restrict__ elem, const Vec4* __restrict__ xo,
        const Vec4* __restrict__ av, NarrowParams P, FeatRec* __restrict__ feats, long long cap_feats,
-       unsigned long long* counters)
+       unsigned long long* counters, bool split_by_kind)
 {
     __shared__ double s_x[CULL_THREADS][CULL_ROW];
     __shared__ double s_v[MOVING ? CULL_THREADS : 1][CULL_ROW];
@@ -258,12 +259,13 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
                     coplanar_coeffs(q, ca, cb, cc, cd);
                     const int kindc = coplanar_maybe(ca, cb, cc, cd, P.dt);
                     keep = kindc != 0;
-                    back = kindc == 2;
+                    back = split_by_kind ? rec.edge != 0 : kindc == 2;
                 }
             }
             // two kinds of entries, one filling the list from the front and one from the back, so that the
             // consumer's warps are homogeneous: proximity -> point-triangle | edge-edge (k_contact);
-            // CCD -> trig branch | other branches of the cubic (k_roots, which re-splits by test kind)
+            // CCD -> point-triangle | edge-edge (k_feature), or, for the staged pipeline, trig branch | other
+            // branches of the cubic (k_roots, which re-splits by test kind)
 #pragma unroll
             for (int kind = 0; kind < 2; ++kind) {
                 const bool mine = keep && back == (kind == 1);
@@ -436,6 +438,155 @@ k_contact(const FeatRec* __restrict__ feats, const RootRec* __restrict__ rootrec
     }
 }
 
+// ------------------------------------------------------------------ fused CCD feature kernel (pipeline 1)
+// One gather per feature.  fastpath.cuh settles four features out of five in plain FP64: no valid root
+// (nothing to do), or "misses at every root" -- then the outcome is the reference's own static test at
+// t = dt, run right here.  Only the features that may fire AT a root go through the correctly rounded
+// solve: they are queued per warp in shared memory and processed 32 at a time, so the double-double code
+// runs with full warps.  Output: the hit list (feature + first hit time), point-triangle entries from the
+// front, edge-edge entries from the back; k_emit turns it into contact and impulse records.
+struct HitRec {  // 32 B
+    FeatRec f;
+    double t;
+};
+#define FEATURE_QCAP 64
+#ifndef FEATURE_MIN_BLOCKS
+#define FEATURE_MIN_BLOCKS 3
+#endif
+
+__device__ __forceinline__ void load_quad(const FeatRec& fr, const Vec4* __restrict__ xo, const Vec4* __restrict__ av, Quad& q)
+{
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        q.id[i] = fr.id[i];
+        const Vec4 x = ldg_vec4(xo + fr.id[i]), v = ldg_vec4(av + fr.id[i]);
+        q.xo[i][0] = x.x; q.xo[i][1] = x.y; q.xo[i][2] = x.z;
+        q.av[i][0] = v.x; q.av[i][1] = v.y; q.av[i][2] = v.z;
+        q.flags[i] = 0;
+        q.body[i] = 0;
+    }
+}
+
+__device__ __forceinline__ void push_hit(HitRec* __restrict__ hits, long long cap_hits, unsigned long long* counters, const FeatRec& fr,
+                                         double t)
+{
+    const bool ee = fr.edge != 0;
+    long long slot;
+    if (ee) slot = (long long)reserve(&counters[CTR_HITS_EE], 1);
+    else slot = (long long)reserve(&counters[CTR_HITS], 1);
+    if (slot < cap_hits) {
+        HitRec* dst = ee ? hits + (cap_hits - 1 - slot) : hits + slot;
+        uint2* o = reinterpret_cast<uint2*>(dst);
+        o[0] = make_uint2(fr.entry, (unsigned)fr.id[0]);
+        o[1] = make_uint2((unsigned)fr.id[1], (unsigned)fr.id[2]);
+        o[2] = make_uint2((unsigned)fr.id[3], fr.edge);
+        reinterpret_cast<double*>(dst)[3] = t;
+    }
+}
+
+__global__ void __launch_bounds__(FEAT_THREADS, FEATURE_MIN_BLOCKS)
+k_feature(const FeatRec* __restrict__ feats, long long cap_feats, const Vec4* __restrict__ xo, const Vec4* __restrict__ av,
+          NarrowParams P, Emit E, HitRec* __restrict__ hits, long long cap_hits)
+{
+    __shared__ long long s_at[FEAT_THREADS / 32][FEATURE_QCAP];
+    __shared__ int s_n[FEAT_THREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long n_pt = (long long)E.counters[CTR_FEATS], n_ee = (long long)E.counters[CTR_FEATS_EE];
+    if (n_pt + n_ee > cap_feats) return;  // overflow: the host grows the list and repeats the pass
+    const long long n = n_pt + n_ee;
+    const double h = P.eps;               // CCD: the static tests run with the rounding tolerance (dcollid.cpp:756)
+    unsigned long long n_cop = 0, n_exact = 0;
+    if (lane == 0) s_n[w] = 0;
+    __syncwarp();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); ; t0 += stride) {
+        const long long t = t0 + lane;
+        if (t0 < n && t < n) {
+            const long long at = t < n_pt ? t : cap_feats - 1 - (t - n_pt);
+            const FeatRec fr = load_featrec(feats + at);
+            Quad q;
+            load_quad(fr, xo, av, q);
+            const bool edge = fr.edge != 0;
+            const int st = feature_fast(q, edge, P.dt, h, P.eps);
+            if (st == FAST_DT_ONLY) {
+                ++n_cop;
+                double X[4][3];
+                positions_at<true>(q, P.dt, X);
+                const bool hit = edge ? edge_to_edge<false>(P, E, q, 0ull, X, h, P.dt) : point_to_tri<false>(P, E, q, 0ull, X, h, P.dt);
+                if (hit) push_hit(hits, cap_hits, E.counters, fr, P.dt);
+            } else if (st == FAST_UNCERTAIN) {
+                const int pos = atomicAdd(&s_n[w], 1);
+                s_at[w][pos] = at;
+            }
+        }
+        __syncwarp();
+        const bool done = t0 + stride >= n;  // no further round for this warp
+        int nq = s_n[w];
+        while (nq >= 32 || (done && nq > 0)) {
+            const int take = nq < 32 ? nq : 32;
+            const int base = nq - take;
+            if (lane < take) {
+                const long long at = s_at[w][base + lane];
+                const FeatRec fr = load_featrec(feats + at);
+                Quad q;
+                load_quad(fr, xo, av, q);
+                double roots[3] = {-1, -1, -1};
+                ++n_exact;
+                if (is_coplanar<false>(q, P.dt, roots)) {
+                    ++n_cop;
+                    const double th = feature_first_hit<true>(P, E, q, fr.edge != 0, h, roots[0], roots[1], roots[2]);
+                    if (th >= 0) push_hit(hits, cap_hits, E.counters, fr, th);
+                }
+            }
+            nq = base;
+            __syncwarp();
+        }
+        __syncwarp();  // every lane has read s_n[w] before lane 0 rewrites it
+        if (lane == 0) s_n[w] = nq;
+        __syncwarp();
+        if (done) break;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        n_cop += __shfl_xor_sync(0xffffffffu, n_cop, o);
+        n_exact += __shfl_xor_sync(0xffffffffu, n_exact, o);
+    }
+    if (lane == 0) {
+        if (n_cop) atomicAdd(&E.counters[CTR_ROOTS], n_cop);   // features with isCoplanar == true (stats)
+        if (n_exact) atomicAdd(&E.counters[CTR_EXACT], n_exact);
+    }
+}
+
+// contact + impulse records of the hit list (the second half of k_contact, on a dense list)
+__global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS)
+k_emit(const HitRec* __restrict__ hits, long long cap_hits, const int2* __restrict__ pairs, const Vec4* __restrict__ xo,
+       const Vec4* __restrict__ av, const uint8_t* __restrict__ vflags, const int* __restrict__ vbody, NarrowParams P, Emit E,
+       unsigned* __restrict__ pair_hit)
+{
+    const long long n_pt = (long long)E.counters[CTR_HITS], n_ee = (long long)E.counters[CTR_HITS_EE];
+    if (n_pt + n_ee > cap_hits) return;  // overflow: the host grows the list and repeats the pass
+    const long long n = n_pt + n_ee;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const long long at = t < n_pt ? t : cap_hits - 1 - (t - n_pt);
+        const FeatRec fr = load_featrec(&hits[at].f);
+        const double th = __ldg(reinterpret_cast<const double*>(hits + at) + 3);
+        Quad q;
+        load_quad(fr, xo, av, q);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q.flags[i] = __ldg(vflags + fr.id[i]);
+        if ((q.flags[0] & 3) && (q.flags[1] & 3) && (q.flags[2] & 3) && (q.flags[3] & 3)) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q.body[i] = __ldg(vbody + q.id[i]);
+        }
+        const unsigned pi = fr.entry & 0x0fffffffu;
+        const int f = (int)(fr.entry >> 28);
+        const int2 pr = __ldg(pairs + pi);
+        const unsigned long long key = ((unsigned long long)(unsigned)pr.x << 34) | ((unsigned long long)(unsigned)pr.y << 4) |
+                                       (unsigned long long)f;
+        feature_emit<true>(P, E, q, key, fr.edge != 0, P.eps, th);
+        atomicOr(pair_hit + (pi >> 5), 1u << (pi & 31));
+    }
+}
+
 // number of pairs for which isProximity / isCollision returned true (the tree's `count`, AABB.cpp:296-297)
 __global__ void k_count_true(const unsigned* __restrict__ pair_hit, long long n_words, unsigned long long* counters)
 {
@@ -518,6 +669,8 @@ struct clsn_ctx {
     DevBuf<FeatRec> feats;
     DevBuf<unsigned> pair_hit;
     DevBuf<RootRec> rootrecs;
+    DevBuf<HitRec> hits;
+    int pipeline = 0;           // 1 = fused CCD feature kernel (k_feature + k_emit), 0 = staged (k_roots + k_contact)
     DevBuf<PointRec> prec, prec_sorted;
     DevBuf<BodyRec> brec;
     DevBuf<Contact> contacts;
@@ -605,6 +758,7 @@ extern "C" int clsn_create(clsn_ctx** out, int device)
     p.eps = 1e-6; p.thickness = 1e-4; p.dt = 1e-3; p.k = 1000; p.m = 0.01; p.lambda = 0.02; p.cr = 0.0;
     for (int i = 0; i < 3; ++i) { p.lo[i] = -1e30; p.hi[i] = 1e30; }
     c->prm = p;
+    if (const char* e = getenv("CLSN_PIPELINE")) c->pipeline = atoi(e) == 0 ? 0 : 1;
     *out = c;
     return CLSN_OK;
 }
@@ -618,7 +772,7 @@ extern "C" void clsn_destroy(clsn_ctx* c)
     c->xo.release(); c->xn.release(); c->av.release(); c->has.release(); c->dirty.release(); c->imp_rg.release(); c->cnt_rg.release();
     c->stage.release(); c->code.release(); c->code_sorted.release(); c->idx.release(); c->leaf_elem.release();
     c->leaf_parent.release(); c->flags.release(); c->nodes.release(); c->lbox.release(); c->bounds.release();
-    c->cub_tmp.release(); c->pairs.release(); c->dbg_cand.release(); c->feats.release(); c->pair_hit.release(); c->rootrecs.release(); c->prec.release(); c->prec_sorted.release(); c->brec.release();
+    c->cub_tmp.release(); c->pairs.release(); c->dbg_cand.release(); c->feats.release(); c->pair_hit.release(); c->rootrecs.release(); c->hits.release(); c->prec.release(); c->prec_sorted.release(); c->brec.release();
     c->contacts.release(); c->cnt.release(); c->offs.release(); c->fill.release(); c->perm.release();
     c->perm_sorted.release(); c->skey.release(); c->counters.release(); c->acc_imp.release(); c->acc_fric.release();
     c->rigid.release(); c->zone_lists.release(); c->strain.release();
@@ -665,6 +819,13 @@ extern "C" int clsn_set_exact_stats(clsn_ctx* c, int on)
 {
     if (!c) return CLSN_E_ARG;
     c->exact_stats = on != 0;
+    return CLSN_OK;
+}
+
+extern "C" int clsn_set_pipeline(clsn_ctx* c, int pipeline)
+{
+    if (!c || (pipeline != 0 && pipeline != 1)) return CLSN_E_ARG;
+    c->pipeline = pipeline;
     return CLSN_OK;
 }
 
@@ -733,7 +894,8 @@ extern "C" int clsn_set_topology(clsn_ctx* c, int V, int T, const int32_t* tri_i
     CK(cudaMemset(c->cnt.p, 0, ((size_t)V + 1) * sizeof(int)));
     if (c->pairs.n == 0) CK(c->pairs.reserve((size_t)16 * n1 + 1024));
     if (c->feats.n == 0) CK(c->feats.reserve((size_t)64 * n1 + 1024));
-    if (c->rootrecs.n == 0) CK(c->rootrecs.reserve((size_t)16 * n1 + 1024));
+    if (c->pipeline == 0 && c->rootrecs.n == 0) CK(c->rootrecs.reserve((size_t)16 * n1 + 1024));
+    if (c->pipeline == 1 && c->hits.n == 0) CK(c->hits.reserve((size_t)4 * n1 + 1024));
     CK(c->pair_hit.reserve(c->pairs.n / 32 + 2));
     if (c->prec.n == 0) CK(c->prec.reserve((size_t)8 * n1 + 1024));
     CK(c->perm.reserve(c->prec.n)); CK(c->perm_sorted.reserve(c->prec.n)); CK(c->skey.reserve(c->prec.n));
@@ -878,7 +1040,7 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
     const int q_lo = (int)((long long)N * c->rank / c->nranks), q_hi = (int)((long long)N * (c->rank + 1) / c->nranks);
     for (int attempt = 0; attempt < 8; ++attempt) {
         CK(cudaMemsetAsync(c->counters.p, 0, CTR_ERROR * sizeof(unsigned long long), c->stream));  // keep CTR_ERROR
-        CK(cudaMemsetAsync(c->counters.p + CTR_DBG_CAND, 0, 6 * sizeof(unsigned long long), c->stream));  // + CTR_FEATS, CTR_BOXSURV, CTR_ROOTS, CTR_FEATS_EE, CTR_ROOTS_EE
+        CK(cudaMemsetAsync(c->counters.p + CTR_DBG_CAND, 0, (CTR_COUNT - CTR_DBG_CAND) * sizeof(unsigned long long), c->stream));  // CTR_FEATS ... CTR_EXACT
         CK(cudaMemsetAsync(c->flags.p, 0, (size_t)N * sizeof(int), c->stream));
         CK(cudaMemsetAsync(c->cnt.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
         CK(cudaMemsetAsync(c->cnt_rg.p, 0, c->nbody * sizeof(int), c->stream));
@@ -914,18 +1076,29 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
         const long long hit_words = (long long)(c->pairs.n / 32 + 1);
         CK(cudaMemsetAsync(c->pair_hit.p, 0, (size_t)hit_words * sizeof(unsigned), c->stream));
         const int grid = c->sm_count * 16;
+        const bool fused = c->pipeline == 1;
         if (moving) {
+            if (fused && c->hits.n == 0) CK(c->hits.reserve((size_t)4 * N + 1024));
+            if (!fused && c->rootrecs.n == 0) CK(c->rootrecs.reserve((size_t)16 * N + 1024));
             k_cull<true><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p, P,
-                                                                c->feats.p, (long long)c->feats.n, c->counters.p);
+                                                                c->feats.p, (long long)c->feats.n, c->counters.p, fused);
             mark(c, PH_CULL);
-            k_roots<<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P.dt, c->rootrecs.p,
-                                                           (long long)c->rootrecs.n, c->counters.p);
-            mark(c, PH_ROOTS);
-            k_contact<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, c->rootrecs.p, (long long)c->rootrecs.n, c->pairs.p,
-                                                                   c->xo.p, c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+            if (fused) {
+                k_feature<<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E, c->hits.p,
+                                                                 (long long)c->hits.n);
+                mark(c, PH_ROOTS);
+                k_emit<<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p, c->vflags.p,
+                                                              c->vbody.p, P, E, c->pair_hit.p);
+            } else {
+                k_roots<<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P.dt, c->rootrecs.p,
+                                                               (long long)c->rootrecs.n, c->counters.p);
+                mark(c, PH_ROOTS);
+                k_contact<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, c->rootrecs.p, (long long)c->rootrecs.n, c->pairs.p,
+                                                                       c->xo.p, c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+            }
         } else {
             k_cull<false><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p, P,
-                                                                 c->feats.p, (long long)c->feats.n, c->counters.p);
+                                                                 c->feats.p, (long long)c->feats.n, c->counters.p, false);
             mark(c, PH_CULL);
             k_contact<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, c->rootrecs.p, (long long)c->feats.n, c->pairs.p,
                                                                     c->xo.p, c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
@@ -947,8 +1120,12 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
             CK(c->feats.reserve((size_t)((h[CTR_FEATS] + h[CTR_FEATS_EE]) * 5 / 4 + 1024)));
             redo = true;
         }
-        if (h[CTR_ROOTS] + h[CTR_ROOTS_EE] > c->rootrecs.n) {
+        if (!fused && h[CTR_ROOTS] + h[CTR_ROOTS_EE] > c->rootrecs.n) {
             CK(c->rootrecs.reserve((size_t)((h[CTR_ROOTS] + h[CTR_ROOTS_EE]) * 5 / 4 + 1024)));
+            redo = true;
+        }
+        if (fused && moving && h[CTR_HITS] + h[CTR_HITS_EE] > c->hits.n) {
+            CK(c->hits.reserve((size_t)((h[CTR_HITS] + h[CTR_HITS_EE]) * 5 / 4 + 1024)));
             redo = true;
         }
         if (h[CTR_PREC] > c->prec.n) {
@@ -970,6 +1147,7 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
             st->features = (int64_t)(h[CTR_FEATS] + h[CTR_FEATS_EE]);
             st->box_survivors = (int64_t)h[CTR_BOXSURV];
             st->coplanar = (int64_t)(h[CTR_ROOTS] + h[CTR_ROOTS_EE]);
+            st->exact_solves = fused && moving ? (int64_t)h[CTR_EXACT] : st->coplanar;
         }
         c->last_nprec = (long long)h[CTR_PREC];
         c->last_nbrec = (long long)h[CTR_BREC];

@@ -14,6 +14,7 @@
 #include <stdint.h>
 #include "crmath.cuh"
 #include "cubic.cuh"
+#include "fastpath.cuh"
 
 namespace clsn {
 
@@ -53,7 +54,8 @@ struct Emit {
 };
 
 enum { CTR_PAIRS = 0, CTR_CAND = 1, CTR_PREC = 2, CTR_BREC = 3, CTR_TRUE = 4, CTR_CONTACTS = 5, CTR_ERROR = 6,
-       CTR_DBG_CAND = 7, CTR_FEATS = 8, CTR_BOXSURV = 9, CTR_ROOTS = 10, CTR_FEATS_EE = 11, CTR_ROOTS_EE = 12, CTR_COUNT = 13 };
+       CTR_DBG_CAND = 7, CTR_FEATS = 8, CTR_BOXSURV = 9, CTR_ROOTS = 10, CTR_FEATS_EE = 11, CTR_ROOTS_EE = 12,
+       CTR_HITS = 13, CTR_HITS_EE = 14, CTR_EXACT = 15, CTR_COUNT = 16 };
 
 __device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 __device__ __forceinline__ double mag3(const double* a) { return sqrt(dot3(a, a)); }

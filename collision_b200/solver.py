@@ -39,7 +39,7 @@ class clsn_params(C.Structure):
 class clsn_pass_stats(C.Structure):
     _fields_ = [("candidates", C.c_int64), ("pairs_tested", C.c_int64), ("true_pairs", C.c_int64),
                 ("contacts", C.c_int64), ("contributions", C.c_int64), ("features", C.c_int64),
-                ("box_survivors", C.c_int64), ("coplanar", C.c_int64)]
+                ("box_survivors", C.c_int64), ("coplanar", C.c_int64), ("exact_solves", C.c_int64)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
@@ -123,6 +123,7 @@ def load_library():
     L.clsn_synchronize.argtypes = [V]
     L.clsn_set_debug.argtypes = [V, I, I]
     L.clsn_set_exact_stats.argtypes = [V, I]
+    L.clsn_set_pipeline.argtypes = [V, I]
     L.clsn_num_candidates.restype = C.c_int64
     L.clsn_num_candidates.argtypes = [V]
     L.clsn_get_candidates.argtypes = [V, P(C.c_int32)]
@@ -415,6 +416,10 @@ class CollisionSolver3d:
     def set_exact_stats(self, on=True):
         """full traversal in every pass so that stats['candidates'] equals the reference's callback count"""
         self.ctx.check(self.ctx.L.clsn_set_exact_stats(self.ctx.h, int(on)))
+
+    def set_pipeline(self, pipeline: int):
+        """1: fused CCD feature kernel (default); 0: staged correctly-rounded solve of every feature.  Same results."""
+        self.ctx.check(self.ctx.L.clsn_set_pipeline(self.ctx.h, int(pipeline)))
 
     def candidates(self):
         c = self.ctx

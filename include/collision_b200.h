@@ -65,6 +65,8 @@ typedef struct {
     int64_t features;       /* feature tests evaluated (survived box cull and, CCD, the classifier) */
     int64_t box_survivors;  /* feature tests that survived the swept-box cull                       */
     int64_t coplanar;       /* CCD: features whose cubic has a usable root (isCoplanar true)        */
+    int64_t exact_solves;   /* CCD: correctly rounded cubic solves (fused pipeline: only the features the
+                               plain-FP64 fast path could not settle; staged pipeline: == features)   */
 } clsn_pass_stats;
 
 typedef struct {
@@ -197,6 +199,13 @@ int clsn_set_debug(clsn_ctx*, int record_candidates, int record_contacts);
  * one, and clsn_pass_stats.candidates counts only the pairs found.  on != 0 restores the full traversal so
  * that `candidates` equals the reference's callback count in every pass (results are identical). */
 int clsn_set_exact_stats(clsn_ctx*, int on);
+/* CCD narrow phase of MovingPointToTri / MovingEdgeToEdge (dcollid3d.cpp:327-369) after the cull.
+ * 1 (default): fused -- one kernel settles every feature the plain-FP64 fast path can prove to miss at all
+ * of its roots (outcome = the static test at t = dt) and runs the correctly rounded cubic solve only for the
+ * rest; a second kernel emits the records of the hit list.  0: staged -- correctly rounded solve of every
+ * feature, then the static tests (the round-1 pipeline, kept for A/B measurements).  Results are bit-identical.
+ * The environment variable CLSN_PIPELINE=0|1 sets the default of new contexts. */
+int clsn_set_pipeline(clsn_ctx*, int pipeline);
 int64_t clsn_num_candidates(clsn_ctx*);
 int clsn_get_candidates(clsn_ctx*, int32_t* pairs /* 2 per pair, unsorted */);
 int64_t clsn_num_contacts(clsn_ctx*);

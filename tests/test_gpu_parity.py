@@ -93,6 +93,41 @@ def test_whole_step_parity(name):
     gpu.close()
 
 
+@pytest.mark.parametrize("name", ["two_sheets", "mixed", "ball_plane", "layered_4x24", "drape_small", "string_string"])
+def test_fused_and_staged_pipelines_agree(name):
+    """The fused CCD feature kernel (plain-FP64 fast path + correctly rounded solve of the undecided features)
+    against the staged pipeline that solves every feature correctly rounded: identical contact sets, counters
+    and state bits, and the fast path must actually save solves."""
+    sc = SCENES[name]()
+    outs = []
+    for pipeline in (0, 1):
+        gpu = CollisionSolver3d()
+        CollisionSolver3d.set_params_from(sc.params)
+        gpu.assembleFromInterface(sc, sc.dt)
+        gpu.set_pipeline(pipeline)
+        gpu.set_exact_stats(True)
+        x, vel = sc.x.copy(), sc.vel.copy()
+        log = []
+        for step in range(3):
+            xg = x + sc.dt * vel
+            vg = vel.copy()
+            has = gpu.resolveCollision(x, xg, vg)
+            st = gpu.last_stats
+            log.append((xg.copy(), vg.copy(), has.copy(),
+                        [(p["candidates"], p["true_pairs"], p["contacts"], p["contributions"], p["features"], p["coplanar"])
+                         for p in st["ccd"]], [p["exact_solves"] for p in st["ccd"]]))
+            x, vel = xg, vg
+        outs.append(log)
+        gpu.close()
+    solves = [0, 0]
+    for a, b in zip(*outs):
+        assert same_bits(a[0], b[0]) and same_bits(a[1], b[1]) and np.array_equal(a[2], b[2])
+        assert a[3] == b[3]
+        solves[0] += sum(a[4]); solves[1] += sum(b[4])
+    if solves[0] > 1000:
+        assert solves[1] < solves[0], solves
+
+
 def test_determinism_and_rerun():
     """same input twice -> identical bits (no floating-point atomics anywhere)"""
     sc = scenes.layered_cloth(4, 24, seed=99)

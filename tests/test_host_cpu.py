@@ -135,3 +135,78 @@ def test_cubic_path_matches_oracle_on_host():
     n, bad, rejected, rejected_wrong, oracle_true = map(int, subprocess.check_output([exe, so, "2000000", "7"], text=True).split())
     assert n == 2000000 and bad == 0 and rejected_wrong == 0
     assert rejected > n // 4 and oracle_true > n // 4   # both outcomes are well represented
+
+
+def _build_fastpath_check():
+    from oracle import port
+    so = port.build()
+    exe, lib = "/tmp/clsn_fastpath_check", "/tmp/libclsn_fastpath_check.so"
+    base = ["g++", "-O2", "-ffp-contract=off", "-mfma", "-x", "c++", "-I", os.path.join(ROOT, "collision_b200", "csrc"),
+            os.path.join(ROOT, "tests", "fastpath_check.cpp")]
+    subprocess.check_call(base + ["-o", exe, "-ldl", "-lm"])
+    subprocess.check_call(base + ["-fPIC", "-shared", "-o", lib, "-ldl", "-lm"])
+    return so, exe, lib
+
+
+def test_ccd_fast_path_is_conservative_on_host():
+    """collision_b200/csrc/fastpath.cuh -- the plain-FP64 fast path of the fused CCD feature kernel -- compiled
+    for the host with a libm perturbed by up to +-4 ulp per call, fuzzed against the oracle's
+    MovingPointToTri / MovingEdgeToEdge (correctly rounded libm): FAST_MISS only where the oracle's isCoplanar is
+    false, FAST_DT_ONLY only where it is true and nothing fires before t = dt.  Half of the cases sit on the
+    accept/reject boundary of the static tests.  (40 M cases were run once by hand.)"""
+    so, exe, _ = _build_fastpath_check()
+    n, wrong, n_miss, n_dt, n_unc, hits, hits_root = map(int, subprocess.check_output([exe, so, "1500000", "3"], text=True).split())
+    assert n == 1500000 and wrong == 0
+    assert n_miss > n // 10 and n_dt > n // 5 and hits_root > n // 5   # every outcome is well represented
+    assert n_unc < hits_root + n // 5                                  # ... and the fast path settles most non-hits
+
+
+def test_ccd_fast_path_on_oracle_scenes():
+    """The same check on real states: every CCD feature test of every candidate pair of every pass of a few
+    oracle-driven steps (cloth stacks, fixed and movable rigid bodies, strings)."""
+    import ctypes as C
+    from collision_b200 import scenes
+    from oracle import port
+    so, _, libp = _build_fastpath_check()
+    L = C.CDLL(libp)
+    L.fastpath_scene_check.restype = C.c_long
+    L.fastpath_scene_check.argtypes = [C.c_char_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                       C.c_double, C.c_void_p]
+    port.set_libm(port.LIBM_CR)
+    try:
+        for sc, steps in ((scenes.layered_cloth(3, 16, seed=3), 2), (scenes.two_sheets(), 2), (scenes.mixed(), 2),
+                          (scenes.ball_plane(level=2), 2), (scenes.string_string(), 20), (scenes.drape(n=24, level=2), 2)):
+            elem = np.full((sc.T + sc.B, 4), -1, np.int32)
+            elem[:sc.T, :3] = sc.tri_idx
+            elem[sc.T:, :2] = sc.bond_idx
+            orc = port.OracleSolver(sc, impact_zones=False, strain_limiting=False)
+            x, vel = sc.x.copy(), sc.vel.copy()
+            tot = np.zeros(4, np.int64)
+            for _ in range(steps):
+                orc.set_state(x, x + sc.dt * vel)
+                orc.avg_velocity()
+                orc.detect(port.PROXIMITY)
+                orc.apply()
+                for _it in range(5):
+                    xo = np.ascontiguousarray(orc.get(port.F_X_OLD))
+                    av = np.ascontiguousarray(orc.get(port.F_AVGVEL))
+                    n_true = orc.detect(port.COLLISION)
+                    cand = np.ascontiguousarray(orc.candidates())
+                    counts = np.zeros(4, np.int64)
+                    wrong = L.fastpath_scene_check(so.encode(), len(cand), cand.ctypes.data, elem.ctypes.data, xo.ctypes.data,
+                                                   av.ctypes.data, sc.dt, sc.params.eps, counts.ctypes.data)
+                    assert wrong == 0, (sc.name, wrong)
+                    tot += counts
+                    orc.apply()
+                    if n_true == 0:
+                        break
+                orc.boundary()
+                orc.final_position()
+                v = vel.copy()
+                orc.final_velocity(v)
+                x, vel = orc.get(port.F_X).copy(), v
+            # uncertain = features that do fire at a root + a thin boundary layer
+            assert tot[2] <= 2 * tot[3] + 50, (sc.name, tot)
+            orc.close()
+    finally:
+        port.set_libm(port.LIBM_NATIVE)
