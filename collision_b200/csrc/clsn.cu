@@ -484,6 +484,28 @@ __device__ __forceinline__ void push_hit(HitRec* __restrict__ hits, long long ca
     }
 }
 
+// correctly rounded solve + the reference's walk over the roots: the cold path of k_feature, kept out of line so
+// that the hot loop's instruction footprint stays small
+template <bool EDGE>
+__device__ __noinline__ double exact_first_hit(const NarrowParams& P, const Emit& E, const Quad& q, bool& coplanar)
+{
+    double roots[3] = {-1, -1, -1};
+    coplanar = is_coplanar<false>(q, P.dt, roots);
+    if (!coplanar) return -1.0;
+    double X[4][3];
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+        const double t = i < 3 ? roots[i] : P.dt;
+        if (t < 0) continue;
+        positions_at<true>(q, t, X);
+        const bool hit = EDGE ? edge_to_edge<false>(P, E, q, 0ull, X, P.eps, t) : point_to_tri<false>(P, E, q, 0ull, X, P.eps, t);
+        if (hit) return t;
+    }
+    return -1.0;
+}
+
+// EDGE = false: the point-triangle entries (front of the work list); EDGE = true: the edge-edge entries (back).
+template <bool EDGE>
 __global__ void __launch_bounds__(FEAT_THREADS, FEATURE_MIN_BLOCKS)
 k_feature(const FeatRec* __restrict__ feats, long long cap_feats, const Vec4* __restrict__ xo, const Vec4* __restrict__ av,
           NarrowParams P, Emit E, HitRec* __restrict__ hits, long long cap_hits)
@@ -493,7 +515,7 @@ k_feature(const FeatRec* __restrict__ feats, long long cap_feats, const Vec4* __
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long n_pt = (long long)E.counters[CTR_FEATS], n_ee = (long long)E.counters[CTR_FEATS_EE];
     if (n_pt + n_ee > cap_feats) return;  // overflow: the host grows the list and repeats the pass
-    const long long n = n_pt + n_ee;
+    const long long n = EDGE ? n_ee : n_pt;
     const double h = P.eps;               // CCD: the static tests run with the rounding tolerance (dcollid.cpp:756)
     unsigned long long n_cop = 0, n_exact = 0;
     if (lane == 0) s_n[w] = 0;
@@ -502,17 +524,16 @@ k_feature(const FeatRec* __restrict__ feats, long long cap_feats, const Vec4* __
     for (long long t0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); ; t0 += stride) {
         const long long t = t0 + lane;
         if (t0 < n && t < n) {
-            const long long at = t < n_pt ? t : cap_feats - 1 - (t - n_pt);
+            const long long at = EDGE ? cap_feats - 1 - t : t;
             const FeatRec fr = load_featrec(feats + at);
             Quad q;
             load_quad(fr, xo, av, q);
-            const bool edge = fr.edge != 0;
-            const int st = feature_fast(q, edge, P.dt, h, P.eps);
+            const int st = feature_fast(q, EDGE, P.dt, h, P.eps);
             if (st == FAST_DT_ONLY) {
                 ++n_cop;
                 double X[4][3];
                 positions_at<true>(q, P.dt, X);
-                const bool hit = edge ? edge_to_edge<false>(P, E, q, 0ull, X, h, P.dt) : point_to_tri<false>(P, E, q, 0ull, X, h, P.dt);
+                const bool hit = EDGE ? edge_to_edge<false>(P, E, q, 0ull, X, h, P.dt) : point_to_tri<false>(P, E, q, 0ull, X, h, P.dt);
                 if (hit) push_hit(hits, cap_hits, E.counters, fr, P.dt);
             } else if (st == FAST_UNCERTAIN) {
                 const int pos = atomicAdd(&s_n[w], 1);
@@ -530,13 +551,11 @@ k_feature(const FeatRec* __restrict__ feats, long long cap_feats, const Vec4* __
                 const FeatRec fr = load_featrec(feats + at);
                 Quad q;
                 load_quad(fr, xo, av, q);
-                double roots[3] = {-1, -1, -1};
                 ++n_exact;
-                if (is_coplanar<false>(q, P.dt, roots)) {
-                    ++n_cop;
-                    const double th = feature_first_hit<true>(P, E, q, fr.edge != 0, h, roots[0], roots[1], roots[2]);
-                    if (th >= 0) push_hit(hits, cap_hits, E.counters, fr, th);
-                }
+                bool cop;
+                const double th = exact_first_hit<EDGE>(P, E, q, cop);
+                if (cop) ++n_cop;
+                if (th >= 0) push_hit(hits, cap_hits, E.counters, fr, th);
             }
             nq = base;
             __syncwarp();
@@ -557,6 +576,7 @@ k_feature(const FeatRec* __restrict__ feats, long long cap_feats, const Vec4* __
 }
 
 // contact + impulse records of the hit list (the second half of k_contact, on a dense list)
+template <bool EDGE>
 __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS)
 k_emit(const HitRec* __restrict__ hits, long long cap_hits, const int2* __restrict__ pairs, const Vec4* __restrict__ xo,
        const Vec4* __restrict__ av, const uint8_t* __restrict__ vflags, const int* __restrict__ vbody, NarrowParams P, Emit E,
@@ -564,9 +584,9 @@ k_emit(const HitRec* __restrict__ hits, long long cap_hits, const int2* __restri
 {
     const long long n_pt = (long long)E.counters[CTR_HITS], n_ee = (long long)E.counters[CTR_HITS_EE];
     if (n_pt + n_ee > cap_hits) return;  // overflow: the host grows the list and repeats the pass
-    const long long n = n_pt + n_ee;
+    const long long n = EDGE ? n_ee : n_pt;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-        const long long at = t < n_pt ? t : cap_hits - 1 - (t - n_pt);
+        const long long at = EDGE ? cap_hits - 1 - t : t;
         const FeatRec fr = load_featrec(&hits[at].f);
         const double th = __ldg(reinterpret_cast<const double*>(hits + at) + 3);
         Quad q;
@@ -582,7 +602,7 @@ k_emit(const HitRec* __restrict__ hits, long long cap_hits, const int2* __restri
         const int2 pr = __ldg(pairs + pi);
         const unsigned long long key = ((unsigned long long)(unsigned)pr.x << 34) | ((unsigned long long)(unsigned)pr.y << 4) |
                                        (unsigned long long)f;
-        feature_emit<true>(P, E, q, key, fr.edge != 0, P.eps, th);
+        feature_emit<true>(P, E, q, key, EDGE, P.eps, th);
         atomicOr(pair_hit + (pi >> 5), 1u << (pi & 31));
     }
 }
@@ -1084,11 +1104,15 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
                                                                 c->feats.p, (long long)c->feats.n, c->counters.p, fused);
             mark(c, PH_CULL);
             if (fused) {
-                k_feature<<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E, c->hits.p,
-                                                                 (long long)c->hits.n);
+                k_feature<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E,
+                                                                        c->hits.p, (long long)c->hits.n);
+                k_feature<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E,
+                                                                       c->hits.p, (long long)c->hits.n);
                 mark(c, PH_ROOTS);
-                k_emit<<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p, c->vflags.p,
-                                                              c->vbody.p, P, E, c->pair_hit.p);
+                k_emit<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p,
+                                                                     c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+                k_emit<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p,
+                                                                    c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
             } else {
                 k_roots<<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P.dt, c->rootrecs.p,
                                                                (long long)c->rootrecs.n, c->counters.p);
@@ -1105,7 +1129,7 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
         }
         k_count_true<<<c->sm_count * 2, 256, 0, c->stream>>>(c->pair_hit.p, hit_words, c->counters.p);
         CK(cudaGetLastError());
-        c->launches += moving ? 4 : 3;
+        c->launches += moving ? (fused ? 6 : 4) : 3;
         mark(c, PH_CONTACT);
         CK(cudaMemcpyAsync(c->h_counters, c->counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));

@@ -203,6 +203,7 @@ CLSN_HD int feature_fast(const Quad& q, bool edge, double dt, double h, double e
     xmax += dt * vmax;
     if (!(vmax < 1e100 && xmax < 1e100)) return FAST_UNCERTAIN;
     const double delta = tol * vmax + 4.0 * CLSN_MACH_EPS * xmax;
+#pragma unroll 1
     for (int i = 0; i < nv; ++i) {
         double X[4][3];
 #pragma unroll
