@@ -46,6 +46,9 @@ __constant__ unsigned char c_feat_tt_static[15][4] = {
 __constant__ unsigned char c_feat_tb[5][4] = {{0, 1, 2, 3}, {0, 1, 2, 4}, {0, 1, 3, 4}, {1, 2, 3, 4}, {2, 0, 3, 4}};
 
 #define CULL_THREADS 128
+#ifndef NARROW_GRID_MULT
+#define NARROW_GRID_MULT 16  // grid-stride narrow-phase kernels: blocks per SM
+#endif
 #define FEAT_THREADS 128
 #ifndef FEAT_MIN_BLOCKS
 #define FEAT_MIN_BLOCKS 4
@@ -1084,7 +1087,7 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
         to.dirty = skip_clean ? c->dirty.p : nullptr;
         to.node_touched = prune ? c->flags.p : nullptr;
         if (q_hi > q_lo)
-            k_traverse<<<nblk(q_hi - q_lo, 128), 128, 0, c->stream>>>(c->nodes.p, c->lbox.p, c->leaf_elem.p, c->elem.p, N, q_lo, q_hi, to);
+            k_traverse<<<nblk(q_hi - q_lo, TRAV_THREADS), TRAV_THREADS, 0, c->stream>>>(c->nodes.p, c->lbox.p, c->leaf_elem.p, c->elem.p, N, q_lo, q_hi, to);
         c->launches += (q_hi > q_lo) ? 1 : 0;
         mark(c, PH_TRAVERSE);
         Emit E;
@@ -1095,7 +1098,7 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
         if ((size_t)c->pairs.n >= (1ull << 28)) return fail(c, CLSN_E_NOMEM, "more than 2^28 pairs in one pass");
         const long long hit_words = (long long)(c->pairs.n / 32 + 1);
         CK(cudaMemsetAsync(c->pair_hit.p, 0, (size_t)hit_words * sizeof(unsigned), c->stream));
-        const int grid = c->sm_count * 16;
+        const int grid = c->sm_count * NARROW_GRID_MULT;
         const bool fused = c->pipeline == 1;
         if (moving) {
             if (fused && c->hits.n == 0) CK(c->hits.reserve((size_t)4 * N + 1024));

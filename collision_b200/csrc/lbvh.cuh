@@ -267,7 +267,9 @@ struct TraverseOut {
                              // be dropped anyway).  `candidates` then counts only the pairs actually found.
 };
 
+#ifndef TRAV_THREADS
 #define TRAV_THREADS 128
+#endif
 #define TRAV_QCAP 96
 
 // Self-query.  Thread = one query leaf (sorted index i in [q_lo, q_hi)); finds leaves j > i whose exact
