@@ -53,6 +53,10 @@ __constant__ unsigned char c_feat_tb[5][4] = {{0, 1, 2, 3}, {0, 1, 2, 4}, {0, 1,
 #ifndef FEAT_MIN_BLOCKS
 #define FEAT_MIN_BLOCKS 4
 #endif
+#ifndef CULL_BATCHED
+#define CULL_BATCHED 1
+#endif
+#define CULL_KEEP_CAP 128  // per-warp buffer of kept features between slot reservations
 #define CULL_ROW 19  // doubles per staged pair row (18 used): odd stride -> conflict-free column access
 
 // Work-list records.  They carry the four point ids of the feature test so that the consumer's gathers
@@ -90,6 +94,18 @@ __device__ __forceinline__ FBox fbox_union(const FBox& a, const FBox& b)
 // 2e-3 * extent term covers the rounding of the test itself, including the barycentric coordinates of
 // nearly degenerate triangles (DESIGN.md "exact culls").
 // FP32 with directed rounding: the gap is rounded down, the margin up, so the cull stays conservative.
+#ifndef CULL_PAIR_MARGIN
+#define CULL_PAIR_MARGIN 0
+#endif
+// Variant with a per-pair margin (the extent of the two elements' boxes bounds the extent of every feature box of
+// the pair, so the margin is only larger, i.e. still conservative): 4 instead of 9 operations per axis and test.
+__device__ __forceinline__ bool boxes_far_m(const FBox& a, const FBox& b, const float* m)
+{
+    bool far = false;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) far = far || (__fsub_rd(a.lo[d], b.hi[d]) > m[d]) || (__fsub_rd(b.lo[d], a.hi[d]) > m[d]);
+    return far;
+}
 __device__ __forceinline__ bool boxes_far(const FBox& a, const FBox& b, float h2, float rel)
 {
     bool far = false;
@@ -121,6 +137,9 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
     __shared__ unsigned s_mask[CULL_THREADS];
     __shared__ int s_pref[CULL_THREADS];
     __shared__ int s_id[CULL_THREADS][7];
+#if CULL_BATCHED
+    __shared__ unsigned short s_keep[CULL_THREADS / 32][CULL_KEEP_CAP];
+#endif
     const int tid = threadIdx.x, lane = tid & 31, wb = tid & ~31;
     long long n_pairs = (long long)counters[CTR_PAIRS];
     if (n_pairs > cap_pairs) n_pairs = cap_pairs;
@@ -172,11 +191,20 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
                     eb[i] = fbox_union(pb[3 + i], pb[3 + (i + 1) % 3]);
                 }
                 const FBox ta = fbox_union(ea[0], pb[2]), tb = fbox_union(eb[0], pb[5]);
+#if CULL_PAIR_MARGIN
+                float pm[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+                    pm[d] = __fmaf_ru(rel, fmaxf(__fsub_ru(ta.hi[d], ta.lo[d]), __fsub_ru(tb.hi[d], tb.lo[d])), h2);
+#define CULL_FAR(a, b) boxes_far_m(a, b, pm)
+#else
+#define CULL_FAR(a, b) boxes_far(a, b, h2, rel)
+#endif
                 // point-triangle features 0..5 (order differs between proximity and CCD, see c_feat_tt_*)
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    const bool a_tri_b_pt = !boxes_far(ta, pb[3 + i], h2, rel);  // triangle a, vertex b_i
-                    const bool b_tri_a_pt = !boxes_far(tb, pb[i], h2, rel);      // triangle b, vertex a_i
+                    const bool a_tri_b_pt = !CULL_FAR(ta, pb[3 + i]);  // triangle a, vertex b_i
+                    const bool b_tri_a_pt = !CULL_FAR(tb, pb[i]);      // triangle b, vertex a_i
                     if (MOVING) {
                         mask |= (a_tri_b_pt ? 1u : 0u) << i;
                         mask |= (b_tri_a_pt ? 1u : 0u) << (3 + i);
@@ -189,7 +217,8 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
                 for (int i = 0; i < 3; ++i)
 #pragma unroll
                     for (int j = 0; j < 3; ++j)
-                        if (!boxes_far(ea[i], eb[j], h2, rel)) mask |= 1u << (6 + 3 * i + j);
+                        if (!CULL_FAR(ea[i], eb[j])) mask |= 1u << (6 + 3 * i + j);
+#undef CULL_FAR
             } else if (A.z >= 0) {
                 // triangle a, bond b: features 0,1 = vertex, 2..4 = tri edge x bond
                 const FBox ta = fbox_union(fbox_union(pb[0], pb[1]), pb[2]), bb = fbox_union(pb[3], pb[4]);
@@ -216,6 +245,117 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
         s_mask[tid] = mask;
         s_pref[tid] = incl - cnt;
         __syncwarp();
+#if CULL_BATCHED
+        // Features that stay are buffered per warp as 10-bit codes (pair row, feature, list end) and written out
+        // in batches: one slot reservation per list end and batch instead of one per round of 32 -- a
+        // same-address atomic is serialised at the L2 (~0.85 cycles per op chip-wide) and sits in every round's
+        // critical path otherwise.  Two list ends, so that the consumer's warps are homogeneous:
+        // proximity -> point-triangle | edge-edge (k_contact); CCD -> point-triangle | edge-edge (k_feature)
+        // or, for the staged pipeline, trig branch | other branches of the cubic (k_roots).
+        int nk = 0;
+        for (int k0 = 0; k0 < total; k0 += 32) {
+            const int k = k0 + lane;
+            bool keep = false;
+            unsigned code = 0;
+            if (k < total) {
+                // owner = last lane whose exclusive prefix is <= k
+                int o = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1)
+                    if (s_pref[wb + o + step] <= k) o += step;
+                const unsigned m = s_mask[wb + o];
+                const int f = __fns(m & 0x7fffu, 0, k - s_pref[wb + o] + 1);
+                const int type = (int)(m >> 16);
+                const bool edge = type == 0 ? f >= 6 : (type == 1 ? f >= 2 : true);
+                bool back = edge;
+                keep = true;
+                if (MOVING) {
+                    int sl[4];
+                    if (type == 0) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) sl[q] = c_feat_tt_moving[f][q];
+                    } else if (type == 1) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) sl[q] = c_feat_tb[f][q];
+                    } else {
+                        sl[0] = 0; sl[1] = 1; sl[2] = 3; sl[3] = 4;
+                    }
+                    Quad q;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            q.xo[i][d] = s_x[wb + o][3 * sl[i] + d];
+                            q.av[i][d] = s_v[MOVING ? wb + o : 0][3 * sl[i] + d];
+                        }
+                    double ca, cb, cc, cd;
+                    coplanar_coeffs(q, ca, cb, cc, cd);
+                    const int kindc = coplanar_maybe(ca, cb, cc, cd, P.dt);
+                    keep = kindc != 0;
+                    if (!split_by_kind) back = kindc == 2;
+                }
+                code = ((unsigned)o << 5) | ((unsigned)f << 1) | (back ? 1u : 0u);
+            }
+            const unsigned kb = __ballot_sync(0xffffffffu, keep);
+            if (keep) s_keep[tid >> 5][nk + __popc(kb & ((1u << lane) - 1u))] = (unsigned short)code;
+            nk += __popc(kb);
+            __syncwarp();
+            if (nk > CULL_KEEP_CAP - 32 || k0 + 32 >= total) {
+                int nb = 0;
+                for (int e = lane; e < nk; e += 32) nb += s_keep[tid >> 5][e] & 1;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) nb += __shfl_xor_sync(0xffffffffu, nb, o);
+                const int nf = nk - nb;
+                unsigned long long base_f = 0, base_b = 0;
+                if (lane == 0) {
+                    if (nf) base_f = atomicAdd(&counters[CTR_FEATS], (unsigned long long)nf);
+                    if (nb) base_b = atomicAdd(&counters[CTR_FEATS_EE], (unsigned long long)nb);
+                }
+                base_f = __shfl_sync(0xffffffffu, base_f, 0);
+                base_b = __shfl_sync(0xffffffffu, base_b, 0);
+                int run_f = 0, run_b = 0;
+                for (int e0 = 0; e0 < nk; e0 += 32) {
+                    const int e = e0 + lane;
+                    const bool valid = e < nk;
+                    const unsigned cde = valid ? s_keep[tid >> 5][e] : 0u;
+                    const bool isb = valid && (cde & 1u);
+                    const unsigned bb = __ballot_sync(0xffffffffu, isb), fb = __ballot_sync(0xffffffffu, valid && !isb);
+                    if (valid) {
+                        const int o = (int)(cde >> 5), f = (int)((cde >> 1) & 15u);
+                        const int type = (int)(s_mask[wb + o] >> 16);
+                        int sl[4];
+                        unsigned edge;
+                        if (type == 0) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) sl[q] = MOVING ? c_feat_tt_moving[f][q] : c_feat_tt_static[f][q];
+                            edge = f >= 6;
+                        } else if (type == 1) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) sl[q] = c_feat_tb[f][q];
+                            edge = f >= 2;
+                        } else {
+                            sl[0] = 0; sl[1] = 1; sl[2] = 3; sl[3] = 4;
+                            edge = 1;
+                        }
+                        const unsigned lt = (1u << lane) - 1u;
+                        const long long slot = isb ? (long long)base_b + run_b + __popc(bb & lt) : (long long)base_f + run_f + __popc(fb & lt);
+                        if (slot < cap_feats) {
+                            uint2* dst = reinterpret_cast<uint2*>(feats + (isb ? cap_feats - 1 - slot : slot));
+                            dst[0] = make_uint2((unsigned)(base + wb + o) | ((unsigned)f << 28), (unsigned)s_id[wb + o][sl[0]]);
+                            dst[1] = make_uint2((unsigned)s_id[wb + o][sl[1]], (unsigned)s_id[wb + o][sl[2]]);
+                            dst[2] = make_uint2((unsigned)s_id[wb + o][sl[3]], edge);
+                        }
+                    }
+                    run_f += __popc(fb);
+                    run_b += __popc(bb);
+                }
+                nk = 0;
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+    }
+#else
         for (int k0 = 0; k0 < total; k0 += 32) {
             const int k = k0 + lane;
             bool keep = false, back = false;  // back: list end (CCD: non-trig cubic branches; proximity: edge-edge)
@@ -288,6 +428,7 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
         }
         __syncwarp();
     }
+#endif
     for (int o = 16; o > 0; o >>= 1) n_box += __shfl_xor_sync(0xffffffffu, n_box, o);
     if (lane == 0 && n_box) atomicAdd(&counters[CTR_BOXSURV], n_box);
 }
@@ -328,8 +469,8 @@ k_roots(const FeatRec* __restrict__ feats, long long cap_feats, const Vec4* __re
         const bool ee = fr.edge != 0;
         // reserve() aggregates the converged lanes onto ONE counter, so the two kinds reserve separately
         long long slot = 0;
-        if (ee) slot = (long long)reserve(&counters[CTR_ROOTS_EE], 1);
-        else slot = (long long)reserve(&counters[CTR_ROOTS], 1);
+        if (ee) slot = (long long)reserve1(&counters[CTR_ROOTS_EE]);
+        else slot = (long long)reserve1(&counters[CTR_ROOTS]);
         if (slot < cap_out) {
             RootRec* dst = ee ? out + (cap_out - 1 - slot) : out + slot;
             uint2* o = reinterpret_cast<uint2*>(dst);
@@ -475,8 +616,8 @@ __device__ __forceinline__ void push_hit(HitRec* __restrict__ hits, long long ca
 {
     const bool ee = fr.edge != 0;
     long long slot;
-    if (ee) slot = (long long)reserve(&counters[CTR_HITS_EE], 1);
-    else slot = (long long)reserve(&counters[CTR_HITS], 1);
+    if (ee) slot = (long long)reserve1(&counters[CTR_HITS_EE]);
+    else slot = (long long)reserve1(&counters[CTR_HITS]);
     if (slot < cap_hits) {
         HitRec* dst = ee ? hits + (cap_hits - 1 - slot) : hits + slot;
         uint2* o = reinterpret_cast<uint2*>(dst);
@@ -490,7 +631,7 @@ __device__ __forceinline__ void push_hit(HitRec* __restrict__ hits, long long ca
 // correctly rounded solve + the reference's walk over the roots: the cold path of k_feature, kept out of line so
 // that the hot loop's instruction footprint stays small
 template <bool EDGE>
-__device__ __noinline__ double exact_first_hit(const NarrowParams& P, const Emit& E, const Quad& q, bool& coplanar)
+__device__ __forceinline__ double exact_first_hit_inl(const NarrowParams& P, const Emit& E, const Quad& q, bool& coplanar)
 {
     double roots[3] = {-1, -1, -1};
     coplanar = is_coplanar<false>(q, P.dt, roots);
@@ -505,6 +646,88 @@ __device__ __noinline__ double exact_first_hit(const NarrowParams& P, const Emit
         if (hit) return t;
     }
     return -1.0;
+}
+
+template <bool EDGE>
+__device__ __noinline__ double exact_first_hit(const NarrowParams& P, const Emit& E, const Quad& q, bool& coplanar)
+{
+    return exact_first_hit_inl<EDGE>(P, E, q, coplanar);
+}
+
+// Pipeline 2: the same work as k_feature in two lean kernels.  k_fast runs the plain-FP64 fast path (and the
+// static test at t = dt for the features it settles) and appends the undecided features to a list; k_exact
+// solves those correctly rounded.  Neither carries the other's code or registers.
+#ifndef FAST_MIN_BLOCKS
+#define FAST_MIN_BLOCKS 4
+#endif
+#ifndef EXACT_MIN_BLOCKS
+#define EXACT_MIN_BLOCKS 4
+#endif
+template <bool EDGE>
+__global__ void __launch_bounds__(FEAT_THREADS, FAST_MIN_BLOCKS)
+k_fast(const FeatRec* __restrict__ feats, long long cap_feats, const Vec4* __restrict__ xo, const Vec4* __restrict__ av,
+       NarrowParams P, Emit E, HitRec* __restrict__ hits, long long cap_hits, FeatRec* __restrict__ unc, long long cap_unc)
+{
+    const int lane = threadIdx.x & 31;
+    const long long n_pt = (long long)E.counters[CTR_FEATS], n_ee = (long long)E.counters[CTR_FEATS_EE];
+    if (n_pt + n_ee > cap_feats) return;  // overflow: the host grows the list and repeats the pass
+    const long long n = EDGE ? n_ee : n_pt;
+    unsigned long long n_cop = 0;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const long long at = EDGE ? cap_feats - 1 - t : t;
+        const FeatRec fr = load_featrec(feats + at);
+        Quad q;
+        load_quad(fr, xo, av, q);
+        const int st = feature_fast(q, EDGE, P.dt, P.eps, P.eps);
+        if (st == FAST_DT_ONLY) {
+            ++n_cop;
+            double X[4][3];
+            positions_at<true>(q, P.dt, X);
+            const bool hit = EDGE ? edge_to_edge<false>(P, E, q, 0ull, X, P.eps, P.dt) : point_to_tri<false>(P, E, q, 0ull, X, P.eps, P.dt);
+            if (hit) push_hit(hits, cap_hits, E.counters, fr, P.dt);
+        } else if (st == FAST_UNCERTAIN) {
+            const long long slot = (long long)reserve1(&E.counters[EDGE ? CTR_UNC_EE : CTR_UNC]);
+            if (slot < cap_unc) {
+                uint2* o = reinterpret_cast<uint2*>(unc + (EDGE ? cap_unc - 1 - slot : slot));
+                o[0] = make_uint2(fr.entry, (unsigned)fr.id[0]);
+                o[1] = make_uint2((unsigned)fr.id[1], (unsigned)fr.id[2]);
+                o[2] = make_uint2((unsigned)fr.id[3], fr.edge);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) n_cop += __shfl_xor_sync(0xffffffffu, n_cop, o);
+    if (lane == 0 && n_cop) atomicAdd(&E.counters[CTR_ROOTS], n_cop);
+}
+
+template <bool EDGE>
+__global__ void __launch_bounds__(FEAT_THREADS, EXACT_MIN_BLOCKS)
+k_exact(const FeatRec* __restrict__ unc, long long cap_unc, const Vec4* __restrict__ xo, const Vec4* __restrict__ av, NarrowParams P,
+        Emit E, HitRec* __restrict__ hits, long long cap_hits)
+{
+    const int lane = threadIdx.x & 31;
+    const long long n_pt = (long long)E.counters[CTR_UNC], n_ee = (long long)E.counters[CTR_UNC_EE];
+    if (n_pt + n_ee > cap_unc) return;  // overflow: the host grows the list and repeats the pass
+    const long long n = EDGE ? n_ee : n_pt;
+    unsigned long long n_cop = 0, n_exact = 0;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const long long at = EDGE ? cap_unc - 1 - t : t;
+        const FeatRec fr = load_featrec(unc + at);
+        Quad q;
+        load_quad(fr, xo, av, q);
+        ++n_exact;
+        bool cop;
+        const double th = exact_first_hit_inl<EDGE>(P, E, q, cop);
+        if (cop) ++n_cop;
+        if (th >= 0) push_hit(hits, cap_hits, E.counters, fr, th);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        n_cop += __shfl_xor_sync(0xffffffffu, n_cop, o);
+        n_exact += __shfl_xor_sync(0xffffffffu, n_exact, o);
+    }
+    if (lane == 0) {
+        if (n_cop) atomicAdd(&E.counters[CTR_ROOTS], n_cop);
+        if (n_exact) atomicAdd(&E.counters[CTR_EXACT], n_exact);
+    }
 }
 
 // EDGE = false: the point-triangle entries (front of the work list); EDGE = true: the edge-edge entries (back).
@@ -693,7 +916,8 @@ struct clsn_ctx {
     DevBuf<unsigned> pair_hit;
     DevBuf<RootRec> rootrecs;
     DevBuf<HitRec> hits;
-    int pipeline = 0;           // 1 = fused CCD feature kernel (k_feature + k_emit), 0 = staged (k_roots + k_contact)
+    DevBuf<FeatRec> unc;        // pipeline 2: features the fast path could not settle
+    int pipeline = 0;           // 0 = staged (k_roots + k_contact), 1 = fused CCD feature kernel (k_feature + k_emit), 2 = k_fast + k_exact + k_emit
     DevBuf<PointRec> prec, prec_sorted;
     DevBuf<BodyRec> brec;
     DevBuf<Contact> contacts;
@@ -781,7 +1005,10 @@ extern "C" int clsn_create(clsn_ctx** out, int device)
     p.eps = 1e-6; p.thickness = 1e-4; p.dt = 1e-3; p.k = 1000; p.m = 0.01; p.lambda = 0.02; p.cr = 0.0;
     for (int i = 0; i < 3; ++i) { p.lo[i] = -1e30; p.hi[i] = 1e30; }
     c->prm = p;
-    if (const char* e = getenv("CLSN_PIPELINE")) c->pipeline = atoi(e) == 0 ? 0 : 1;
+    if (const char* e = getenv("CLSN_PIPELINE")) {
+        const int v = atoi(e);
+        if (v >= 0 && v <= 2) c->pipeline = v;
+    }
     *out = c;
     return CLSN_OK;
 }
@@ -795,7 +1022,7 @@ extern "C" void clsn_destroy(clsn_ctx* c)
     c->xo.release(); c->xn.release(); c->av.release(); c->has.release(); c->dirty.release(); c->imp_rg.release(); c->cnt_rg.release();
     c->stage.release(); c->code.release(); c->code_sorted.release(); c->idx.release(); c->leaf_elem.release();
     c->leaf_parent.release(); c->flags.release(); c->nodes.release(); c->lbox.release(); c->bounds.release();
-    c->cub_tmp.release(); c->pairs.release(); c->dbg_cand.release(); c->feats.release(); c->pair_hit.release(); c->rootrecs.release(); c->hits.release(); c->prec.release(); c->prec_sorted.release(); c->brec.release();
+    c->cub_tmp.release(); c->pairs.release(); c->dbg_cand.release(); c->feats.release(); c->pair_hit.release(); c->rootrecs.release(); c->hits.release(); c->unc.release(); c->prec.release(); c->prec_sorted.release(); c->brec.release();
     c->contacts.release(); c->cnt.release(); c->offs.release(); c->fill.release(); c->perm.release();
     c->perm_sorted.release(); c->skey.release(); c->counters.release(); c->acc_imp.release(); c->acc_fric.release();
     c->rigid.release(); c->zone_lists.release(); c->strain.release();
@@ -847,7 +1074,7 @@ extern "C" int clsn_set_exact_stats(clsn_ctx* c, int on)
 
 extern "C" int clsn_set_pipeline(clsn_ctx* c, int pipeline)
 {
-    if (!c || (pipeline != 0 && pipeline != 1)) return CLSN_E_ARG;
+    if (!c || pipeline < 0 || pipeline > 2) return CLSN_E_ARG;
     c->pipeline = pipeline;
     return CLSN_OK;
 }
@@ -918,7 +1145,7 @@ extern "C" int clsn_set_topology(clsn_ctx* c, int V, int T, const int32_t* tri_i
     if (c->pairs.n == 0) CK(c->pairs.reserve((size_t)16 * n1 + 1024));
     if (c->feats.n == 0) CK(c->feats.reserve((size_t)64 * n1 + 1024));
     if (c->pipeline == 0 && c->rootrecs.n == 0) CK(c->rootrecs.reserve((size_t)16 * n1 + 1024));
-    if (c->pipeline == 1 && c->hits.n == 0) CK(c->hits.reserve((size_t)4 * n1 + 1024));
+    if (c->pipeline >= 1 && c->hits.n == 0) CK(c->hits.reserve((size_t)4 * n1 + 1024));
     CK(c->pair_hit.reserve(c->pairs.n / 32 + 2));
     if (c->prec.n == 0) CK(c->prec.reserve((size_t)8 * n1 + 1024));
     CK(c->perm.reserve(c->prec.n)); CK(c->perm_sorted.reserve(c->prec.n)); CK(c->skey.reserve(c->prec.n));
@@ -1099,14 +1326,30 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
         const long long hit_words = (long long)(c->pairs.n / 32 + 1);
         CK(cudaMemsetAsync(c->pair_hit.p, 0, (size_t)hit_words * sizeof(unsigned), c->stream));
         const int grid = c->sm_count * NARROW_GRID_MULT;
-        const bool fused = c->pipeline == 1;
+        const bool fused = c->pipeline >= 1;
+        const bool split = c->pipeline == 2;
         if (moving) {
             if (fused && c->hits.n == 0) CK(c->hits.reserve((size_t)4 * N + 1024));
+            if (split && c->unc.n == 0) CK(c->unc.reserve((size_t)4 * N + 1024));
             if (!fused && c->rootrecs.n == 0) CK(c->rootrecs.reserve((size_t)16 * N + 1024));
             k_cull<true><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p, P,
                                                                 c->feats.p, (long long)c->feats.n, c->counters.p, fused);
             mark(c, PH_CULL);
-            if (fused) {
+            if (split) {
+                k_fast<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E, c->hits.p,
+                                                                     (long long)c->hits.n, c->unc.p, (long long)c->unc.n);
+                k_fast<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E, c->hits.p,
+                                                                    (long long)c->hits.n, c->unc.p, (long long)c->unc.n);
+                k_exact<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->unc.p, (long long)c->unc.n, c->xo.p, c->av.p, P, E, c->hits.p,
+                                                                      (long long)c->hits.n);
+                k_exact<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->unc.p, (long long)c->unc.n, c->xo.p, c->av.p, P, E, c->hits.p,
+                                                                     (long long)c->hits.n);
+                mark(c, PH_ROOTS);
+                k_emit<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p,
+                                                                     c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+                k_emit<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p,
+                                                                    c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+            } else if (fused) {
                 k_feature<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E,
                                                                         c->hits.p, (long long)c->hits.n);
                 k_feature<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E,
@@ -1132,7 +1375,7 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
         }
         k_count_true<<<c->sm_count * 2, 256, 0, c->stream>>>(c->pair_hit.p, hit_words, c->counters.p);
         CK(cudaGetLastError());
-        c->launches += moving ? (fused ? 6 : 4) : 3;
+        c->launches += moving ? (split ? 8 : (fused ? 6 : 4)) : 3;
         mark(c, PH_CONTACT);
         CK(cudaMemcpyAsync(c->h_counters, c->counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
@@ -1149,6 +1392,10 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
         }
         if (!fused && h[CTR_ROOTS] + h[CTR_ROOTS_EE] > c->rootrecs.n) {
             CK(c->rootrecs.reserve((size_t)((h[CTR_ROOTS] + h[CTR_ROOTS_EE]) * 5 / 4 + 1024)));
+            redo = true;
+        }
+        if (split && moving && h[CTR_UNC] + h[CTR_UNC_EE] > c->unc.n) {
+            CK(c->unc.reserve((size_t)((h[CTR_UNC] + h[CTR_UNC_EE]) * 5 / 4 + 1024)));
             redo = true;
         }
         if (fused && moving && h[CTR_HITS] + h[CTR_HITS_EE] > c->hits.n) {

@@ -13,6 +13,15 @@
 
 namespace clsn {
 
+// Two tuning variants, measured on the B200 against each other (tools/ab_bench.py); the default is the faster one.
+#ifndef CLSN_SCATTER_V2
+#define CLSN_SCATTER_V2 0
+#endif
+#ifndef CLSN_REDUCE_V2
+#define CLSN_REDUCE_V2 0
+#endif
+
+#if CLSN_SCATTER_V2
 // records -> per-point slots.  fill[] must be zero.
 __global__ void k_scatter(const PointRec* __restrict__ rec, const unsigned long long* __restrict__ n_rec_ptr,
                           long long cap, const int* __restrict__ offs, int* fill, int* __restrict__ perm,
@@ -49,6 +58,25 @@ __global__ void k_scatter(const PointRec* __restrict__ rec, const unsigned long 
         }
     }
 }
+
+#else
+// records -> per-point slots.  fill[] must be zero.
+__global__ void k_scatter(const PointRec* __restrict__ rec, const unsigned long long* __restrict__ n_rec_ptr,
+                          long long cap, const int* __restrict__ offs, int* fill, int* __restrict__ perm,
+                          unsigned long long* __restrict__ skey)
+{
+    long long n = (long long)*n_rec_ptr;
+    if (n > cap) n = cap;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        const ulonglong2 h = *reinterpret_cast<const ulonglong2*>(rec + r);
+        const int p = (int)(unsigned)h.y;
+        const int slot = offs[p] + atomicAdd(fill + p, 1);
+        perm[slot] = (int)r;
+        skey[slot] = h.x;
+    }
+}
+
+#endif
 
 // per-point / per-body record counts of an externally gathered record set (multi-GPU import)
 __global__ void k_count_records(const PointRec* __restrict__ prec, long long nprec, const BodyRec* __restrict__ brec,
@@ -102,6 +130,7 @@ __global__ void k_owner_scatter(const PointRec* __restrict__ rec, long long n, i
     }
 }
 
+#if CLSN_REDUCE_V2
 // One warp per point.  Rank the point's keys (all-pairs compare, keys are unique), bring the
 // records into rank order, then lanes 0..5 each sum one of imp.xyz / fric.xyz sequentially.
 // mode 0: apply to avgVel (updateAverageVelocity :707-724); mode 1: write the sums to acc arrays.
@@ -178,6 +207,57 @@ k_reduce_points(const PointRec* __restrict__ rec, const int* __restrict__ offs, 
         __syncwarp();
     }
 }
+
+#else
+// One warp per point.  Rank the point's keys (all-pairs compare, keys are unique), store the
+// records in rank order, then lanes 0..5 each sum one of imp.xyz / fric.xyz sequentially.
+// mode 0: apply to avgVel (updateAverageVelocity :707-724); mode 1: write the sums to acc arrays.
+__global__ void __launch_bounds__(256)
+k_reduce_points(const PointRec* __restrict__ rec, const int* __restrict__ offs, const int* __restrict__ cnt, int V,
+                const int* __restrict__ perm, int* __restrict__ perm_sorted, const unsigned long long* __restrict__ skey,
+                const uint8_t* __restrict__ vflags, Vec4* av, uint8_t* has, uint8_t* dirty, int mode, double* __restrict__ acc_imp,
+                double* __restrict__ acc_fric, unsigned long long* counters)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int p = blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < V; p += gridDim.x * warps_per_block) {
+        const int n = cnt[p];
+        if (n == 0) continue;
+        const int base = offs[p];
+        // rank = number of smaller keys
+        for (int t = lane; t < n; t += 32) {
+            const unsigned long long k = skey[base + t];
+            int rank = 0;
+            for (int u = 0; u < n; ++u) rank += skey[base + u] < k ? 1 : 0;
+            perm_sorted[base + rank] = perm[base + t];
+        }
+        __syncwarp();
+        double sum = 0.0;
+        if (lane < 6) {
+            for (int t = 0; t < n; ++t) {
+                const int r = perm_sorted[base + t];
+                const double* val = reinterpret_cast<const double*>(rec + r) + 2;  // imp[3], fric[3]
+                sum += val[lane];
+            }
+        }
+        const double fr = __shfl_down_sync(0xffffffffu, sum, 3);  // lanes 0..2 get fric.xyz
+        if (mode == 0) {
+            if (lane < 3 && !(vflags[p] & 1)) {
+                double* a = reinterpret_cast<double*>(av + p) + lane;
+                const double v = *a + (sum + fr) / n;
+                *a = v;
+                if (isinf(v) || isnan(v)) atomicAdd(&counters[CTR_ERROR], 1ull);
+                if (lane == 0) { has[p] = 1; dirty[p] = 1; }
+            }
+        } else if (lane < 6) {
+            if (lane < 3) acc_imp[3 * (size_t)p + lane] = sum;
+            else acc_fric[3 * (size_t)p + lane - 3] = sum;
+        }
+        __syncwarp();
+    }
+}
+
+#endif
 
 // Rigid-rigid contacts: per-body sums in key order.  One thread per body; records are few.
 // imp_rg accumulates across passes and steps -- the reference never zeroes collsnImpulse_RG

@@ -200,11 +200,12 @@ int clsn_set_debug(clsn_ctx*, int record_candidates, int record_contacts);
  * that `candidates` equals the reference's callback count in every pass (results are identical). */
 int clsn_set_exact_stats(clsn_ctx*, int on);
 /* CCD narrow phase of MovingPointToTri / MovingEdgeToEdge (dcollid3d.cpp:327-369) after the cull.
- * 1 (default): fused -- one kernel settles every feature the plain-FP64 fast path can prove to miss at all
- * of its roots (outcome = the static test at t = dt) and runs the correctly rounded cubic solve only for the
- * rest; a second kernel emits the records of the hit list.  0: staged -- correctly rounded solve of every
- * feature, then the static tests (the round-1 pipeline, kept for A/B measurements).  Results are bit-identical.
- * The environment variable CLSN_PIPELINE=0|1 sets the default of new contexts. */
+ * 0: staged -- correctly rounded solve of every feature (k_roots), then the static tests and the records
+ * (k_contact).  1 / 2: a plain-FP64 fast path first settles every feature it can prove to miss at all of its
+ * roots (outcome = the static test at t = dt) and only the rest gets the correctly rounded solve -- in one
+ * fused kernel (1) or as two lean kernels (2); a last kernel emits the records of the hit list.
+ * Results are bit-identical; which one is the default is a measured choice.
+ * The environment variable CLSN_PIPELINE=0|1|2 sets the default of new contexts. */
 int clsn_set_pipeline(clsn_ctx*, int pipeline);
 int64_t clsn_num_candidates(clsn_ctx*);
 int clsn_get_candidates(clsn_ctx*, int32_t* pairs /* 2 per pair, unsorted */);

@@ -24,6 +24,15 @@ VARIANTS = {
     "g32": ["-DNARROW_GRID_MULT=32"],
     "t64": ["-DTRAV_THREADS=64"],
     "t256": ["-DTRAV_THREADS=256"],
+    "s2": ["-DCLSN_SCATTER_V2=1"],
+    "r2": ["-DCLSN_REDUCE_V2=1"],
+    "cb0": ["-DCULL_BATCHED=0"],
+    "c5cb0": ["-DCULL_BATCHED=0", "-DCULL_MIN_BLOCKS=5"],
+    "fa5": ["-DFAST_MIN_BLOCKS=5"],
+    "fa3": ["-DFAST_MIN_BLOCKS=3"],
+    "ex5": ["-DEXACT_MIN_BLOCKS=5"],
+    "r5": ["-DROOTS_MIN_BLOCKS=6"],
+    "pm": ["-DCULL_PAIR_MARGIN=1"],
 }
 
 
