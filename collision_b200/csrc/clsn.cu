@@ -45,6 +45,34 @@ __constant__ unsigned char c_feat_tt_static[15][4] = {
 // tri (a) - bond (b = slots 3,4) (TriToBond :508-530, MovingTriToBond :219-241)
 __constant__ unsigned char c_feat_tb[5][4] = {{0, 1, 2, 3}, {0, 1, 2, 4}, {0, 1, 3, 4}, {1, 2, 3, 4}, {2, 0, 3, 4}};
 
+// The same tables computed arithmetically: a lane-varying index into __constant__ memory is replayed once per
+// distinct address in the warp, these few integer operations are not.  type 0 tri-tri, 1 tri-bond, 2 bond-bond.
+// (tests/test_host_cpu.py checks this function against the tables above.)
+template <bool MOVING>
+__host__ __device__ __forceinline__ void feature_slots(int type, int f, int sl[4])
+{
+    if (type == 0) {
+        if (f < 6) {
+            const bool tri_a = MOVING ? f < 3 : f >= 3;   // whose triangle; the vertex comes from the other element
+            const int v = f < 3 ? f : f - 3;
+            const int t0 = tri_a ? 0 : 3;
+            sl[0] = t0; sl[1] = t0 + 1; sl[2] = t0 + 2; sl[3] = (tri_a ? 3 : 0) + v;
+        } else {
+            const int e = f - 6, i = e / 3, j = e - 3 * i;
+            sl[0] = i; sl[1] = i == 2 ? 0 : i + 1; sl[2] = 3 + j; sl[3] = j == 2 ? 3 : 4 + j;
+        }
+    } else if (type == 1) {
+        if (f < 2) {
+            sl[0] = 0; sl[1] = 1; sl[2] = 2; sl[3] = 3 + f;
+        } else {
+            const int i = f - 2;
+            sl[0] = i; sl[1] = i == 2 ? 0 : i + 1; sl[2] = 3; sl[3] = 4;
+        }
+    } else {
+        sl[0] = 0; sl[1] = 1; sl[2] = 3; sl[3] = 4;
+    }
+}
+
 #define CULL_THREADS 128
 #ifndef NARROW_GRID_MULT
 #define NARROW_GRID_MULT 16  // grid-stride narrow-phase kernels: blocks per SM
@@ -52,9 +80,6 @@ __constant__ unsigned char c_feat_tb[5][4] = {{0, 1, 2, 3}, {0, 1, 2, 4}, {0, 1,
 #define FEAT_THREADS 128
 #ifndef FEAT_MIN_BLOCKS
 #define FEAT_MIN_BLOCKS 4
-#endif
-#ifndef CULL_BATCHED
-#define CULL_BATCHED 1
 #endif
 #define CULL_KEEP_CAP 128  // per-warp buffer of kept features between slot reservations
 #define CULL_ROW 19  // doubles per staged pair row (18 used): odd stride -> conflict-free column access
@@ -94,18 +119,6 @@ __device__ __forceinline__ FBox fbox_union(const FBox& a, const FBox& b)
 // 2e-3 * extent term covers the rounding of the test itself, including the barycentric coordinates of
 // nearly degenerate triangles (DESIGN.md "exact culls").
 // FP32 with directed rounding: the gap is rounded down, the margin up, so the cull stays conservative.
-#ifndef CULL_PAIR_MARGIN
-#define CULL_PAIR_MARGIN 0
-#endif
-// Variant with a per-pair margin (the extent of the two elements' boxes bounds the extent of every feature box of
-// the pair, so the margin is only larger, i.e. still conservative): 4 instead of 9 operations per axis and test.
-__device__ __forceinline__ bool boxes_far_m(const FBox& a, const FBox& b, const float* m)
-{
-    bool far = false;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) far = far || (__fsub_rd(a.lo[d], b.hi[d]) > m[d]) || (__fsub_rd(b.lo[d], a.hi[d]) > m[d]);
-    return far;
-}
 __device__ __forceinline__ bool boxes_far(const FBox& a, const FBox& b, float h2, float rel)
 {
     bool far = false;
@@ -137,9 +150,7 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
     __shared__ unsigned s_mask[CULL_THREADS];
     __shared__ int s_pref[CULL_THREADS];
     __shared__ int s_id[CULL_THREADS][7];
-#if CULL_BATCHED
     __shared__ unsigned short s_keep[CULL_THREADS / 32][CULL_KEEP_CAP];
-#endif
     const int tid = threadIdx.x, lane = tid & 31, wb = tid & ~31;
     long long n_pairs = (long long)counters[CTR_PAIRS];
     if (n_pairs > cap_pairs) n_pairs = cap_pairs;
@@ -191,20 +202,11 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
                     eb[i] = fbox_union(pb[3 + i], pb[3 + (i + 1) % 3]);
                 }
                 const FBox ta = fbox_union(ea[0], pb[2]), tb = fbox_union(eb[0], pb[5]);
-#if CULL_PAIR_MARGIN
-                float pm[3];
-#pragma unroll
-                for (int d = 0; d < 3; ++d)
-                    pm[d] = __fmaf_ru(rel, fmaxf(__fsub_ru(ta.hi[d], ta.lo[d]), __fsub_ru(tb.hi[d], tb.lo[d])), h2);
-#define CULL_FAR(a, b) boxes_far_m(a, b, pm)
-#else
-#define CULL_FAR(a, b) boxes_far(a, b, h2, rel)
-#endif
                 // point-triangle features 0..5 (order differs between proximity and CCD, see c_feat_tt_*)
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    const bool a_tri_b_pt = !CULL_FAR(ta, pb[3 + i]);  // triangle a, vertex b_i
-                    const bool b_tri_a_pt = !CULL_FAR(tb, pb[i]);      // triangle b, vertex a_i
+                    const bool a_tri_b_pt = !boxes_far(ta, pb[3 + i], h2, rel);  // triangle a, vertex b_i
+                    const bool b_tri_a_pt = !boxes_far(tb, pb[i], h2, rel);      // triangle b, vertex a_i
                     if (MOVING) {
                         mask |= (a_tri_b_pt ? 1u : 0u) << i;
                         mask |= (b_tri_a_pt ? 1u : 0u) << (3 + i);
@@ -217,8 +219,7 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
                 for (int i = 0; i < 3; ++i)
 #pragma unroll
                     for (int j = 0; j < 3; ++j)
-                        if (!CULL_FAR(ea[i], eb[j])) mask |= 1u << (6 + 3 * i + j);
-#undef CULL_FAR
+                        if (!boxes_far(ea[i], eb[j], h2, rel)) mask |= 1u << (6 + 3 * i + j);
             } else if (A.z >= 0) {
                 // triangle a, bond b: features 0,1 = vertex, 2..4 = tri edge x bond
                 const FBox ta = fbox_union(fbox_union(pb[0], pb[1]), pb[2]), bb = fbox_union(pb[3], pb[4]);
@@ -245,12 +246,11 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
         s_mask[tid] = mask;
         s_pref[tid] = incl - cnt;
         __syncwarp();
-#if CULL_BATCHED
         // Features that stay are buffered per warp as 10-bit codes (pair row, feature, list end) and written out
         // in batches: one slot reservation per list end and batch instead of one per round of 32 -- a
         // same-address atomic is serialised at the L2 (~0.85 cycles per op chip-wide) and sits in every round's
         // critical path otherwise.  Two list ends, so that the consumer's warps are homogeneous:
-        // proximity -> point-triangle | edge-edge (k_contact); CCD -> point-triangle | edge-edge (k_feature)
+        // proximity -> point-triangle | edge-edge (k_contact); CCD -> point-triangle | edge-edge (k_fast)
         // or, for the staged pipeline, trig branch | other branches of the cubic (k_roots).
         int nk = 0;
         for (int k0 = 0; k0 < total; k0 += 32) {
@@ -271,15 +271,7 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
                 keep = true;
                 if (MOVING) {
                     int sl[4];
-                    if (type == 0) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) sl[q] = c_feat_tt_moving[f][q];
-                    } else if (type == 1) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) sl[q] = c_feat_tb[f][q];
-                    } else {
-                        sl[0] = 0; sl[1] = 1; sl[2] = 3; sl[3] = 4;
-                    }
+                    feature_slots<true>(type, f, sl);
                     Quad q;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
@@ -324,19 +316,8 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
                         const int o = (int)(cde >> 5), f = (int)((cde >> 1) & 15u);
                         const int type = (int)(s_mask[wb + o] >> 16);
                         int sl[4];
-                        unsigned edge;
-                        if (type == 0) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) sl[q] = MOVING ? c_feat_tt_moving[f][q] : c_feat_tt_static[f][q];
-                            edge = f >= 6;
-                        } else if (type == 1) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) sl[q] = c_feat_tb[f][q];
-                            edge = f >= 2;
-                        } else {
-                            sl[0] = 0; sl[1] = 1; sl[2] = 3; sl[3] = 4;
-                            edge = 1;
-                        }
+                        feature_slots<MOVING>(type, f, sl);
+                        const unsigned edge = type == 0 ? f >= 6 : (type == 1 ? f >= 2 : 1);
                         const unsigned lt = (1u << lane) - 1u;
                         const long long slot = isb ? (long long)base_b + run_b + __popc(bb & lt) : (long long)base_f + run_f + __popc(fb & lt);
                         if (slot < cap_feats) {
@@ -355,80 +336,6 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
         }
         __syncwarp();
     }
-#else
-        for (int k0 = 0; k0 < total; k0 += 32) {
-            const int k = k0 + lane;
-            bool keep = false, back = false;  // back: list end (CCD: non-trig cubic branches; proximity: edge-edge)
-            FeatRec rec;
-            rec.entry = 0; rec.edge = 0;
-            rec.id[0] = rec.id[1] = rec.id[2] = rec.id[3] = 0;
-            if (k < total) {
-                // owner = last lane whose exclusive prefix is <= k
-                int o = 0;
-#pragma unroll
-                for (int step = 16; step > 0; step >>= 1)
-                    if (s_pref[wb + o + step] <= k) o += step;
-                const unsigned m = s_mask[wb + o];
-                const int f = __fns(m & 0x7fffu, 0, k - s_pref[wb + o] + 1);
-                rec.entry = (unsigned)(base + wb + o) | ((unsigned)f << 28);
-                keep = true;
-                const int type = (int)(m >> 16);
-                int sl[4];
-                if (type == 0) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) sl[q] = MOVING ? c_feat_tt_moving[f][q] : c_feat_tt_static[f][q];
-                    rec.edge = f >= 6;
-                } else if (type == 1) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) sl[q] = c_feat_tb[f][q];
-                    rec.edge = f >= 2;
-                } else {
-                    sl[0] = 0; sl[1] = 1; sl[2] = 3; sl[3] = 4;
-                    rec.edge = 1;
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) rec.id[i] = s_id[wb + o][sl[i]];
-                if (!MOVING) back = rec.edge != 0;
-                if (MOVING) {
-                    Quad q;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) {
-                            q.xo[i][d] = s_x[wb + o][3 * sl[i] + d];
-                            q.av[i][d] = s_v[MOVING ? wb + o : 0][3 * sl[i] + d];
-                        }
-                    double ca, cb, cc, cd;
-                    coplanar_coeffs(q, ca, cb, cc, cd);
-                    const int kindc = coplanar_maybe(ca, cb, cc, cd, P.dt);
-                    keep = kindc != 0;
-                    back = split_by_kind ? rec.edge != 0 : kindc == 2;
-                }
-            }
-            // two kinds of entries, one filling the list from the front and one from the back, so that the
-            // consumer's warps are homogeneous: proximity -> point-triangle | edge-edge (k_contact);
-            // CCD -> point-triangle | edge-edge (k_feature), or, for the staged pipeline, trig branch | other
-            // branches of the cubic (k_roots, which re-splits by test kind)
-#pragma unroll
-            for (int kind = 0; kind < 2; ++kind) {
-                const bool mine = keep && back == (kind == 1);
-                const unsigned ballot = __ballot_sync(0xffffffffu, mine);
-                if (!ballot) continue;
-                unsigned long long slot0 = 0;
-                if (lane == 0) slot0 = atomicAdd(&counters[kind ? CTR_FEATS_EE : CTR_FEATS], (unsigned long long)__popc(ballot));
-                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-                const long long slot = (long long)(slot0 + __popc(ballot & ((1u << lane) - 1u)));
-                if (mine && slot < cap_feats) {
-                    uint2* dst = reinterpret_cast<uint2*>(feats + (kind ? cap_feats - 1 - slot : slot));
-                    dst[0] = make_uint2(rec.entry, (unsigned)rec.id[0]);
-                    dst[1] = make_uint2((unsigned)rec.id[1], (unsigned)rec.id[2]);
-                    dst[2] = make_uint2((unsigned)rec.id[3], rec.edge);
-                }
-            }
-        }
-        __syncwarp();
-    }
-#endif
     for (int o = 16; o > 0; o >>= 1) n_box += __shfl_xor_sync(0xffffffffu, n_box, o);
     if (lane == 0 && n_box) atomicAdd(&counters[CTR_BOXSURV], n_box);
 }
@@ -582,21 +489,18 @@ k_contact(const FeatRec* __restrict__ feats, const RootRec* __restrict__ rootrec
     }
 }
 
-// ------------------------------------------------------------------ fused CCD feature kernel (pipeline 1)
-// One gather per feature.  fastpath.cuh settles four features out of five in plain FP64: no valid root
-// (nothing to do), or "misses at every root" -- then the outcome is the reference's own static test at
-// t = dt, run right here.  Only the features that may fire AT a root go through the correctly rounded
-// solve: they are queued per warp in shared memory and processed 32 at a time, so the double-double code
-// runs with full warps.  Output: the hit list (feature + first hit time), point-triangle entries from the
-// front, edge-edge entries from the back; k_emit turns it into contact and impulse records.
+// ------------------------------------------------------------------ CCD features with the fast path (pipeline 1)
+// fastpath.cuh settles three features out of four in plain FP64: no valid root (nothing to do), or "misses at
+// every root" -- then the outcome is the reference's own static test at t = dt, run right there.  Only the
+// features that may fire AT a root need the correctly rounded solve.  Two lean kernels, so that neither carries
+// the other's code or registers: k_fast (fast path + test at dt; the undecided features go to a list) and
+// k_exact (correctly rounded solve + the reference's walk over the roots for that list).  Both append to the hit
+// list (feature + first hit time), point-triangle entries from the front, edge-edge entries from the back;
+// k_emit turns it into contact and impulse records.
 struct HitRec {  // 32 B
     FeatRec f;
     double t;
 };
-#define FEATURE_QCAP 64
-#ifndef FEATURE_MIN_BLOCKS
-#define FEATURE_MIN_BLOCKS 3
-#endif
 
 __device__ __forceinline__ void load_quad(const FeatRec& fr, const Vec4* __restrict__ xo, const Vec4* __restrict__ av, Quad& q)
 {
@@ -611,6 +515,14 @@ __device__ __forceinline__ void load_quad(const FeatRec& fr, const Vec4* __restr
     }
 }
 
+__device__ __forceinline__ void store_featrec(FeatRec* dst, const FeatRec& fr)
+{
+    uint2* o = reinterpret_cast<uint2*>(dst);
+    o[0] = make_uint2(fr.entry, (unsigned)fr.id[0]);
+    o[1] = make_uint2((unsigned)fr.id[1], (unsigned)fr.id[2]);
+    o[2] = make_uint2((unsigned)fr.id[3], fr.edge);
+}
+
 __device__ __forceinline__ void push_hit(HitRec* __restrict__ hits, long long cap_hits, unsigned long long* counters, const FeatRec& fr,
                                          double t)
 {
@@ -620,18 +532,15 @@ __device__ __forceinline__ void push_hit(HitRec* __restrict__ hits, long long ca
     else slot = (long long)reserve1(&counters[CTR_HITS]);
     if (slot < cap_hits) {
         HitRec* dst = ee ? hits + (cap_hits - 1 - slot) : hits + slot;
-        uint2* o = reinterpret_cast<uint2*>(dst);
-        o[0] = make_uint2(fr.entry, (unsigned)fr.id[0]);
-        o[1] = make_uint2((unsigned)fr.id[1], (unsigned)fr.id[2]);
-        o[2] = make_uint2((unsigned)fr.id[3], fr.edge);
+        store_featrec(&dst->f, fr);
         reinterpret_cast<double*>(dst)[3] = t;
     }
 }
 
-// correctly rounded solve + the reference's walk over the roots: the cold path of k_feature, kept out of line so
-// that the hot loop's instruction footprint stays small
+// correctly rounded solve + the reference's walk over the roots (MovingPointToTri / MovingEdgeToEdge,
+// dcollid3d.cpp:327-369): first time at which the static test fires, or -1
 template <bool EDGE>
-__device__ __forceinline__ double exact_first_hit_inl(const NarrowParams& P, const Emit& E, const Quad& q, bool& coplanar)
+__device__ __forceinline__ double exact_first_hit(const NarrowParams& P, const Emit& E, const Quad& q, bool& coplanar)
 {
     double roots[3] = {-1, -1, -1};
     coplanar = is_coplanar<false>(q, P.dt, roots);
@@ -648,21 +557,18 @@ __device__ __forceinline__ double exact_first_hit_inl(const NarrowParams& P, con
     return -1.0;
 }
 
-template <bool EDGE>
-__device__ __noinline__ double exact_first_hit(const NarrowParams& P, const Emit& E, const Quad& q, bool& coplanar)
-{
-    return exact_first_hit_inl<EDGE>(P, E, q, coplanar);
-}
-
-// Pipeline 2: the same work as k_feature in two lean kernels.  k_fast runs the plain-FP64 fast path (and the
-// static test at t = dt for the features it settles) and appends the undecided features to a list; k_exact
-// solves those correctly rounded.  Neither carries the other's code or registers.
 #ifndef FAST_MIN_BLOCKS
 #define FAST_MIN_BLOCKS 4
 #endif
 #ifndef EXACT_MIN_BLOCKS
 #define EXACT_MIN_BLOCKS 4
 #endif
+#define FAST_QCAP 64
+
+// EDGE = false: the point-triangle entries (front of the work list); EDGE = true: the edge-edge entries (back).
+// The two outputs of a round (hits at dt, undecided features) are buffered per warp as work-list indices and
+// written out 32 at a time: one slot reservation per 32 entries instead of one or two per round (a same-address
+// atomic is serialised at the L2 and its round trip would sit in every round's critical path).
 template <bool EDGE>
 __global__ void __launch_bounds__(FEAT_THREADS, FAST_MIN_BLOCKS)
 k_fast(const FeatRec* __restrict__ feats, long long cap_feats, const Vec4* __restrict__ xo, const Vec4* __restrict__ av,
@@ -673,30 +579,68 @@ k_fast(const FeatRec* __restrict__ feats, long long cap_feats, const Vec4* __res
     if (n_pt + n_ee > cap_feats) return;  // overflow: the host grows the list and repeats the pass
     const long long n = EDGE ? n_ee : n_pt;
     unsigned long long n_cop = 0;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-        const long long at = EDGE ? cap_feats - 1 - t : t;
-        const FeatRec fr = load_featrec(feats + at);
-        Quad q;
-        load_quad(fr, xo, av, q);
-        const int st = feature_fast(q, EDGE, P.dt, P.eps, P.eps);
-        if (st == FAST_DT_ONLY) {
-            ++n_cop;
-            double X[4][3];
-            positions_at<true>(q, P.dt, X);
-            const bool hit = EDGE ? edge_to_edge<false>(P, E, q, 0ull, X, P.eps, P.dt) : point_to_tri<false>(P, E, q, 0ull, X, P.eps, P.dt);
-            if (hit) push_hit(hits, cap_hits, E.counters, fr, P.dt);
-        } else if (st == FAST_UNCERTAIN) {
-            const long long slot = (long long)reserve1(&E.counters[EDGE ? CTR_UNC_EE : CTR_UNC]);
-            if (slot < cap_unc) {
-                uint2* o = reinterpret_cast<uint2*>(unc + (EDGE ? cap_unc - 1 - slot : slot));
-                o[0] = make_uint2(fr.entry, (unsigned)fr.id[0]);
-                o[1] = make_uint2((unsigned)fr.id[1], (unsigned)fr.id[2]);
-                o[2] = make_uint2((unsigned)fr.id[3], fr.edge);
+    __shared__ long long s_hit[FEAT_THREADS / 32][FAST_QCAP], s_unc[FEAT_THREADS / 32][FAST_QCAP];
+    const int w = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    int nh = 0, nu = 0;  // warp-uniform fill of the two buffers
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); t0 < n; t0 += stride) {
+        const long long t = t0 + lane;
+        bool hit = false, undecided = false;
+        long long at = 0;
+        if (t < n) {
+            at = EDGE ? cap_feats - 1 - t : t;
+            const FeatRec fr = load_featrec(feats + at);
+            Quad q;
+            load_quad(fr, xo, av, q);
+            const int st = feature_fast(q, EDGE, P.dt, P.eps, P.eps);
+            if (st == FAST_DT_ONLY) {
+                ++n_cop;
+                double X[4][3];
+                positions_at<true>(q, P.dt, X);
+                hit = EDGE ? edge_to_edge<false>(P, E, q, 0ull, X, P.eps, P.dt) : point_to_tri<false>(P, E, q, 0ull, X, P.eps, P.dt);
+            } else {
+                undecided = st == FAST_UNCERTAIN;
             }
+        }
+        const unsigned hb = __ballot_sync(0xffffffffu, hit), ub = __ballot_sync(0xffffffffu, undecided);
+        if (hit) s_hit[w][nh + __popc(hb & lt)] = at;
+        if (undecided) s_unc[w][nu + __popc(ub & lt)] = at;
+        nh += __popc(hb);
+        nu += __popc(ub);
+        __syncwarp();
+        const bool last = t0 + stride >= n;
+        while (nh >= 32 || (last && nh > 0)) {
+            const int take = nh < 32 ? nh : 32;
+            unsigned long long s0 = 0;
+            if (lane == 0) s0 = atomicAdd(&E.counters[EDGE ? CTR_HITS_EE : CTR_HITS], (unsigned long long)take);
+            s0 = __shfl_sync(0xffffffffu, s0, 0);
+            const long long slot = (long long)s0 + lane;
+            if (lane < take && slot < cap_hits) {
+                const FeatRec fr = load_featrec(feats + s_hit[w][nh - take + lane]);
+                HitRec* dst = EDGE ? hits + (cap_hits - 1 - slot) : hits + slot;
+                store_featrec(&dst->f, fr);
+                reinterpret_cast<double*>(dst)[3] = P.dt;
+            }
+            nh -= take;
+            __syncwarp();
+        }
+        while (nu >= 32 || (last && nu > 0)) {
+            const int take = nu < 32 ? nu : 32;
+            unsigned long long s0 = 0;
+            if (lane == 0) s0 = atomicAdd(&E.counters[EDGE ? CTR_UNC_EE : CTR_UNC], (unsigned long long)take);
+            s0 = __shfl_sync(0xffffffffu, s0, 0);
+            const long long slot = (long long)s0 + lane;
+            if (lane < take && slot < cap_unc) {
+                const FeatRec fr = load_featrec(feats + s_unc[w][nu - take + lane]);
+                store_featrec(EDGE ? unc + (cap_unc - 1 - slot) : unc + slot, fr);
+            }
+            nu -= take;
+            __syncwarp();
         }
     }
     for (int o = 16; o > 0; o >>= 1) n_cop += __shfl_xor_sync(0xffffffffu, n_cop, o);
-    if (lane == 0 && n_cop) atomicAdd(&E.counters[CTR_ROOTS], n_cop);
+    if (lane == 0 && n_cop) atomicAdd(&E.counters[CTR_ROOTS], n_cop);   // features with isCoplanar == true (stats)
 }
 
 template <bool EDGE>
@@ -716,7 +660,7 @@ k_exact(const FeatRec* __restrict__ unc, long long cap_unc, const Vec4* __restri
         load_quad(fr, xo, av, q);
         ++n_exact;
         bool cop;
-        const double th = exact_first_hit_inl<EDGE>(P, E, q, cop);
+        const double th = exact_first_hit<EDGE>(P, E, q, cop);
         if (cop) ++n_cop;
         if (th >= 0) push_hit(hits, cap_hits, E.counters, fr, th);
     }
@@ -726,77 +670,6 @@ k_exact(const FeatRec* __restrict__ unc, long long cap_unc, const Vec4* __restri
     }
     if (lane == 0) {
         if (n_cop) atomicAdd(&E.counters[CTR_ROOTS], n_cop);
-        if (n_exact) atomicAdd(&E.counters[CTR_EXACT], n_exact);
-    }
-}
-
-// EDGE = false: the point-triangle entries (front of the work list); EDGE = true: the edge-edge entries (back).
-template <bool EDGE>
-__global__ void __launch_bounds__(FEAT_THREADS, FEATURE_MIN_BLOCKS)
-k_feature(const FeatRec* __restrict__ feats, long long cap_feats, const Vec4* __restrict__ xo, const Vec4* __restrict__ av,
-          NarrowParams P, Emit E, HitRec* __restrict__ hits, long long cap_hits)
-{
-    __shared__ long long s_at[FEAT_THREADS / 32][FEATURE_QCAP];
-    __shared__ int s_n[FEAT_THREADS / 32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const long long n_pt = (long long)E.counters[CTR_FEATS], n_ee = (long long)E.counters[CTR_FEATS_EE];
-    if (n_pt + n_ee > cap_feats) return;  // overflow: the host grows the list and repeats the pass
-    const long long n = EDGE ? n_ee : n_pt;
-    const double h = P.eps;               // CCD: the static tests run with the rounding tolerance (dcollid.cpp:756)
-    unsigned long long n_cop = 0, n_exact = 0;
-    if (lane == 0) s_n[w] = 0;
-    __syncwarp();
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long t0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); ; t0 += stride) {
-        const long long t = t0 + lane;
-        if (t0 < n && t < n) {
-            const long long at = EDGE ? cap_feats - 1 - t : t;
-            const FeatRec fr = load_featrec(feats + at);
-            Quad q;
-            load_quad(fr, xo, av, q);
-            const int st = feature_fast(q, EDGE, P.dt, h, P.eps);
-            if (st == FAST_DT_ONLY) {
-                ++n_cop;
-                double X[4][3];
-                positions_at<true>(q, P.dt, X);
-                const bool hit = EDGE ? edge_to_edge<false>(P, E, q, 0ull, X, h, P.dt) : point_to_tri<false>(P, E, q, 0ull, X, h, P.dt);
-                if (hit) push_hit(hits, cap_hits, E.counters, fr, P.dt);
-            } else if (st == FAST_UNCERTAIN) {
-                const int pos = atomicAdd(&s_n[w], 1);
-                s_at[w][pos] = at;
-            }
-        }
-        __syncwarp();
-        const bool done = t0 + stride >= n;  // no further round for this warp
-        int nq = s_n[w];
-        while (nq >= 32 || (done && nq > 0)) {
-            const int take = nq < 32 ? nq : 32;
-            const int base = nq - take;
-            if (lane < take) {
-                const long long at = s_at[w][base + lane];
-                const FeatRec fr = load_featrec(feats + at);
-                Quad q;
-                load_quad(fr, xo, av, q);
-                ++n_exact;
-                bool cop;
-                const double th = exact_first_hit<EDGE>(P, E, q, cop);
-                if (cop) ++n_cop;
-                if (th >= 0) push_hit(hits, cap_hits, E.counters, fr, th);
-            }
-            nq = base;
-            __syncwarp();
-        }
-        __syncwarp();  // every lane has read s_n[w] before lane 0 rewrites it
-        if (lane == 0) s_n[w] = nq;
-        __syncwarp();
-        if (done) break;
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        n_cop += __shfl_xor_sync(0xffffffffu, n_cop, o);
-        n_exact += __shfl_xor_sync(0xffffffffu, n_exact, o);
-    }
-    if (lane == 0) {
-        if (n_cop) atomicAdd(&E.counters[CTR_ROOTS], n_cop);   // features with isCoplanar == true (stats)
         if (n_exact) atomicAdd(&E.counters[CTR_EXACT], n_exact);
     }
 }
@@ -916,8 +789,8 @@ struct clsn_ctx {
     DevBuf<unsigned> pair_hit;
     DevBuf<RootRec> rootrecs;
     DevBuf<HitRec> hits;
-    DevBuf<FeatRec> unc;        // pipeline 2: features the fast path could not settle
-    int pipeline = 0;           // 0 = staged (k_roots + k_contact), 1 = fused CCD feature kernel (k_feature + k_emit), 2 = k_fast + k_exact + k_emit
+    DevBuf<FeatRec> unc;        // pipeline 1: features the fast path could not settle
+    int pipeline = 1;           // 1 = fast path first (k_fast + k_exact + k_emit), 0 = staged (k_roots + k_contact)
     DevBuf<PointRec> prec, prec_sorted;
     DevBuf<BodyRec> brec;
     DevBuf<Contact> contacts;
@@ -1007,7 +880,7 @@ extern "C" int clsn_create(clsn_ctx** out, int device)
     c->prm = p;
     if (const char* e = getenv("CLSN_PIPELINE")) {
         const int v = atoi(e);
-        if (v >= 0 && v <= 2) c->pipeline = v;
+        if (v == 0 || v == 1) c->pipeline = v;
     }
     *out = c;
     return CLSN_OK;
@@ -1074,7 +947,7 @@ extern "C" int clsn_set_exact_stats(clsn_ctx* c, int on)
 
 extern "C" int clsn_set_pipeline(clsn_ctx* c, int pipeline)
 {
-    if (!c || pipeline < 0 || pipeline > 2) return CLSN_E_ARG;
+    if (!c || (pipeline != 0 && pipeline != 1)) return CLSN_E_ARG;
     c->pipeline = pipeline;
     return CLSN_OK;
 }
@@ -1145,7 +1018,7 @@ extern "C" int clsn_set_topology(clsn_ctx* c, int V, int T, const int32_t* tri_i
     if (c->pairs.n == 0) CK(c->pairs.reserve((size_t)16 * n1 + 1024));
     if (c->feats.n == 0) CK(c->feats.reserve((size_t)64 * n1 + 1024));
     if (c->pipeline == 0 && c->rootrecs.n == 0) CK(c->rootrecs.reserve((size_t)16 * n1 + 1024));
-    if (c->pipeline >= 1 && c->hits.n == 0) CK(c->hits.reserve((size_t)4 * n1 + 1024));
+    if (c->pipeline == 1 && c->hits.n == 0) CK(c->hits.reserve((size_t)4 * n1 + 1024));
     CK(c->pair_hit.reserve(c->pairs.n / 32 + 2));
     if (c->prec.n == 0) CK(c->prec.reserve((size_t)8 * n1 + 1024));
     CK(c->perm.reserve(c->prec.n)); CK(c->perm_sorted.reserve(c->prec.n)); CK(c->skey.reserve(c->prec.n));
@@ -1326,16 +1199,15 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
         const long long hit_words = (long long)(c->pairs.n / 32 + 1);
         CK(cudaMemsetAsync(c->pair_hit.p, 0, (size_t)hit_words * sizeof(unsigned), c->stream));
         const int grid = c->sm_count * NARROW_GRID_MULT;
-        const bool fused = c->pipeline >= 1;
-        const bool split = c->pipeline == 2;
+        const bool fused = c->pipeline == 1;
         if (moving) {
             if (fused && c->hits.n == 0) CK(c->hits.reserve((size_t)4 * N + 1024));
-            if (split && c->unc.n == 0) CK(c->unc.reserve((size_t)4 * N + 1024));
+            if (fused && c->unc.n == 0) CK(c->unc.reserve((size_t)4 * N + 1024));
             if (!fused && c->rootrecs.n == 0) CK(c->rootrecs.reserve((size_t)16 * N + 1024));
             k_cull<true><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p, P,
                                                                 c->feats.p, (long long)c->feats.n, c->counters.p, fused);
             mark(c, PH_CULL);
-            if (split) {
+            if (fused) {
                 k_fast<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E, c->hits.p,
                                                                      (long long)c->hits.n, c->unc.p, (long long)c->unc.n);
                 k_fast<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E, c->hits.p,
@@ -1344,16 +1216,6 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
                                                                       (long long)c->hits.n);
                 k_exact<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->unc.p, (long long)c->unc.n, c->xo.p, c->av.p, P, E, c->hits.p,
                                                                      (long long)c->hits.n);
-                mark(c, PH_ROOTS);
-                k_emit<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p,
-                                                                     c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
-                k_emit<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p,
-                                                                    c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
-            } else if (fused) {
-                k_feature<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E,
-                                                                        c->hits.p, (long long)c->hits.n);
-                k_feature<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E,
-                                                                       c->hits.p, (long long)c->hits.n);
                 mark(c, PH_ROOTS);
                 k_emit<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p,
                                                                      c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
@@ -1375,7 +1237,7 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
         }
         k_count_true<<<c->sm_count * 2, 256, 0, c->stream>>>(c->pair_hit.p, hit_words, c->counters.p);
         CK(cudaGetLastError());
-        c->launches += moving ? (split ? 8 : (fused ? 6 : 4)) : 3;
+        c->launches += moving ? (fused ? 8 : 4) : 3;
         mark(c, PH_CONTACT);
         CK(cudaMemcpyAsync(c->h_counters, c->counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
@@ -1394,7 +1256,7 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
             CK(c->rootrecs.reserve((size_t)((h[CTR_ROOTS] + h[CTR_ROOTS_EE]) * 5 / 4 + 1024)));
             redo = true;
         }
-        if (split && moving && h[CTR_UNC] + h[CTR_UNC_EE] > c->unc.n) {
+        if (fused && moving && h[CTR_UNC] + h[CTR_UNC_EE] > c->unc.n) {
             CK(c->unc.reserve((size_t)((h[CTR_UNC] + h[CTR_UNC_EE]) * 5 / 4 + 1024)));
             redo = true;
         }

@@ -13,53 +13,6 @@
 
 namespace clsn {
 
-// Two tuning variants, measured on the B200 against each other (tools/ab_bench.py); the default is the faster one.
-#ifndef CLSN_SCATTER_V2
-#define CLSN_SCATTER_V2 0
-#endif
-#ifndef CLSN_REDUCE_V2
-#define CLSN_REDUCE_V2 0
-#endif
-
-#if CLSN_SCATTER_V2
-// records -> per-point slots.  fill[] must be zero.
-__global__ void k_scatter(const PointRec* __restrict__ rec, const unsigned long long* __restrict__ n_rec_ptr,
-                          long long cap, const int* __restrict__ offs, int* fill, int* __restrict__ perm,
-                          unsigned long long* __restrict__ skey)
-{
-    long long n = (long long)*n_rec_ptr;
-    if (n > cap) n = cap;
-    // four records per thread and round: the header loads, then the slot atomics, are issued back to back so
-    // that four memory round trips overlap instead of queueing behind each other (the kernel is latency bound)
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long r0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; r0 < n; r0 += 4 * stride) {
-        ulonglong2 h[4];
-        int slot[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const long long r = r0 + u * stride;
-            if (r < n) h[u] = __ldg(reinterpret_cast<const ulonglong2*>(rec + r));
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const long long r = r0 + u * stride;
-            if (r < n) {
-                const int p = (int)(unsigned)h[u].y;
-                slot[u] = __ldg(offs + p) + atomicAdd(fill + p, 1);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const long long r = r0 + u * stride;
-            if (r < n) {
-                perm[slot[u]] = (int)r;
-                skey[slot[u]] = h[u].x;
-            }
-        }
-    }
-}
-
-#else
 // records -> per-point slots.  fill[] must be zero.
 __global__ void k_scatter(const PointRec* __restrict__ rec, const unsigned long long* __restrict__ n_rec_ptr,
                           long long cap, const int* __restrict__ offs, int* fill, int* __restrict__ perm,
@@ -76,7 +29,6 @@ __global__ void k_scatter(const PointRec* __restrict__ rec, const unsigned long 
     }
 }
 
-#endif
 
 // per-point / per-body record counts of an externally gathered record set (multi-GPU import)
 __global__ void k_count_records(const PointRec* __restrict__ prec, long long nprec, const BodyRec* __restrict__ brec,
@@ -130,85 +82,6 @@ __global__ void k_owner_scatter(const PointRec* __restrict__ rec, long long n, i
     }
 }
 
-#if CLSN_REDUCE_V2
-// One warp per point.  Rank the point's keys (all-pairs compare, keys are unique), bring the
-// records into rank order, then lanes 0..5 each sum one of imp.xyz / fric.xyz sequentially.
-// mode 0: apply to avgVel (updateAverageVelocity :707-724); mode 1: write the sums to acc arrays.
-__global__ void __launch_bounds__(256)
-k_reduce_points(const PointRec* __restrict__ rec, const int* __restrict__ offs, const int* __restrict__ cnt, int V,
-                const int* __restrict__ perm, int* __restrict__ perm_sorted, const unsigned long long* __restrict__ skey,
-                const uint8_t* __restrict__ vflags, Vec4* av, uint8_t* has, uint8_t* dirty, int mode, double* __restrict__ acc_imp,
-                double* __restrict__ acc_fric, unsigned long long* counters)
-{
-    // staging of one point's records in rank order: [warp][rank][imp.xyz fric.xyz]
-    __shared__ double s_val[256 / 32][32][6];
-    const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const int warps_per_block = blockDim.x >> 5;
-    for (int p = blockIdx.x * warps_per_block + wib; p < V; p += gridDim.x * warps_per_block) {
-        const int n = cnt[p];
-        if (n == 0) continue;
-        const int base = offs[p];
-        double sum = 0.0;
-        if (n <= 32) {
-            // one record per lane: key ranks by register shuffles, all value loads in flight together, then the
-            // six sequential sums (same order as the generic path: ascending key, starting from 0.0) out of
-            // shared memory -- one memory round trip per point instead of one per record
-            unsigned long long k = ~0ull;
-            int r = 0;
-            if (lane < n) {
-                k = skey[base + lane];
-                r = perm[base + lane];
-            }
-            int rank = 0;
-            for (int u = 0; u < n; ++u) {
-                const unsigned long long ku = __shfl_sync(0xffffffffu, k, u);
-                rank += ku < k ? 1 : 0;
-            }
-            if (lane < n) {
-                const double2* val = reinterpret_cast<const double2*>(rec + r) + 1;  // imp[3], fric[3]
-                const double2 v0 = __ldg(val), v1 = __ldg(val + 1), v2 = __ldg(val + 2);
-                double* dst = s_val[wib][rank];
-                dst[0] = v0.x; dst[1] = v0.y; dst[2] = v1.x; dst[3] = v1.y; dst[4] = v2.x; dst[5] = v2.y;
-            }
-            __syncwarp();
-            if (lane < 6)
-                for (int t = 0; t < n; ++t) sum += s_val[wib][t][lane];
-        } else {
-            // rank = number of smaller keys
-            for (int t = lane; t < n; t += 32) {
-                const unsigned long long k = skey[base + t];
-                int rank = 0;
-                for (int u = 0; u < n; ++u) rank += skey[base + u] < k ? 1 : 0;
-                perm_sorted[base + rank] = perm[base + t];
-            }
-            __syncwarp();
-            if (lane < 6) {
-                for (int t = 0; t < n; ++t) {
-                    const int r = perm_sorted[base + t];
-                    const double* val = reinterpret_cast<const double*>(rec + r) + 2;  // imp[3], fric[3]
-                    sum += val[lane];
-                }
-            }
-        }
-        const double fr = __shfl_down_sync(0xffffffffu, sum, 3);  // lanes 0..2 get fric.xyz
-        if (mode == 0) {
-            if (lane < 3 && !(vflags[p] & 1)) {
-                double* a = reinterpret_cast<double*>(av + p) + lane;
-                const double v = *a + (sum + fr) / n;
-                *a = v;
-                if (isinf(v) || isnan(v)) atomicAdd(&counters[CTR_ERROR], 1ull);
-                if (lane == 0) { has[p] = 1; dirty[p] = 1; }
-            }
-        } else if (lane < 6) {
-            if (lane < 3) acc_imp[3 * (size_t)p + lane] = sum;
-            else acc_fric[3 * (size_t)p + lane - 3] = sum;
-        }
-        __syncwarp();
-    }
-}
-
-#else
 // One warp per point.  Rank the point's keys (all-pairs compare, keys are unique), store the
 // records in rank order, then lanes 0..5 each sum one of imp.xyz / fric.xyz sequentially.
 // mode 0: apply to avgVel (updateAverageVelocity :707-724); mode 1: write the sums to acc arrays.
@@ -257,7 +130,6 @@ k_reduce_points(const PointRec* __restrict__ rec, const int* __restrict__ offs, 
     }
 }
 
-#endif
 
 // Rigid-rigid contacts: per-body sums in key order.  One thread per body; records are few.
 // imp_rg accumulates across passes and steps -- the reference never zeroes collsnImpulse_RG

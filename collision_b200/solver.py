@@ -418,7 +418,8 @@ class CollisionSolver3d:
         self.ctx.check(self.ctx.L.clsn_set_exact_stats(self.ctx.h, int(on)))
 
     def set_pipeline(self, pipeline: int):
-        """1: fused CCD feature kernel (default); 0: staged correctly-rounded solve of every feature.  Same results."""
+        """1: plain-FP64 fast path, correctly rounded solve of the undecided features only (default);
+        0: staged correctly rounded solve of every feature.  Same results."""
         self.ctx.check(self.ctx.L.clsn_set_pipeline(self.ctx.h, int(pipeline)))
 
     def candidates(self):

@@ -65,8 +65,8 @@ typedef struct {
     int64_t features;       /* feature tests evaluated (survived box cull and, CCD, the classifier) */
     int64_t box_survivors;  /* feature tests that survived the swept-box cull                       */
     int64_t coplanar;       /* CCD: features whose cubic has a usable root (isCoplanar true)        */
-    int64_t exact_solves;   /* CCD: correctly rounded cubic solves (fused pipeline: only the features the
-                               plain-FP64 fast path could not settle; staged pipeline: == features)   */
+    int64_t exact_solves;   /* CCD: correctly rounded cubic solves (pipeline 1: only the features the
+                               plain-FP64 fast path could not settle; pipeline 0: == coplanar)        */
 } clsn_pass_stats;
 
 typedef struct {
@@ -200,12 +200,11 @@ int clsn_set_debug(clsn_ctx*, int record_candidates, int record_contacts);
  * that `candidates` equals the reference's callback count in every pass (results are identical). */
 int clsn_set_exact_stats(clsn_ctx*, int on);
 /* CCD narrow phase of MovingPointToTri / MovingEdgeToEdge (dcollid3d.cpp:327-369) after the cull.
- * 0: staged -- correctly rounded solve of every feature (k_roots), then the static tests and the records
- * (k_contact).  1 / 2: a plain-FP64 fast path first settles every feature it can prove to miss at all of its
- * roots (outcome = the static test at t = dt) and only the rest gets the correctly rounded solve -- in one
- * fused kernel (1) or as two lean kernels (2); a last kernel emits the records of the hit list.
- * Results are bit-identical; which one is the default is a measured choice.
- * The environment variable CLSN_PIPELINE=0|1|2 sets the default of new contexts. */
+ * 1 (default): a plain-FP64 fast path (k_fast) first settles every feature it can prove to miss at all of its
+ * roots -- the outcome is then the static test at t = dt -- and only the rest gets the correctly rounded cubic
+ * solve (k_exact); k_emit writes the records of the hit list.  0: staged -- correctly rounded solve of every
+ * feature (k_roots), then the static tests and the records (k_contact); kept for A/B measurements.
+ * Results are bit-identical.  The environment variable CLSN_PIPELINE=0|1 sets the default of new contexts. */
 int clsn_set_pipeline(clsn_ctx*, int pipeline);
 int64_t clsn_num_candidates(clsn_ctx*);
 int clsn_get_candidates(clsn_ctx*, int32_t* pairs /* 2 per pair, unsorted */);

@@ -94,13 +94,13 @@ def test_whole_step_parity(name):
 
 
 @pytest.mark.parametrize("name", ["two_sheets", "mixed", "ball_plane", "layered_4x24", "drape_small", "string_string"])
-def test_fused_and_staged_pipelines_agree(name):
-    """The fast-path pipelines (1: one fused kernel, 2: k_fast + k_exact; plain-FP64 fast path + correctly rounded
-    solve of the undecided features) against the staged pipeline that solves every feature correctly rounded:
-    identical contact sets, counters and state bits, and the fast path must actually save solves."""
+def test_fast_path_and_staged_pipelines_agree(name):
+    """The fast-path pipeline (k_fast + k_exact: plain-FP64 fast path, correctly rounded solve of the undecided
+    features only) against the staged pipeline that solves every feature correctly rounded: identical contact
+    sets, counters and state bits, and the fast path must actually save solves."""
     sc = SCENES[name]()
     outs = []
-    for pipeline in (0, 1, 2):
+    for pipeline in (0, 1):
         gpu = CollisionSolver3d()
         CollisionSolver3d.set_params_from(sc.params)
         gpu.assembleFromInterface(sc, sc.dt)
@@ -119,13 +119,11 @@ def test_fused_and_staged_pipelines_agree(name):
             x, vel = xg, vg
         outs.append(log)
         gpu.close()
-    solves = [0, 0, 0]
-    for a, b, c in zip(*outs):
-        for o in (b, c):
-            assert same_bits(a[0], o[0]) and same_bits(a[1], o[1]) and np.array_equal(a[2], o[2])
-            assert a[3] == o[3]
-        solves[0] += sum(a[4]); solves[1] += sum(b[4]); solves[2] += sum(c[4])
-    assert solves[1] == solves[2]
+    solves = [0, 0]
+    for a, b in zip(*outs):
+        assert same_bits(a[0], b[0]) and same_bits(a[1], b[1]) and np.array_equal(a[2], b[2])
+        assert a[3] == b[3]
+        solves[0] += sum(a[4]); solves[1] += sum(b[4])
     if solves[0] > 1000:
         assert solves[1] < solves[0], solves
 

@@ -210,3 +210,28 @@ def test_ccd_fast_path_on_oracle_scenes():
             orc.close()
     finally:
         port.set_libm(port.LIBM_NATIVE)
+
+
+def test_feature_slot_arithmetic_matches_the_tables():
+    """k_cull computes the local point slots of a feature test arithmetically (feature_slots) instead of indexing
+    the __constant__ tables that document the reference's loop order (MovingTriToTri :286-323, TriToTri :592-625,
+    TriToBond / MovingTriToBond): both are extracted from clsn.cu and compared on the host."""
+    src = open(os.path.join(ROOT, "collision_b200", "csrc", "clsn.cu")).read()
+
+    def table(name):
+        m = re.search(name + r"\[\d+\]\[4\] = \{(.*?)\};", src, re.S)
+        return [list(map(int, re.findall(r"\d+", row))) for row in re.findall(r"\{([^{}]*)\}", m.group(1))]
+
+    tm, ts, tb = table("c_feat_tt_moving"), table("c_feat_tt_static"), table("c_feat_tb")
+    assert (len(tm), len(ts), len(tb)) == (15, 15, 5)
+    a = src.index("template <bool MOVING>\n__host__ __device__ __forceinline__ void feature_slots")
+    fn = src[a:src.index("#define CULL_THREADS 128")].replace("__host__ __device__ __forceinline__", "static inline")
+    calls = []
+    for mv, typ, n in (("true", 0, 15), ("false", 0, 15), ("true", 1, 5), ("false", 1, 5), ("true", 2, 1)):
+        calls += [f'feature_slots<{mv}>({typ},{f},sl); printf("%d %d %d %d\\n",sl[0],sl[1],sl[2],sl[3]);' for f in range(n)]
+    prog = "#include <cstdio>\n" + fn + "\nint main(){int sl[4];\n" + "\n".join(calls) + "\nreturn 0;}\n"
+    with open("/tmp/clsn_slots.cpp", "w") as f:
+        f.write(prog)
+    subprocess.check_call(["g++", "-O1", "/tmp/clsn_slots.cpp", "-o", "/tmp/clsn_slots"])
+    out = [list(map(int, ln.split())) for ln in subprocess.check_output(["/tmp/clsn_slots"], text=True).strip().splitlines()]
+    assert out == tm + ts + tb + tb + [[0, 1, 3, 4]]

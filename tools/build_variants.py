@@ -16,23 +16,16 @@ from collision_b200 import build as b  # noqa: E402
 OUT = os.path.join(ROOT, "collision_b200", "variants")
 
 VARIANTS = {
-    "f2": ["-DFEATURE_MIN_BLOCKS=2"],
-    "f4": ["-DFEATURE_MIN_BLOCKS=4"],
     "c3": ["-DCULL_MIN_BLOCKS=3"],
     "c5": ["-DCULL_MIN_BLOCKS=5"],
     "g8": ["-DNARROW_GRID_MULT=8"],
     "g32": ["-DNARROW_GRID_MULT=32"],
     "t64": ["-DTRAV_THREADS=64"],
     "t256": ["-DTRAV_THREADS=256"],
-    "s2": ["-DCLSN_SCATTER_V2=1"],
-    "r2": ["-DCLSN_REDUCE_V2=1"],
-    "cb0": ["-DCULL_BATCHED=0"],
-    "c5cb0": ["-DCULL_BATCHED=0", "-DCULL_MIN_BLOCKS=5"],
-    "fa5": ["-DFAST_MIN_BLOCKS=5"],
     "fa3": ["-DFAST_MIN_BLOCKS=3"],
+    "fa5": ["-DFAST_MIN_BLOCKS=5"],
     "ex5": ["-DEXACT_MIN_BLOCKS=5"],
-    "r5": ["-DROOTS_MIN_BLOCKS=6"],
-    "pm": ["-DCULL_PAIR_MARGIN=1"],
+    "r6": ["-DROOTS_MIN_BLOCKS=6"],
 }
 
 

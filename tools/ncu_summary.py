@@ -52,7 +52,7 @@ def main():
         # DRAM bytes (read + write) of one step per bench phase -> profiles/traffic.json
         import json
         steps = float(sys.argv[sys.argv.index("--traffic-json") + 2]) if len(sys.argv) > sys.argv.index("--traffic-json") + 2 else 1.0
-        phase_of = {"k_cull": "cull", "k_roots": "roots", "k_contact": "contact", "k_traverse": "traverse", "k_refit": "refit",
+        phase_of = {"k_cull": "cull", "k_roots": "roots", "k_fast": "roots", "k_exact": "roots", "k_contact": "contact", "k_emit": "contact", "k_traverse": "traverse", "k_refit": "refit",
                     "k_reduce_points": "reduce", "k_scatter": "reduce", "DeviceScan": "reduce", "k_reset_dirty": "reduce",
                     "k_avg_velocity": "avgvel", "k_boundary": "finalize", "k_final_position": "finalize",
                     "k_morton": "build", "k_hierarchy": "build", "k_scene_bounds": "build", "DeviceRadixSort": "build"}
