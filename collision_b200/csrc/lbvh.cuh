@@ -286,8 +286,6 @@ k_traverse(const WideNode* __restrict__ nodes, const double* __restrict__ lbox, 
 {
     __shared__ int2 s_q[TRAV_THREADS / 32][TRAV_QCAP];
     __shared__ int s_n[TRAV_THREADS / 32];
-    __shared__ int2 s_out[TRAV_THREADS / 32][64];
-    int n_out = 0;  // warp-uniform fill of s_out
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int i = q_lo + blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long n_cand = 0;
@@ -392,20 +390,13 @@ k_traverse(const WideNode* __restrict__ nodes, const double* __restrict__ lbox, 
                     }
                 }
             }
-            // emitted pairs are staged per warp and written 32 at a time: one slot reservation (a same-address
-            // atomic, serialised at the L2) and one coalesced 256-byte store per 32 pairs
             const unsigned ballot = __ballot_sync(0xffffffffu, emit);
-            if (emit) s_out[w][n_out + __popc(ballot & ((1u << lane) - 1u))] = make_int2(a, b);
-            n_out += __popc(ballot);
-            __syncwarp();
-            if (n_out >= 32) {
+            if (ballot) {
                 unsigned long long s0 = 0;
-                if (lane == 0) s0 = atomicAdd(&out.counters[CTR_PAIRS], 32ull);
+                if (lane == 0) s0 = atomicAdd(&out.counters[CTR_PAIRS], (unsigned long long)__popc(ballot));
                 s0 = __shfl_sync(0xffffffffu, s0, 0);
-                const unsigned long long sl = s0 + lane;
-                if ((long long)sl < out.cap_pairs) out.pairs[sl] = s_out[w][n_out - 32 + lane];
-                n_out -= 32;
-                __syncwarp();
+                const unsigned long long sl = s0 + __popc(ballot & ((1u << lane) - 1u));
+                if (emit && (long long)sl < out.cap_pairs) out.pairs[sl] = make_int2(a, b);
             }
             nq = base;
             __syncwarp();
@@ -413,13 +404,6 @@ k_traverse(const WideNode* __restrict__ nodes, const double* __restrict__ lbox, 
         __syncwarp();  // every lane has read s_n[w] before lane 0 rewrites it
         if (lane == 0) s_n[w] = nq;
         __syncwarp();
-    }
-    if (n_out > 0) {  // the warp's last, partial batch
-        unsigned long long s0 = 0;
-        if (lane == 0) s0 = atomicAdd(&out.counters[CTR_PAIRS], (unsigned long long)n_out);
-        s0 = __shfl_sync(0xffffffffu, s0, 0);
-        const unsigned long long sl = s0 + lane;
-        if (lane < n_out && (long long)sl < out.cap_pairs) out.pairs[sl] = s_out[w][lane];
     }
     // candidate count: warp-reduce, one atomic per warp
     for (int o = 16; o > 0; o >>= 1) n_cand += __shfl_xor_sync(0xffffffffu, n_cand, o);
