@@ -1,10 +1,10 @@
 #!/bin/bash
-# Final GPU call of the round: smoke, bench (both arms), then the GPU test suite.
+# One gpurun call that mirrors the driver's round-end checks: smoke, bench (both arms, config 3), then the GPU test suite.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 T0=$(date +%s)
-log() { echo "[$(( $(date +%s) - T0 ))s] $*" | tee -a gpurun_out/call_final.log; }
-timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee -a gpurun_out/call_final.log
+log() { echo "[$(( $(date +%s) - T0 ))s] $*" | tee -a gpurun_out/round_end.log; }
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee -a gpurun_out/round_end.log
 log "bench"
 timeout 200 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
 log "bench exit $? $(cut -c1-200 gpurun_out/bench_final.json)"
