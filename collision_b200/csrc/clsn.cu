@@ -31,21 +31,25 @@
 using namespace clsn;
 
 // ------------------------------------------------------------------ narrow-phase kernel
-// feature tables: local point slots (0..2 = element a, 3..5 = element b) of the 4 points of each test
+// Feature tables: local point slots (0..2 = element a, 3..5 = element b) of the 4 points of each test, in the
+// reference's loop order.  Documentation (and the reference data of
+// tests/test_host_cpu.py::test_feature_slot_arithmetic_matches_the_tables); the kernels use feature_slots() below.
+/*
 // tri-tri CCD (MovingTriToTri :286-323): k=0 tri a + vertex b_i, k=1 tri b + vertex a_i, then edges
-__constant__ unsigned char c_feat_tt_moving[15][4] = {
+c_feat_tt_moving[15][4] = {
     {0, 1, 2, 3}, {0, 1, 2, 4}, {0, 1, 2, 5}, {3, 4, 5, 0}, {3, 4, 5, 1}, {3, 4, 5, 2},
     {0, 1, 3, 4}, {0, 1, 4, 5}, {0, 1, 5, 3}, {1, 2, 3, 4}, {1, 2, 4, 5}, {1, 2, 5, 3},
     {2, 0, 3, 4}, {2, 0, 4, 5}, {2, 0, 5, 3}};
 // tri-tri proximity (TriToTri :592-625): k=0 tri b (tri2) + vertex a_i, k=1 tri a + vertex b_i
-__constant__ unsigned char c_feat_tt_static[15][4] = {
+c_feat_tt_static[15][4] = {
     {3, 4, 5, 0}, {3, 4, 5, 1}, {3, 4, 5, 2}, {0, 1, 2, 3}, {0, 1, 2, 4}, {0, 1, 2, 5},
     {0, 1, 3, 4}, {0, 1, 4, 5}, {0, 1, 5, 3}, {1, 2, 3, 4}, {1, 2, 4, 5}, {1, 2, 5, 3},
     {2, 0, 3, 4}, {2, 0, 4, 5}, {2, 0, 5, 3}};
 // tri (a) - bond (b = slots 3,4) (TriToBond :508-530, MovingTriToBond :219-241)
-__constant__ unsigned char c_feat_tb[5][4] = {{0, 1, 2, 3}, {0, 1, 2, 4}, {0, 1, 3, 4}, {1, 2, 3, 4}, {2, 0, 3, 4}};
+c_feat_tb[5][4] = {{0, 1, 2, 3}, {0, 1, 2, 4}, {0, 1, 3, 4}, {1, 2, 3, 4}, {2, 0, 3, 4}};
+*/
 
-// The same tables computed arithmetically: a lane-varying index into __constant__ memory is replayed once per
+// The tables computed arithmetically: a lane-varying index into a __constant__ table is replayed once per
 // distinct address in the warp, these few integer operations are not.  type 0 tri-tri, 1 tri-bond, 2 bond-bond.
 // (tests/test_host_cpu.py checks this function against the tables above.)
 template <bool MOVING>
@@ -202,7 +206,7 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
                     eb[i] = fbox_union(pb[3 + i], pb[3 + (i + 1) % 3]);
                 }
                 const FBox ta = fbox_union(ea[0], pb[2]), tb = fbox_union(eb[0], pb[5]);
-                // point-triangle features 0..5 (order differs between proximity and CCD, see c_feat_tt_*)
+                // point-triangle features 0..5 (order differs between proximity and CCD, see the tables above)
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const bool a_tri_b_pt = !boxes_far(ta, pb[3 + i], h2, rel);  // triangle a, vertex b_i
