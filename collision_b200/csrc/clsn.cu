@@ -872,6 +872,12 @@ extern "C" int clsn_create(clsn_ctx** out, int device)
     }
     c->stream = c->own_stream;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+#ifdef CULL_SMEM_CARVEOUT
+    // tuning experiment (tools/build_variants.py): k_cull keeps 44.5 KB of shared memory per block, so a fifth
+    // resident block (CULL_MIN_BLOCKS=5) needs the full shared-memory carve-out
+    cudaFuncSetAttribute(k_cull<true>, cudaFuncAttributePreferredSharedMemoryCarveout, CULL_SMEM_CARVEOUT);
+    cudaFuncSetAttribute(k_cull<false>, cudaFuncAttributePreferredSharedMemoryCarveout, CULL_SMEM_CARVEOUT);
+#endif
     for (auto& e : c->ev) cudaEventCreate(&e);
     cudaEventCreate(&c->bracket[0]);
     cudaEventCreate(&c->bracket[1]);

@@ -18,6 +18,7 @@ OUT = os.path.join(ROOT, "collision_b200", "variants")
 VARIANTS = {
     "c3": ["-DCULL_MIN_BLOCKS=3"],
     "c5": ["-DCULL_MIN_BLOCKS=5"],
+    "c5co": ["-DCULL_MIN_BLOCKS=5", "-DCULL_SMEM_CARVEOUT=100"],   # 5 resident blocks: <= 102 registers + full carve-out
     "g8": ["-DNARROW_GRID_MULT=8"],
     "g32": ["-DNARROW_GRID_MULT=32"],
     "t64": ["-DTRAV_THREADS=64"],
