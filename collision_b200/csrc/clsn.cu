@@ -85,6 +85,9 @@ __host__ __device__ __forceinline__ void feature_slots(int type, int f, int sl[4
 #ifndef FEAT_MIN_BLOCKS
 #define FEAT_MIN_BLOCKS 4
 #endif
+#ifndef CULL_PREFILTER
+#define CULL_PREFILTER 0
+#endif
 #define CULL_KEEP_CAP 128  // per-warp buffer of kept features between slot reservations
 #define CULL_ROW 19  // doubles per staged pair row (18 used): odd stride -> conflict-free column access
 
@@ -284,11 +287,19 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
                             q.xo[i][d] = s_x[wb + o][3 * sl[i] + d];
                             q.av[i][d] = s_v[MOVING ? wb + o : 0][3 * sl[i] + d];
                         }
-                    double ca, cb, cc, cd;
-                    coplanar_coeffs(q, ca, cb, cc, cd);
-                    const int kindc = coplanar_maybe(ca, cb, cc, cd, P.dt);
-                    keep = kindc != 0;
-                    if (!split_by_kind) back = kindc == 2;
+#if CULL_PREFILTER
+                    // experimental (tools/build_variants.py "pf"): FP32 Bernstein test in front of the FP64 classifier
+                    if (coplanar_prefilter32(q, P.dt)) {
+                        keep = false;
+                    } else
+#endif
+                    {
+                        double ca, cb, cc, cd;
+                        coplanar_coeffs(q, ca, cb, cc, cd);
+                        const int kindc = coplanar_maybe(ca, cb, cc, cd, P.dt);
+                        keep = kindc != 0;
+                        if (!split_by_kind) back = kindc == 2;
+                    }
                 }
                 code = ((unsigned)o << 5) | ((unsigned)f << 1) | (back ? 1u : 0u);
             }

@@ -127,6 +127,79 @@ CLSN_HD int coplanar_maybe(double a, double b, double c, double d, double dt)
     return (ok0 || ok1) ? 2 : 0;
 }
 
+// FP32 pre-filter in front of coplanar_maybe(): "true" = isCoplanar certainly finds no root that survives its
+// [0, dt] filter, decided without a single FP64 multiplication (experimental, -DCULL_PREFILTER=1).
+//
+// With times in units of dt and lengths scaled to O(1), the coplanarity cubic is the multilinear expansion of
+// p(t) = X3(t) . (X1(t) x X2(t)),  Xi(t) = xi + t wi  (positions and per-step displacements relative to point 0).
+// If its four Bernstein coefficients on [0, 1] have one sign, |p| >= m = min |k_j| on [0, 1] (convex hull).  A
+// root the reference would keep, t^ in [MACH_EPS, dt + MACH_EPS], comes out of closed formulas whose error is
+// bounded in terms of sigma = max(|A|, sqrt|B|, cbrt|C|) (A, B, C the monic coefficients; all roots are <= 2 sigma):
+//   * t^ is within g = 3e-13 sigma of an exact root of the monic cubic with (Q, R) perturbed by the rounding of
+//     their evaluation (trig branch: S + |A/3| <= 1.7 sigma; Cardano: |A_c| + |B_c| + |A/3| <= 2.8 sigma),
+//     i.e. |p(t*)| <= alpha (3 sigma^2 + 5 sigma^3) 1e-13 for some |t* - t^| <= g;
+//   * the Cardano branch's extra double root sits at the real part of a conjugate pair whose imaginary part is
+//     below 1e-10 (absolute, in time units): |p| <= alpha (1 + 2 sigma) 0.75e-20 / dt^2 there.
+// So no kept root exists if  m > E32 + U64,  E32 = 4e-6 * 6 prod(|xi| + |wi|) the FP32 evaluation error of a
+// Bernstein coefficient and U64 the FP64-level terms above plus g |p'|max (1e-13 = ~900 u: two orders of
+// magnitude of head-room over the operation counts).  Degenerate cubics (tiny leading coefficient: sigma huge,
+// or the reference's quadratic / linear branches) make U64 large or fail the alpha test and stay undecided, as
+// does every NaN (unordered comparisons are false).  Fuzzed against the oracle by tests/cubic_check.cpp.
+CLSN_HD bool coplanar_prefilter32(const Quad& q, double dt)
+{
+    double dx[3][3], dw[3][3], big = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            dx[i][k] = q.xo[i + 1][k] - q.xo[0][k];
+            dw[i][k] = (q.av[i + 1][k] - q.av[0][k]) * dt;
+            big = fmax(big, fmax(fabs(dx[i][k]), fabs(dw[i][k])));
+        }
+    if (!(big > 1e-300 && big < 1e300 && dt > 1e-30)) return false;
+    const double sc = 1.0 / big;
+    float x[3][3], w[3][3], X[3], W[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        X[i] = 0.f; W[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            x[i][k] = (float)(dx[i][k] * sc);
+            w[i][k] = (float)(dw[i][k] * sc);
+            X[i] = fmaxf(X[i], fabsf(x[i][k]));
+            W[i] = fmaxf(W[i], fabsf(w[i][k]));
+        }
+    }
+    // s . (u x v)
+#define CLSN_TRIPLE(u, v, s) ((s)[0] * ((u)[1] * (v)[2] - (u)[2] * (v)[1]) + (s)[1] * ((u)[2] * (v)[0] - (u)[0] * (v)[2]) + \
+                              (s)[2] * ((u)[0] * (v)[1] - (u)[1] * (v)[0]))
+    const float d = CLSN_TRIPLE(x[0], x[1], x[2]);
+    const float c = CLSN_TRIPLE(w[0], x[1], x[2]) + CLSN_TRIPLE(x[0], w[1], x[2]) + CLSN_TRIPLE(x[0], x[1], w[2]);
+    const float b = CLSN_TRIPLE(x[0], w[1], w[2]) + CLSN_TRIPLE(w[0], x[1], w[2]) + CLSN_TRIPLE(w[0], w[1], x[2]);
+    const float a = CLSN_TRIPLE(w[0], w[1], w[2]);
+#undef CLSN_TRIPLE
+    const float k0 = d, k1 = d + c * (1.f / 3.f), k2 = d + (2.f * c + b) * (1.f / 3.f), k3 = d + c + b + a;
+    const bool pos = k0 > 0.f && k1 > 0.f && k2 > 0.f && k3 > 0.f;
+    const bool neg = k0 < 0.f && k1 < 0.f && k2 < 0.f && k3 < 0.f;
+    if (!(pos || neg)) return false;
+    const float m = fminf(fminf(fabsf(k0), fabsf(k1)), fminf(fabsf(k2), fabsf(k3)));
+    const float mtot = 6.f * (X[0] + W[0]) * (X[1] + W[1]) * (X[2] + W[2]);
+    const float e32 = 4e-6f * mtot;
+    if (!(m > 2.f * e32)) return false;
+    // FP64-level terms; they matter only for nearly degenerate cubics, which must stay undecided
+    const float al = fabsf(a);
+    if (!(al > 64e-6f * W[0] * W[1] * W[2])) return false;   // leading coefficient known to ~10 %: else undecided
+    const float A = fabsf(b) / al, B = fabsf(c) / al, C = fabsf(d) / al;
+    const float sg = 1.2f * fmaxf(A, fmaxf(sqrtf(B), cbrtf(C)));
+    const float dtf = (float)dt;
+    const float g = 3e-13f * sg + 4e-16f / dtf;
+    if (!(g < 0.01f)) return false;
+    const float dmax = 1.1f * (fabsf(c) + 2.f * fabsf(b) + 3.f * al);
+    const float u64 = al * (3.f * sg * sg + 5.f * sg * sg * sg) * 1e-13f + g * dmax +
+                      al * (1.f + 2.f * sg) * (1e-20f / (dtf * dtf)) + 1e-13f * mtot;
+    return m > 2.f * (e32 + u64);
+}
+
 // isCoplanar, dcollid3d.cpp:371-482.  Returns true iff some root > MACH_EPS; roots[0..2] sorted.
 // CLASSIFY = false when the caller has already run coplanar_maybe() on this feature (k_cull).
 template <bool CLASSIFY>

@@ -1,7 +1,8 @@
 // Host-side fuzz of collision_b200/csrc/cubic.cuh (the CUDA path's isCoplanar: coefficients, trig-free
 // classifier, selective correctly rounded solve) against the oracle's is_coplanar (binary128 libm flavour).
 // Built and run by tests/test_host_cpu.py.  Usage: cubic_check <liboracle.so> <cases> [seed]
-// Prints: cases, mismatches (ret or any root bit), classifier rejections, of which oracle-true (must be 0).
+// Prints: cases, mismatches (ret or any root bit), classifier rejections, of which oracle-true (must be 0), oracle-true
+// cases, FP32 pre-filter rejections, of which the oracle keeps a root (must be 0).
 #include <dlfcn.h>
 #include <cmath>
 #include <cstdio>
@@ -29,7 +30,7 @@ int main(int argc, char** argv)
     const double params[6] = {1e-6, 1e-4, 1000, 0.01, 0.02, 0};
     const unsigned char flags[4] = {0, 0, 0, 0};
     const double mass[4] = {1, 1, 1, 1};
-    long bad = 0, rejected = 0, rejected_wrong = 0, oracle_true = 0;
+    long bad = 0, rejected = 0, rejected_wrong = 0, oracle_true = 0, pre = 0, pre_wrong = 0;
     for (long it = 0; it < N; ++it) {
         double x[4][3], v[4][3];
         const double L = 4e-3 * pow(10.0, (it % 5 == 0) ? 3 * S() : 0.0);   // element size, sometimes rescaled
@@ -72,6 +73,11 @@ int main(int argc, char** argv)
         clsn::coplanar_coeffs(q, a, b, c, d);
         const int kind = clsn::coplanar_maybe(a, b, c, d, dt);
         oracle_true += ret_or;
+        if (clsn::coplanar_prefilter32(q, dt)) {
+            // the FP32 pre-filter may only reject what the oracle rejects
+            ++pre;
+            if (ret_or || r_or[0] >= 0 || r_or[1] >= 0 || r_or[2] >= 0) ++pre_wrong;
+        }
         if (kind == 0) {
             ++rejected;
             // a rejected cubic must have NO root surviving the [0, dt] filter in the oracle
@@ -86,6 +92,6 @@ int main(int argc, char** argv)
             }
         }
     }
-    printf("%ld %ld %ld %ld %ld\n", N, bad, rejected, rejected_wrong, oracle_true);
+    printf("%ld %ld %ld %ld %ld %ld %ld\n", N, bad, rejected, rejected_wrong, oracle_true, pre, pre_wrong);
     return 0;
 }

@@ -40,7 +40,9 @@ static void cross(const double* a, const double* b, double* r)
 
 // Scene-level check (called through ctypes by tests/test_host_cpu.py): every CCD feature test of every
 // non-adjacent candidate pair of a pass, on the state the oracle had before that pass.
-// elem: 4 ints per element (p0, p1, p2 or -1 for a bond, unused).  counts: miss, dt_only, uncertain, oracle hits.
+// elem: 4 ints per element (p0, p1, p2 or -1 for a bond, unused).  counts: miss, dt_only, uncertain, oracle hits,
+// classifier rejections (coplanar_maybe == 0), FP32 pre-filter rejections; both kinds of rejection are checked against
+// the oracle's roots as well.
 extern "C" long fastpath_scene_check(const char* oracle_so, long npairs, const int* pairs, const int* elem, const double* xo,
                                      const double* av, double dt, double eps, long* counts)
 {
@@ -57,7 +59,7 @@ extern "C" long fastpath_scene_check(const char* oracle_so, long npairs, const i
     const unsigned char flags[4] = {0, 0, 0, 0};
     const double mass[4] = {1, 1, 1, 1};
     long wrong = 0;
-    counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    for (int i = 0; i < 6; ++i) counts[i] = 0;
     for (long pi = 0; pi < npairs; ++pi) {
         int ea = pairs[2 * pi], eb = pairs[2 * pi + 1];
         if (ea > eb) { int t = ea; ea = eb; eb = t; }
@@ -88,6 +90,11 @@ extern "C" long fastpath_scene_check(const char* oracle_so, long npairs, const i
             const int ret_or = orc_feature(edge ? 4 : 3, qx, qx, qv, flags, mass, eps, dt, params, r_or, acc, &hit_root);
             const bool cop = r_or[0] > DBL_EPSILON || r_or[1] > DBL_EPSILON || r_or[2] > DBL_EPSILON;
             if (ret_or > 0) ++counts[3];
+            const bool any_root = r_or[0] >= 0 || r_or[1] >= 0 || r_or[2] >= 0;
+            double ca, cb, cc, cd;
+            clsn::coplanar_coeffs(q, ca, cb, cc, cd);
+            if (clsn::coplanar_maybe(ca, cb, cc, cd, dt) == 0) { ++counts[4]; if (any_root) ++wrong; }
+            if (clsn::coplanar_prefilter32(q, dt)) { ++counts[5]; if (any_root) ++wrong; }
             const int st = clsn::feature_fast(q, edge, dt, eps, eps);
             ++counts[st];
             if (st == clsn::FAST_MISS && (cop || ret_or != 0)) ++wrong;

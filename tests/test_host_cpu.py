@@ -132,8 +132,10 @@ def test_cubic_path_matches_oracle_on_host():
     exe = "/tmp/clsn_cubic_check"
     subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-mfma", "-x", "c++", "-I", os.path.join(ROOT, "collision_b200", "csrc"),
                            os.path.join(ROOT, "tests", "cubic_check.cpp"), "-o", exe, "-ldl", "-lm"])
-    n, bad, rejected, rejected_wrong, oracle_true = map(int, subprocess.check_output([exe, so, "2000000", "7"], text=True).split())
+    n, bad, rejected, rejected_wrong, oracle_true, pre, pre_wrong = map(
+        int, subprocess.check_output([exe, so, "2000000", "7"], text=True).split())
     assert n == 2000000 and bad == 0 and rejected_wrong == 0
+    assert pre > n // 8 and pre_wrong == 0   # the (opt-in) FP32 pre-filter only rejects what the oracle rejects
     assert rejected > n // 4 and oracle_true > n // 4   # both outcomes are well represented
 
 
@@ -181,7 +183,7 @@ def test_ccd_fast_path_on_oracle_scenes():
             elem[sc.T:, :2] = sc.bond_idx
             orc = port.OracleSolver(sc, impact_zones=False, strain_limiting=False)
             x, vel = sc.x.copy(), sc.vel.copy()
-            tot = np.zeros(4, np.int64)
+            tot = np.zeros(6, np.int64)
             for _ in range(steps):
                 orc.set_state(x, x + sc.dt * vel)
                 orc.avg_velocity()
@@ -192,7 +194,7 @@ def test_ccd_fast_path_on_oracle_scenes():
                     av = np.ascontiguousarray(orc.get(port.F_AVGVEL))
                     n_true = orc.detect(port.COLLISION)
                     cand = np.ascontiguousarray(orc.candidates())
-                    counts = np.zeros(4, np.int64)
+                    counts = np.zeros(6, np.int64)   # miss, dt_only, uncertain, oracle hits, classifier / pre-filter rejections
                     wrong = L.fastpath_scene_check(so.encode(), len(cand), cand.ctypes.data, elem.ctypes.data, xo.ctypes.data,
                                                    av.ctypes.data, sc.dt, sc.params.eps, counts.ctypes.data)
                     assert wrong == 0, (sc.name, wrong)
@@ -207,6 +209,7 @@ def test_ccd_fast_path_on_oracle_scenes():
                 x, vel = orc.get(port.F_X).copy(), v
             # uncertain = features that do fire at a root + a thin boundary layer
             assert tot[2] <= 2 * tot[3] + 50, (sc.name, tot)
+            assert tot[5] <= tot[4]   # the FP32 pre-filter is weaker than the FP64 classifier
             orc.close()
     finally:
         port.set_libm(port.LIBM_NATIVE)
