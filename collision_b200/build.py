@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libcollision_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 SOURCES = ["clsn.cu"]
-HEADERS = ["narrow.cuh", "cubic.cuh", "lbvh.cuh", "reduce.cuh", "rigid.cuh", "strain.cuh", "crmath.cuh", "crmath_constants.inc"]
+HEADERS = ["narrow.cuh", "cubic.cuh", "fastpath.cuh", "lbvh.cuh", "reduce.cuh", "rigid.cuh", "strain.cuh", "crmath.cuh", "crmath_constants.inc"]
 
 # --fmad=false: FP64 expressions must round exactly like the reference's (no FMA contraction);
 # the double-double code in crmath.cuh issues its FMAs explicitly.
