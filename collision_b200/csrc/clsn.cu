@@ -689,12 +689,42 @@ k_exact(const FeatRec* __restrict__ unc, long long cap_unc, const Vec4* __restri
     }
 }
 
-// contact + impulse records of the hit list (the second half of k_contact, on a dense list)
+// Pipeline 2 (experimental): per-point record counts of the hit list, so that k_emit<EDGE, true> can write every record
+// straight into its point's segment.  Mirrors the emission rules of PointToTriImpulse / EdgeToEdgeImpulse: one point
+// record per non-static point (dcollid3d.cpp:1053-1079, 1235-1284), none when all four points are rigid (body records).
 template <bool EDGE>
+__global__ void k_count_hits(const HitRec* __restrict__ hits, long long cap_hits, const uint8_t* __restrict__ vflags, int* cnt,
+                             unsigned long long* counters)
+{
+    const long long n_pt = (long long)counters[CTR_HITS], n_ee = (long long)counters[CTR_HITS_EE];
+    if (n_pt + n_ee > cap_hits) return;
+    const long long n = EDGE ? n_ee : n_pt;
+    unsigned long long total = 0;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const long long at = EDGE ? cap_hits - 1 - t : t;
+        const FeatRec fr = load_featrec(&hits[at].f);
+        int fl[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) fl[i] = __ldg(vflags + fr.id[i]);
+        if ((fl[0] & 3) && (fl[1] & 3) && (fl[2] & 3) && (fl[3] & 3)) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (!(fl[i] & 1)) {
+                atomicAdd(cnt + fr.id[i], 1);
+                ++total;
+            }
+    }
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if ((threadIdx.x & 31) == 0 && total) atomicAdd(&counters[CTR_PREC], total);
+}
+
+// contact + impulse records of the hit list (the second half of k_contact, on a dense list).
+// SEG: records go to per-point segments (offsets from the scan of k_count_hits' counts) instead of the append list.
+template <bool EDGE, bool SEG = false>
 __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS)
 k_emit(const HitRec* __restrict__ hits, long long cap_hits, const int2* __restrict__ pairs, const Vec4* __restrict__ xo,
        const Vec4* __restrict__ av, const uint8_t* __restrict__ vflags, const int* __restrict__ vbody, NarrowParams P, Emit E,
-       unsigned* __restrict__ pair_hit)
+       unsigned* __restrict__ pair_hit, SegOut S = SegOut{nullptr, nullptr})
 {
     const long long n_pt = (long long)E.counters[CTR_HITS], n_ee = (long long)E.counters[CTR_HITS_EE];
     if (n_pt + n_ee > cap_hits) return;  // overflow: the host grows the list and repeats the pass
@@ -716,7 +746,7 @@ k_emit(const HitRec* __restrict__ hits, long long cap_hits, const int2* __restri
         const int2 pr = __ldg(pairs + pi);
         const unsigned long long key = ((unsigned long long)(unsigned)pr.x << 34) | ((unsigned long long)(unsigned)pr.y << 4) |
                                        (unsigned long long)f;
-        feature_emit<true>(P, E, q, key, EDGE, P.eps, th);
+        feature_emit<true, SEG>(P, E, q, key, EDGE, P.eps, th, S);
         atomicOr(pair_hit + (pi >> 5), 1u << (pi & 31));
     }
 }
@@ -805,7 +835,9 @@ struct clsn_ctx {
     DevBuf<RootRec> rootrecs;
     DevBuf<HitRec> hits;
     DevBuf<FeatRec> unc;        // pipeline 1: features the fast path could not settle
-    int pipeline = 1;           // 1 = fast path first (k_fast + k_exact + k_emit), 0 = staged (k_roots + k_contact)
+    bool seg_records = false;   // pipeline 2: the pending records already sit in per-point segments (offs valid)
+    int pipeline = 1;           // 1 = fast path first (k_fast + k_exact + k_emit), 0 = staged (k_roots + k_contact),
+                                // 2 = 1 + records emitted into per-point segments (experimental)
     DevBuf<PointRec> prec, prec_sorted;
     DevBuf<BodyRec> brec;
     DevBuf<Contact> contacts;
@@ -901,7 +933,7 @@ extern "C" int clsn_create(clsn_ctx** out, int device)
     c->prm = p;
     if (const char* e = getenv("CLSN_PIPELINE")) {
         const int v = atoi(e);
-        if (v == 0 || v == 1) c->pipeline = v;
+        if (v >= 0 && v <= 2) c->pipeline = v;
     }
     *out = c;
     return CLSN_OK;
@@ -968,7 +1000,7 @@ extern "C" int clsn_set_exact_stats(clsn_ctx* c, int on)
 
 extern "C" int clsn_set_pipeline(clsn_ctx* c, int pipeline)
 {
-    if (!c || (pipeline != 0 && pipeline != 1)) return CLSN_E_ARG;
+    if (!c || pipeline < 0 || pipeline > 2) return CLSN_E_ARG;
     c->pipeline = pipeline;
     return CLSN_OK;
 }
@@ -1039,7 +1071,7 @@ extern "C" int clsn_set_topology(clsn_ctx* c, int V, int T, const int32_t* tri_i
     if (c->pairs.n == 0) CK(c->pairs.reserve((size_t)16 * n1 + 1024));
     if (c->feats.n == 0) CK(c->feats.reserve((size_t)64 * n1 + 1024));
     if (c->pipeline == 0 && c->rootrecs.n == 0) CK(c->rootrecs.reserve((size_t)16 * n1 + 1024));
-    if (c->pipeline == 1 && c->hits.n == 0) CK(c->hits.reserve((size_t)4 * n1 + 1024));
+    if (c->pipeline >= 1 && c->hits.n == 0) CK(c->hits.reserve((size_t)4 * n1 + 1024));
     CK(c->pair_hit.reserve(c->pairs.n / 32 + 2));
     if (c->prec.n == 0) CK(c->prec.reserve((size_t)8 * n1 + 1024));
     CK(c->perm.reserve(c->prec.n)); CK(c->perm_sorted.reserve(c->prec.n)); CK(c->skey.reserve(c->prec.n));
@@ -1220,7 +1252,9 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
         const long long hit_words = (long long)(c->pairs.n / 32 + 1);
         CK(cudaMemsetAsync(c->pair_hit.p, 0, (size_t)hit_words * sizeof(unsigned), c->stream));
         const int grid = c->sm_count * NARROW_GRID_MULT;
-        const bool fused = c->pipeline == 1;
+        const bool fused = c->pipeline >= 1;
+        // segments only where this context reduces its own records (multi-GPU ranks exchange the plain list)
+        const bool seg = moving && c->pipeline == 2 && c->nranks == 1;
         if (moving) {
             if (fused && c->hits.n == 0) CK(c->hits.reserve((size_t)4 * N + 1024));
             if (fused && c->unc.n == 0) CK(c->unc.reserve((size_t)4 * N + 1024));
@@ -1238,10 +1272,25 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
                 k_exact<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->unc.p, (long long)c->unc.n, c->xo.p, c->av.p, P, E, c->hits.p,
                                                                      (long long)c->hits.n);
                 mark(c, PH_ROOTS);
-                k_emit<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p,
-                                                                     c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
-                k_emit<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p,
-                                                                    c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+                if (seg) {
+                    // per-point record counts of the hit list -> segment offsets -> records written in place
+                    k_count_hits<false><<<grid, 256, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->vflags.p, c->cnt.p, c->counters.p);
+                    k_count_hits<true><<<grid, 256, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->vflags.p, c->cnt.p, c->counters.p);
+                    size_t tmp = c->cub_tmp.n;
+                    CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->cnt.p, c->offs.p, V + 1, c->stream));
+                    CK(cudaMemsetAsync(c->fill.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
+                    const SegOut S{c->offs.p, c->fill.p};
+                    k_emit<false, true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p,
+                                                                               c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p, S);
+                    k_emit<true, true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p,
+                                                                              c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p, S);
+                    c->launches += 4;
+                } else {
+                    k_emit<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p,
+                                                                         c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+                    k_emit<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p,
+                                                                        c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+                }
             } else {
                 k_roots<<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P.dt, c->rootrecs.p,
                                                                (long long)c->rootrecs.n, c->counters.p);
@@ -1311,6 +1360,7 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, in
         c->n_dbg_cand = (long long)h[CTR_DBG_CAND];
         c->n_contacts = (long long)h[CTR_CONTACTS];
         c->records_pending = true;
+        c->seg_records = seg;
         c->imp_nprec = -1;
         c->last_detect_mode = mode;
         c->dirty_valid = false;  // becomes valid again once these records have been applied
@@ -1354,20 +1404,28 @@ static int reduce_records(clsn_ctx* c, int mode, int what = 3)  // what: bit 0 p
             CK(c->perm.reserve((size_t)nprec)); CK(c->perm_sorted.reserve((size_t)nprec)); CK(c->skey.reserve((size_t)nprec));
         }
     }
+    const bool seg = c->seg_records && c->imp_nprec < 0;   // records already grouped per point by k_emit<., true>
     if (nprec > 0 && (what & 1)) {
-        size_t tmp = c->cub_tmp.n;
-        CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->cnt.p, c->offs.p, V + 1, c->stream));
-        CK(cudaMemsetAsync(c->fill.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
-        const long long cap = c->imp_nprec >= 0 ? nprec : (long long)c->prec.n;
-        k_scatter<<<c->sm_count * 8, 256, 0, c->stream>>>(prec, n_prec_dev, cap, c->offs.p, c->fill.p, c->perm.p, c->skey.p);
+        if (!seg) {
+            size_t tmp = c->cub_tmp.n;
+            CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->cnt.p, c->offs.p, V + 1, c->stream));
+            CK(cudaMemsetAsync(c->fill.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
+            const long long cap = c->imp_nprec >= 0 ? nprec : (long long)c->prec.n;
+            k_scatter<<<c->sm_count * 8, 256, 0, c->stream>>>(prec, n_prec_dev, cap, c->offs.p, c->fill.p, c->perm.p, c->skey.p);
+        }
         if (mode == 1) {
             CK(c->acc_imp.reserve(3 * (size_t)V)); CK(c->acc_fric.reserve(3 * (size_t)V));
             CK(cudaMemsetAsync(c->acc_imp.p, 0, 3 * (size_t)V * sizeof(double), c->stream));
             CK(cudaMemsetAsync(c->acc_fric.p, 0, 3 * (size_t)V * sizeof(double), c->stream));
         }
-        k_reduce_points<<<c->sm_count * 8, 256, 0, c->stream>>>(prec, c->offs.p, c->cnt.p, V, c->perm.p, c->perm_sorted.p, c->skey.p,
-                                                                  c->vflags.p, c->av.p, c->has.p, c->dirty.p, mode, c->acc_imp.p,
-                                                                  c->acc_fric.p, c->counters.p);
+        if (seg)
+            k_reduce_points<true><<<c->sm_count * 8, 256, 0, c->stream>>>(prec, c->offs.p, c->cnt.p, V, c->perm.p, c->perm_sorted.p,
+                                                                            c->skey.p, c->vflags.p, c->av.p, c->has.p, c->dirty.p, mode,
+                                                                            c->acc_imp.p, c->acc_fric.p, c->counters.p);
+        else
+            k_reduce_points<false><<<c->sm_count * 8, 256, 0, c->stream>>>(prec, c->offs.p, c->cnt.p, V, c->perm.p, c->perm_sorted.p,
+                                                                             c->skey.p, c->vflags.p, c->av.p, c->has.p, c->dirty.p, mode,
+                                                                             c->acc_imp.p, c->acc_fric.p, c->counters.p);
         c->launches += 2 + 2;  // scan (init + scan), scatter, reduce
     } else if (mode == 1 && (what & 1)) {
         CK(c->acc_imp.reserve(3 * (size_t)V)); CK(c->acc_fric.reserve(3 * (size_t)V));

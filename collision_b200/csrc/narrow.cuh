@@ -136,6 +136,28 @@ __device__ __forceinline__ void store_prec(PointRec* dst, unsigned long long key
     dd[3] = make_double2(fric[1], fric[2]);
 }
 
+// Where an impulse record goes.  SEG = false: appended to the pass's record list (slot from reserve()), counted per
+// point in E.cnt -- the reduction then groups the list with a counting sort.  SEG = true (pipeline 2): the per-point
+// counts are known before emission (k_count_hits), so the record is written straight into its point's segment
+// [offs[p], offs[p] + cnt[p]) of the same buffer; no grouping pass is needed afterwards.
+struct SegOut {
+    const int* offs;
+    int* fill;
+};
+template <bool SEG>
+__device__ __forceinline__ void put_prec(const Emit& E, const SegOut& S, unsigned long long& slot, unsigned long long key, int point,
+                                         const double* imp, const double* fric)
+{
+    if (SEG) {
+        const long long s = (long long)S.offs[point] + atomicAdd(&S.fill[point], 1);
+        if (s < E.cap_prec) store_prec(E.prec + s, key, point, imp, fric);
+    } else {
+        atomicAdd(&E.cnt[point], 1);
+        if ((long long)slot < E.cap_prec) store_prec(E.prec + slot, key, point, imp, fric);
+        ++slot;
+    }
+}
+
 __device__ __noinline__ void emit_contact(const Emit& E, int4 ids, unsigned long long key, int kind, double root,
                                           double dist, double n0, double n1, double n2, double w0, double w1, double w2)
 {
@@ -168,7 +190,8 @@ __device__ __forceinline__ void emit_body(const Emit& E, unsigned long long key,
 }
 
 // PointToTriImpulse, dcollid3d.cpp:925-1107.  q: 0..2 triangle, 3 point.  w is modified as in the reference.
-__device__ __forceinline__ void point_to_tri_impulse(const NarrowParams& P, const Emit& E, const Quad& q,
+template <bool SEG>
+__device__ __forceinline__ void point_to_tri_impulse(const NarrowParams& P, const Emit& E, const SegOut& S, const Quad& q,
                                                       unsigned long long key, const double* nor, double* w, double dist)
 {
     double v_rel[3] = {0.0, 0.0, 0.0}, vn, vt;
@@ -228,7 +251,7 @@ __device__ __forceinline__ void point_to_tri_impulse(const NarrowParams& P, cons
     int n = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) n += q_static(q, i) ? 0 : 1;
-    unsigned long long slot = reserve(&E.counters[CTR_PREC], n);
+    unsigned long long slot = SEG ? 0ull : reserve(&E.counters[CTR_PREC], n);
     const bool has_fric = fabs(vt) > CLSN_ROUND_EPS;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -241,9 +264,7 @@ __device__ __forceinline__ void point_to_tri_impulse(const NarrowParams& P, cons
             imp[j] = w[i] * t_impulse * nor[j];
             fric[j] = has_fric ? stdmax(-fabs(lambda * w[i] * t_impulse / vt), -1.0) * (v_rel[j] - vn * nor[j]) : 0.0;
         }
-        atomicAdd(&E.cnt[q.id[i]], 1);
-        if ((long long)slot < E.cap_prec) store_prec(E.prec + slot, key, q.id[i], imp, fric);
-        ++slot;
+        put_prec<SEG>(E, S, slot, key, q.id[i], imp, fric);
     }
     if (!q_static(q, 3)) {
         double t_impulse = m_impulse;
@@ -255,13 +276,13 @@ __device__ __forceinline__ void point_to_tri_impulse(const NarrowParams& P, cons
             imp[j] = -(t_impulse * nor[j]);
             fric[j] = has_fric ? stdmax(-fabs(lambda * t_impulse / vt), -1.0) * (v_rel[j] - vn * nor[j]) : 0.0;
         }
-        atomicAdd(&E.cnt[q.id[3]], 1);
-        if ((long long)slot < E.cap_prec) store_prec(E.prec + slot, key, q.id[3], imp, fric);
+        put_prec<SEG>(E, S, slot, key, q.id[3], imp, fric);
     }
 }
 
 // EdgeToEdgeImpulse, dcollid3d.cpp:1109-1300.  q: edge 0-1 against edge 2-3.
-__device__ __forceinline__ void edge_to_edge_impulse(const NarrowParams& P, const Emit& E, const Quad& q,
+template <bool SEG>
+__device__ __forceinline__ void edge_to_edge_impulse(const NarrowParams& P, const Emit& E, const SegOut& S, const Quad& q,
                                                       unsigned long long key, const double* nor, double a, double b, double dist)
 {
     double v_rel[3], vn, vt;
@@ -315,7 +336,7 @@ __device__ __forceinline__ void edge_to_edge_impulse(const NarrowParams& P, cons
     int n = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) n += q_static(q, i) ? 0 : 1;
-    unsigned long long slot = reserve(&E.counters[CTR_PREC], n);
+    unsigned long long slot = SEG ? 0ull : reserve(&E.counters[CTR_PREC], n);
     const bool has_fric = fabs(vt) > CLSN_ROUND_EPS;
     const double wgt[4] = {wa0, wa1, wb0, wb1};
 #pragma unroll
@@ -330,18 +351,16 @@ __device__ __forceinline__ void edge_to_edge_impulse(const NarrowParams& P, cons
             imp[j] = (i < 2) ? t : -t;
             fric[j] = has_fric ? stdmax(-fabs(lambda * wgt[i] * t_impulse / vt), -1.0) * (v_rel[j] - vn * nor[j]) : 0.0;
         }
-        atomicAdd(&E.cnt[q.id[i]], 1);
-        if ((long long)slot < E.cap_prec) store_prec(E.prec + slot, key, q.id[i], imp, fric);
-        ++slot;
+        put_prec<SEG>(E, S, slot, key, q.id[i], imp, fric);
     }
 }
 
 // PointToTri, dcollid3d.cpp:778-922.  X = positions at test time.
 // EMIT = false: decision only (no records, no counters) -- used to find the first hit of a feature;
 // EMIT = true: the same arithmetic followed by the contact record and the impulse.
-template <bool EMIT>
+template <bool EMIT, bool SEG = false>
 __device__ __forceinline__ bool point_to_tri(const NarrowParams& P, const Emit& E, const Quad& q, unsigned long long key,
-                                              const double X[4][3], double h, double root)
+                                              const double X[4][3], double h, double root, const SegOut& S = SegOut{nullptr, nullptr})
 {
     double w[3];
     double x13[3], x23[3], x43[3], nor[3], nor_mag, dist, det;
@@ -390,15 +409,15 @@ __device__ __forceinline__ bool point_to_tri(const NarrowParams& P, const Emit& 
         if (w[i] > 1 + P.eps || w[i] < -P.eps) return false;
     if (EMIT) {
         emit_contact(E, make_int4(q.id[0], q.id[1], q.id[2], q.id[3]), key, 0, root, dist, nor[0], nor[1], nor[2], w[0], w[1], w[2]);
-        point_to_tri_impulse(P, E, q, key, nor, w, dist);
+        point_to_tri_impulse<SEG>(P, E, S, q, key, nor, w, dist);
     }
     return true;
 }
 
 // EdgeToEdge, dcollid3d.cpp:643-776
-template <bool EMIT>
+template <bool EMIT, bool SEG = false>
 __device__ __forceinline__ bool edge_to_edge(const NarrowParams& P, const Emit& E, const Quad& q, unsigned long long key,
-                                              const double X[4][3], double h, double root)
+                                              const double X[4][3], double h, double root, const SegOut& S = SegOut{nullptr, nullptr})
 {
     double x21[3], x43[3], x31[3], tmp[3], v1[3], v2[3], nor[3], nor_mag, dist, a, b;
     sub3(X[1], X[0], x21);
@@ -443,7 +462,7 @@ __device__ __forceinline__ bool edge_to_edge(const NarrowParams& P, const Emit& 
     for (int i = 0; i < 3; ++i) nor[i] /= nor_mag;
     if (EMIT) {
         emit_contact(E, make_int4(q.id[0], q.id[1], q.id[2], q.id[3]), key, 1, root, dist, nor[0], nor[1], nor[2], a, b, 0.0);
-        edge_to_edge_impulse(P, E, q, key, nor, a, b, dist);
+        edge_to_edge_impulse<SEG>(P, E, S, q, key, nor, a, b, dist);
     }
     return true;
 }
@@ -482,14 +501,14 @@ __device__ __forceinline__ double feature_first_hit(const NarrowParams& P, const
     return -1.0;
 }
 
-template <bool MOVING>
+template <bool MOVING, bool SEG = false>
 __device__ __forceinline__ void feature_emit(const NarrowParams& P, const Emit& E, const Quad& q, unsigned long long key, bool edge,
-                                             double h, double t)
+                                             double h, double t, const SegOut& S = SegOut{nullptr, nullptr})
 {
     double X[4][3];
     positions_at<MOVING>(q, t, X);
-    if (edge) edge_to_edge<true>(P, E, q, key, X, h, t);
-    else point_to_tri<true>(P, E, q, key, X, h, t);
+    if (edge) edge_to_edge<true, SEG>(P, E, q, key, X, h, t, S);
+    else point_to_tri<true, SEG>(P, E, q, key, X, h, t, S);
 }
 
 } // namespace clsn

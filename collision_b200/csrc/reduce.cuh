@@ -85,6 +85,7 @@ __global__ void k_owner_scatter(const PointRec* __restrict__ rec, long long n, i
 // One warp per point.  Rank the point's keys (all-pairs compare, keys are unique), store the
 // records in rank order, then lanes 0..5 each sum one of imp.xyz / fric.xyz sequentially.
 // mode 0: apply to avgVel (updateAverageVelocity :707-724); mode 1: write the sums to acc arrays.
+template <bool SEG>
 __global__ void __launch_bounds__(256)
 k_reduce_points(const PointRec* __restrict__ rec, const int* __restrict__ offs, const int* __restrict__ cnt, int V,
                 const int* __restrict__ perm, int* __restrict__ perm_sorted, const unsigned long long* __restrict__ skey,
@@ -99,10 +100,11 @@ k_reduce_points(const PointRec* __restrict__ rec, const int* __restrict__ offs, 
         const int base = offs[p];
         // rank = number of smaller keys
         for (int t = lane; t < n; t += 32) {
-            const unsigned long long k = skey[base + t];
+            // SEG: the point's records are the contiguous segment rec[base .. base + n) (written there by k_emit<., true>)
+            const unsigned long long k = SEG ? rec[base + t].key : skey[base + t];
             int rank = 0;
-            for (int u = 0; u < n; ++u) rank += skey[base + u] < k ? 1 : 0;
-            perm_sorted[base + rank] = perm[base + t];
+            for (int u = 0; u < n; ++u) rank += (SEG ? rec[base + u].key : skey[base + u]) < k ? 1 : 0;
+            perm_sorted[base + rank] = SEG ? base + t : perm[base + t];
         }
         __syncwarp();
         double sum = 0.0;

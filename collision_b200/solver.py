@@ -419,7 +419,8 @@ class CollisionSolver3d:
 
     def set_pipeline(self, pipeline: int):
         """1: plain-FP64 fast path, correctly rounded solve of the undecided features only (default);
-        0: staged correctly rounded solve of every feature.  Same results."""
+        0: staged correctly rounded solve of every feature; 2: experimental, 1 + impulse records emitted straight into
+        per-point segments.  Same results."""
         self.ctx.check(self.ctx.L.clsn_set_pipeline(self.ctx.h, int(pipeline)))
 
     def candidates(self):

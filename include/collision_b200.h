@@ -204,7 +204,10 @@ int clsn_set_exact_stats(clsn_ctx*, int on);
  * roots -- the outcome is then the static test at t = dt -- and only the rest gets the correctly rounded cubic
  * solve (k_exact); k_emit writes the records of the hit list.  0: staged -- correctly rounded solve of every
  * feature (k_roots), then the static tests and the records (k_contact); kept for A/B measurements.
- * Results are bit-identical.  The environment variable CLSN_PIPELINE=0|1 sets the default of new contexts. */
+ * 2 (experimental, not yet measured on a B200): like 1, but the per-point record counts are taken from the hit list
+ * first, so that k_emit writes every impulse record straight into its point's segment and the reduction needs no
+ * grouping pass (single-GPU contexts only; ranks of a multi-GPU run keep exchanging the plain record list).
+ * Results are bit-identical.  The environment variable CLSN_PIPELINE=0|1|2 sets the default of new contexts. */
 int clsn_set_pipeline(clsn_ctx*, int pipeline);
 int64_t clsn_num_candidates(clsn_ctx*);
 int clsn_get_candidates(clsn_ctx*, int32_t* pairs /* 2 per pair, unsorted */);
