@@ -238,3 +238,34 @@ def test_feature_slot_arithmetic_matches_the_tables():
     subprocess.check_call(["g++", "-O1", "/tmp/clsn_slots.cpp", "-o", "/tmp/clsn_slots"])
     out = [list(map(int, ln.split())) for ln in subprocess.check_output(["/tmp/clsn_slots"], text=True).strip().splitlines()]
     assert out == tm + ts + tb + tb + [[0, 1, 3, 4]]
+
+
+def test_vtk_dump_mirrors_the_reference_layout(tmp_path):
+    """collision_b200/vtkdump.py (vtk.cpp:14-93): points numbered by first appearance in
+    hseList, CollsnImpulse point vectors, cells red where a point collected an impulse -- parsed back from the file."""
+    import xml.etree.ElementTree as ET
+    from collision_b200 import scenes, vtkdump
+    sc = scenes.mixed()
+    rng = np.random.default_rng(5)
+    imp = np.zeros((sc.V, 3))
+    cnt = np.zeros(sc.V, np.int32)
+    hit = rng.choice(sc.V, 40, replace=False)
+    imp[hit] = rng.normal(size=(40, 3))
+    cnt[hit] = rng.integers(1, 5, 40)
+    f = str(tmp_path / "collsn.vtp")
+    info = vtkdump.vtkplotVectorSurface(f, sc.x, sc.tri_idx, sc.bond_idx, imp, cnt)
+    order = vtkdump.point_order(sc.tri_idx, sc.bond_idx)
+    assert order[:3].tolist() == sc.tri_idx[0].tolist() and len(set(order.tolist())) == order.size
+    assert info == {"points": order.size, "cells": sc.T + sc.B}
+    piece = ET.parse(f).getroot().find("PolyData/Piece")
+    assert int(piece.get("NumberOfPolys")) == sc.T and int(piece.get("NumberOfLines")) == sc.B
+    arr = lambda e: np.array(e.text.split(), dtype=np.float64)
+    pts = arr(piece.find("Points/DataArray")).reshape(-1, 3)
+    assert np.allclose(pts, sc.x[order], rtol=1e-7)
+    vec = arr(piece.find("PointData/DataArray")).reshape(-1, 3)
+    assert np.allclose(vec, imp[order], rtol=1e-7)
+    conn = arr(piece.find("Polys/DataArray[@Name='connectivity']")).astype(int).reshape(-1, 3)
+    assert np.array_equal(order[conn], sc.tri_idx)
+    col = arr(piece.find("CellData/DataArray")).astype(int).reshape(-1, 3)
+    red_tris = (cnt[sc.tri_idx] > 0).any(axis=1)
+    assert np.array_equal(col[sc.B:, 0] == 255, red_tris) and np.array_equal(col[sc.B:, 1] == 255, ~red_tris)
