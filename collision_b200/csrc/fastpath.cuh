@@ -24,7 +24,7 @@
 //                   switches are "uncertain" inside that band.
 //   quadratic / linear branches use IEEE operations only: tol = 0, roots identical.
 // A root at distance > tol from 0, MACH_EPS and dt is classified like the reference's.  The static test at
-// the approximate time sees every point moved by at most delta = tol * max|avgVel| + 2.3e-16 * max|x|;
+// the approximate time sees every point moved by at most delta = tol * max|avgVel| + 4 MACH_EPS * max|x|;
 // the barycentric coordinates (a, b of the edge pair) are the solution of a 2x2 least-squares system
 // whose perturbation bound is  err = 16 eta (P + L (1 + |w0| + |w1|)) / (l^2 sin^2)  with eta = 4 delta + 32 u L,
 // L / l the longer / shorter edge, P the length of the right-hand side, sin^2 = det / (G11 G22)
