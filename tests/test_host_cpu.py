@@ -155,7 +155,7 @@ def test_ccd_fast_path_is_conservative_on_host():
     for the host with a libm perturbed by up to +-4 ulp per call, fuzzed against the oracle's
     MovingPointToTri / MovingEdgeToEdge (correctly rounded libm): FAST_MISS only where the oracle's isCoplanar is
     false, FAST_DT_ONLY only where it is true and nothing fires before t = dt.  Half of the cases sit on the
-    accept/reject boundary of the static tests.  (40 M cases were run once by hand.)"""
+    accept/reject boundary of the static tests.  (190 M cases were run once by hand.)"""
     so, exe, _ = _build_fastpath_check()
     n, wrong, n_miss, n_dt, n_unc, hits, hits_root = map(int, subprocess.check_output([exe, so, "1500000", "3"], text=True).split())
     assert n == 1500000 and wrong == 0
