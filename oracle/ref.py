@@ -13,6 +13,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libcollision_ref.so")
+# the same reference objects linked against a correctly rounded acos/cos/sin/pow (oracle/cr_libm.c, oracle/Makefile)
+LIB_PATH_CR = os.path.join(_HERE, "_ref", "libcollision_ref_cr.so")
+LIBM_NATIVE, LIBM_CR = "native", "cr"
 
 F_X_OLD, F_COORDS, F_VEL, F_AVGVEL, F_IMP, F_FRIC, F_IMP_RG = range(7)
 I_CNT, I_CNT_RG, I_HAS_COLLSN = range(3)
@@ -21,11 +24,20 @@ I_CNT, I_CNT_RG, I_HAS_COLLSN = range(3)
  PH_IMPZONE_ON, PH_IMPZONE_OFF, PH_ZONE_VELOCITY, PH_COMPUTE_IMPACT_ZONE) = range(14)
 K_ISCOPLANAR, K_POINT_TO_TRI, K_EDGE_TO_EDGE, K_MOVING_POINT_TO_TRI, K_MOVING_EDGE_TO_EDGE = range(5)
 
-_lib = None
+_libs = {}
+_flavour = LIBM_NATIVE
 
 
-def available() -> bool:
-    return os.path.exists(LIB_PATH)
+def available(flavour: str = LIBM_NATIVE) -> bool:
+    return os.path.exists(LIB_PATH_CR if flavour == LIBM_CR else LIB_PATH)
+
+
+def set_libm(flavour: str):
+    """Which build RefSolver() / feature() use from now on: LIBM_NATIVE = the host libm, exactly as the reference
+    ships; LIBM_CR = the same objects with a correctly rounded libm bound in (what the CUDA path is held to)."""
+    global _flavour
+    assert flavour in (LIBM_NATIVE, LIBM_CR)
+    _flavour = flavour
 
 
 def _dp(a):
@@ -40,10 +52,10 @@ def _bp(a):
     return a.ctypes.data_as(C.POINTER(C.c_ubyte))
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        L = C.CDLL(LIB_PATH)
+def lib(flavour: str | None = None):
+    flavour = flavour or _flavour
+    if flavour not in _libs:
+        L = C.CDLL(LIB_PATH_CR if flavour == LIBM_CR else LIB_PATH)
         L.clsn_ref_create.restype = C.c_void_p
         L.clsn_ref_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
                                       C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
@@ -74,15 +86,21 @@ def lib():
                                        C.POINTER(C.c_double), C.POINTER(C.c_ubyte), C.POINTER(C.c_double),
                                        C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_double), C.POINTER(C.c_double)]
-        _lib = L
-    return _lib
+        L.clsn_ref_clock_reset.argtypes = []
+        L.clsn_ref_feature_batch.restype = C.c_long
+        L.clsn_ref_feature_batch.argtypes = [C.c_long, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                             C.POINTER(C.c_double), C.POINTER(C.c_ubyte), C.POINTER(C.c_double),
+                                             C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int),
+                                             C.POINTER(C.c_double)]
+        _libs[flavour] = L
+    return _libs[flavour]
 
 
 class RefSolver:
     """The reference's CollisionSolver3d driven on a collision_b200.scenes.Scene."""
 
     def __init__(self, scene):
-        L = lib()
+        L = self.L = lib()
         self.scene = scene
         self.V, self.T, self.B = scene.V, scene.T, scene.B
         self._keep = [np.ascontiguousarray(a) for a in (
@@ -101,7 +119,7 @@ class RefSolver:
 
     def close(self):
         if self.h:
-            lib().clsn_ref_destroy(self.h)
+            self.L.clsn_ref_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -115,58 +133,58 @@ class RefSolver:
         x_old = np.ascontiguousarray(x_old, dtype=np.float64)
         x_new = np.ascontiguousarray(x_new, dtype=np.float64)
         v = None if vel is None else np.ascontiguousarray(vel, dtype=np.float64)
-        lib().clsn_ref_set_state(self.h, _dp(x_old), _dp(x_new), None if v is None else _dp(v))
+        self.L.clsn_ref_set_state(self.h, _dp(x_old), _dp(x_new), None if v is None else _dp(v))
 
     def set_rest_lengths(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
-        lib().clsn_ref_set_rest_lengths(self.h, _dp(x))
+        self.L.clsn_ref_set_rest_lengths(self.h, _dp(x))
 
     def get(self, field) -> np.ndarray:
         out = np.empty((self.V, 3), dtype=np.float64)
-        lib().clsn_ref_get_f64(self.h, field, _dp(out))
+        self.L.clsn_ref_get_f64(self.h, field, _dp(out))
         return out
 
     def put(self, field, a):
         a = np.ascontiguousarray(a, dtype=np.float64)
-        lib().clsn_ref_set_f64(self.h, field, _dp(a))
+        self.L.clsn_ref_set_f64(self.h, field, _dp(a))
 
     def geti(self, field) -> np.ndarray:
         out = np.empty(self.V, dtype=np.int32)
-        lib().clsn_ref_get_i32(self.h, field, _ip(out))
+        self.L.clsn_ref_get_i32(self.h, field, _ip(out))
         return out
 
     def puti(self, field, a):
         a = np.ascontiguousarray(a, dtype=np.int32)
-        lib().clsn_ref_set_i32(self.h, field, _ip(a))
+        self.L.clsn_ref_set_i32(self.h, field, _ip(a))
 
     # ---- driving
     def assemble(self, dt):
-        if lib().clsn_ref_assemble(self.h, float(dt)) != 0:
+        if self.L.clsn_ref_assemble(self.h, float(dt)) != 0:
             raise RuntimeError("reference aborted in assembleFromInterface")
 
     def resolve(self, strain_limiting=False):
-        if lib().clsn_ref_resolve(self.h, 1 if strain_limiting else 0) != 0:
+        if self.L.clsn_ref_resolve(self.h, 1 if strain_limiting else 0) != 0:
             raise RuntimeError("reference aborted (clean_up(ERROR)) in resolveCollision")
 
     def phase(self, ph) -> int:
-        r = lib().clsn_ref_phase(self.h, ph)
+        r = self.L.clsn_ref_phase(self.h, ph)
         if r < 0:
             raise RuntimeError(f"reference aborted in phase {ph}")
         return r
 
     def record(self, on=True):
-        lib().clsn_ref_record(self.h, 1 if on else 0)
+        self.L.clsn_ref_record(self.h, 1 if on else 0)
 
     def pairs(self) -> np.ndarray:
         """(n,3) int32: a, b, result for every narrow-phase callback since record()."""
-        n = lib().clsn_ref_num_pairs(self.h)
+        n = self.L.clsn_ref_num_pairs(self.h)
         out = np.empty((n, 3), dtype=np.int32)
         if n:
-            lib().clsn_ref_get_pairs(self.h, _ip(out))
+            self.L.clsn_ref_get_pairs(self.h, _ip(out))
         return out
 
     def num_callbacks(self) -> int:
-        return int(lib().clsn_ref_num_callbacks(self.h))
+        return int(self.L.clsn_ref_num_callbacks(self.h))
 
 
 def clock(name: str) -> float:
@@ -194,3 +212,24 @@ def feature(kind, x_old, coords, avg_vel, flags, mass, h, dt, params):
     if r < 0:
         raise RuntimeError(f"reference feature call failed ({r})")
     return dict(ret=int(r), roots=roots, acc=acc, hit_root=float(hit.value))
+
+
+def feature_batch(kind, pts, x_old, avg_vel, vflags, vmass, h, dt, params):
+    """n calls of a dcollid3d.cpp primitive: kind[n], pts[n,4] index the per-vertex arrays.  Returns (ret[n], hit_root[n])."""
+    kind = np.ascontiguousarray(kind, dtype=np.int32)
+    pts = np.ascontiguousarray(pts, dtype=np.int32).reshape(-1, 4)
+    n = len(kind)
+    assert pts.shape[0] == n
+    x_old = np.ascontiguousarray(x_old, dtype=np.float64)
+    avg_vel = np.ascontiguousarray(avg_vel, dtype=np.float64)
+    vflags = np.ascontiguousarray(vflags, dtype=np.uint8)
+    vmass = np.ascontiguousarray(vmass, dtype=np.float64)
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(6)
+    ret = np.zeros(n, np.int32)
+    hit = np.full(n, -1.0)
+    if n:
+        lib().clsn_ref_feature_batch(n, _ip(kind), _ip(pts), _dp(x_old), _dp(avg_vel), _bp(vflags), _dp(vmass), float(h),
+                                     float(dt), _dp(params), _ip(ret), _dp(hit))
+    if (ret < 0).any():
+        raise RuntimeError("reference feature call aborted")
+    return ret, hit

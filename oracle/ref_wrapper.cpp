@@ -630,4 +630,30 @@ int clsn_ref_feature(int kind, const double* x_old, const double* coords, const 
     return ret;
 }
 
+/* n calls of clsn_ref_feature in one go (the comparison against the reference's primitives makes ~10^5 of them per
+ * pass): pts[4n] indexes the per-vertex arrays x_old/avgVel[3V], flags[V], mass[V]; Coords = x_old on entry.
+ * ret[n] (negative = that call aborted), hit_root[n]; returns the number of calls that returned true. */
+long clsn_ref_feature_batch(long n, const int* kind, const int* pts, const double* x_old, const double* avgVel,
+                            const unsigned char* flags, const double* mass, double h, double dt, const double* params,
+                            int* ret, double* hit_root)
+{
+    long hits = 0;
+    for (long c = 0; c < n; ++c) {
+        double xo[12], av[12], m[4], roots[4], acc[40];
+        unsigned char fl[4];
+        for (int i = 0; i < 4; ++i) {
+            const int p = pts[4 * c + i];
+            for (int j = 0; j < 3; ++j) {
+                xo[3 * i + j] = x_old[3 * (long)p + j];
+                av[3 * i + j] = avgVel[3 * (long)p + j];
+            }
+            fl[i] = flags[p];
+            m[i] = mass[p];
+        }
+        ret[c] = clsn_ref_feature(kind[c], xo, xo, av, fl, m, h, dt, params, roots, acc, &hit_root[c]);
+        if (ret[c] > 0) ++hits;
+    }
+    return hits;
+}
+
 } /* extern "C" */
