@@ -94,9 +94,9 @@ __host__ __device__ __forceinline__ void feature_slots(int type, int f, int sl[4
 // Work-list records.  They carry the four point ids of the feature test so that the consumer's gathers
 // start right after one record load (no pairs -> elem -> points pointer chase).
 struct FeatRec {  // 24 B
-    unsigned entry;  // pair index | feature << 28
+    unsigned entry;  // index into the pass's pair list (up to 2^32 - 1 pairs)
     int id[4];       // points as passed to PointToTri / EdgeToEdge
-    unsigned edge;   // 1 = edge-edge test, 0 = point-triangle
+    unsigned edge;   // bit 0: 1 = edge-edge test, 0 = point-triangle; bits 1..4: feature index inside the pair
 };
 struct RootRec {  // 48 B: a feature whose coplanarity cubic has a usable root
     FeatRec f;
@@ -142,7 +142,7 @@ __device__ __forceinline__ bool boxes_far(const FBox& a, const FBox& b, float h2
 // box survivors of the warp's 32 pairs are pooled and dealt out evenly to the 32 lanes (the six points
 // of every pair are staged in shared memory, one row per pair), each lane computes the coefficients of
 // the coplanarity cubic and runs the trig-free classifier coplanar_maybe().  Features that can still
-// fire are appended to the work list as (pair index | feature << 28).
+// fire are appended to the work list (FeatRec: pair index, the four points, test kind | feature index).
 #ifndef CULL_MIN_BLOCKS
 #define CULL_MIN_BLOCKS 4
 #endif
@@ -337,9 +337,9 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
                         const long long slot = isb ? (long long)base_b + run_b + __popc(bb & lt) : (long long)base_f + run_f + __popc(fb & lt);
                         if (slot < cap_feats) {
                             uint2* dst = reinterpret_cast<uint2*>(feats + (isb ? cap_feats - 1 - slot : slot));
-                            dst[0] = make_uint2((unsigned)(base + wb + o) | ((unsigned)f << 28), (unsigned)s_id[wb + o][sl[0]]);
+                            dst[0] = make_uint2((unsigned)(base + wb + o), (unsigned)s_id[wb + o][sl[0]]);
                             dst[1] = make_uint2((unsigned)s_id[wb + o][sl[1]], (unsigned)s_id[wb + o][sl[2]]);
-                            dst[2] = make_uint2((unsigned)s_id[wb + o][sl[3]], edge);
+                            dst[2] = make_uint2((unsigned)s_id[wb + o][sl[3]], edge | ((unsigned)f << 1));
                         }
                     }
                     run_f += __popc(fb);
@@ -388,7 +388,7 @@ k_roots(const FeatRec* __restrict__ feats, long long cap_feats, const Vec4* __re
         }
         double roots[3] = {-1, -1, -1};
         if (!is_coplanar<false>(q, dt, roots)) continue;
-        const bool ee = fr.edge != 0;
+        const bool ee = (fr.edge & 1u) != 0;
         // reserve() aggregates the converged lanes onto ONE counter, so the two kinds reserve separately
         long long slot = 0;
         if (ee) slot = (long long)reserve1(&counters[CTR_ROOTS_EE]);
@@ -462,7 +462,7 @@ k_contact(const FeatRec* __restrict__ feats, const RootRec* __restrict__ rootrec
             Quad q;
             double r0, r1, r2;
             load_contact_item<MOVING>(feats, rootrecs, at, xo, av, vflags, fr, q, r0, r1, r2);
-            const double th = feature_first_hit<MOVING>(P, E, q, fr.edge != 0, h, r0, r1, r2);
+            const double th = feature_first_hit<MOVING>(P, E, q, (fr.edge & 1u) != 0, h, r0, r1, r2);
             if (th >= 0) {
                 const int pos = atomicAdd(&s_n[w], 1);
                 s_at[w][pos] = at;
@@ -486,12 +486,12 @@ k_contact(const FeatRec* __restrict__ feats, const RootRec* __restrict__ rootrec
 #pragma unroll
                     for (int i = 0; i < 4; ++i) q.body[i] = __ldg(vbody + q.id[i]);
                 }
-                const unsigned pi = fr.entry & 0x0fffffffu;
-                const int f = (int)(fr.entry >> 28);
+                const unsigned pi = fr.entry;
+                const int f = (int)(fr.edge >> 1);
                 const int2 pr = __ldg(pairs + pi);
                 const unsigned long long key = ((unsigned long long)(unsigned)pr.x << 34) | ((unsigned long long)(unsigned)pr.y << 4) |
                                                (unsigned long long)f;
-                feature_emit<MOVING>(P, E, q, key, fr.edge != 0, h, th);
+                feature_emit<MOVING>(P, E, q, key, (fr.edge & 1u) != 0, h, th);
                 atomicOr(pair_hit + (pi >> 5), 1u << (pi & 31));
             }
             nq = base;
@@ -541,7 +541,7 @@ __device__ __forceinline__ void store_featrec(FeatRec* dst, const FeatRec& fr)
 __device__ __forceinline__ void push_hit(HitRec* __restrict__ hits, long long cap_hits, unsigned long long* counters, const FeatRec& fr,
                                          double t)
 {
-    const bool ee = fr.edge != 0;
+    const bool ee = (fr.edge & 1u) != 0;
     long long slot;
     if (ee) slot = (long long)reserve1(&counters[CTR_HITS_EE]);
     else slot = (long long)reserve1(&counters[CTR_HITS]);
@@ -741,8 +741,8 @@ k_emit(const HitRec* __restrict__ hits, long long cap_hits, const int2* __restri
 #pragma unroll
             for (int i = 0; i < 4; ++i) q.body[i] = __ldg(vbody + q.id[i]);
         }
-        const unsigned pi = fr.entry & 0x0fffffffu;
-        const int f = (int)(fr.entry >> 28);
+        const unsigned pi = fr.entry;
+        const int f = (int)(fr.edge >> 1);
         const int2 pr = __ldg(pairs + pi);
         const unsigned long long key = ((unsigned long long)(unsigned)pr.x << 34) | ((unsigned long long)(unsigned)pr.y << 4) |
                                        (unsigned long long)f;
@@ -817,17 +817,28 @@ struct clsn_ctx {
     bool dirty_valid = false;   // dirty[] describes exactly the change between the last two CCD passes
     bool exact_stats = false;   // count every overlapping pair in `candidates` even where the query could be pruned
     int last_detect_mode = -1;
-    DevBuf<double> imp_rg;
+    DevBuf<double> imp_rg, imp_rg_keep;   // keep: start-of-step copy (a step that has to be repeated restores it)
+    DevBuf<Vec4> xf;                      // final positions (x_new stays intact for a repeated step)
+    bool final_valid = false;
+    bool phase_timing = true;             // record CUDA-event marks between kernel groups inside clsn_resolve
     DevBuf<int> cnt_rg;
     DevBuf<double> stage;  // 3V doubles, host<->device staging of packed arrays
     // bvh
     DevBuf<unsigned> code, code_sorted;
-    DevBuf<int> idx, leaf_elem, leaf_parent, flags;
-    DevBuf<WideNode> nodes;
+    DevBuf<int> idx, leaf_elem;
+    DevBuf<int4> selem;             // elem[] in Morton (leaf) order
+    DevBuf<Node8> nodes;
+    DevBuf<float> tree_scratch;     // upper-level ping-pong boxes of k_refit8 + root box (last 8 floats)
+    DevBuf<uint8_t> tree_scratch_t;
+    DevBuf<unsigned> tree_ticket;
+    Tree8 tree;
     DevBuf<double> lbox;
     DevBuf<unsigned long long> bounds;
     DevBuf<unsigned char> cub_tmp;
     bool tree_built = false;
+    bool keep_tree = true;     // reuse the leaf order across steps (CLSN_KEEP_TREE=0: rebuild every step)
+    int tree_age = 0;          // steps refitted since the last build
+    double tree_volume = 0.0;  // volume of the root box at the first refit after the build
     // pass buffers
     DevBuf<int2> pairs, dbg_cand;
     DevBuf<FeatRec> feats;
@@ -845,7 +856,11 @@ struct clsn_ctx {
     DevBuf<unsigned long long> skey;
     DevBuf<unsigned long long> counters;
     DevBuf<double> acc_imp, acc_fric;
-    unsigned long long* h_counters = nullptr;  // pinned
+    unsigned long long* h_counters = nullptr;  // pinned: PASS_SLOTS blocks of CTR_STRIDE counters
+    unsigned long long* ctr = nullptr;         // counter block of the pass being enqueued / applied
+    const unsigned long long* pending_gate = nullptr;  // gate of the pass whose records are pending (see enqueue_detect)
+    long long last_true = 0;
+    bool cnt_rg_preset = false;   // clsn_set_body_accumulators wrote collsn_num_RG (parity tests)
     double* h_pin = nullptr;                   // pinned staging for host arrays (3V doubles x 2)
     size_t h_pin_n = 0;
     // imported record set (multi-GPU)
@@ -924,13 +939,17 @@ extern "C" int clsn_create(clsn_ctx** out, int device)
     for (auto& e : c->ev) cudaEventCreate(&e);
     cudaEventCreate(&c->bracket[0]);
     cudaEventCreate(&c->bracket[1]);
-    cudaMallocHost((void**)&c->h_counters, 64 * sizeof(unsigned long long));
-    c->counters.reserve(256);
+    cudaMallocHost((void**)&c->h_counters, (8 * 32 + 8) * sizeof(unsigned long long));   // + root box of the last refit
+    c->counters.reserve(256 + 8 * 32);
+    cudaMemset(c->counters.p, 0, (256 + 8 * 32) * sizeof(unsigned long long));
+    c->ctr = c->counters.p + 256 + 32 * 7;
     c->bounds.reserve(8);
     clsn_params p;
     p.eps = 1e-6; p.thickness = 1e-4; p.dt = 1e-3; p.k = 1000; p.m = 0.01; p.lambda = 0.02; p.cr = 0.0;
     for (int i = 0; i < 3; ++i) { p.lo[i] = -1e30; p.hi[i] = 1e30; }
     c->prm = p;
+    if (const char* e = getenv("CLSN_KEEP_TREE")) c->keep_tree = atoi(e) != 0;
+    if (const char* e = getenv("CLSN_PHASE_TIMING")) c->phase_timing = atoi(e) != 0;
     if (const char* e = getenv("CLSN_PIPELINE")) {
         const int v = atoi(e);
         if (v >= 0 && v <= 2) c->pipeline = v;
@@ -945,9 +964,10 @@ extern "C" void clsn_destroy(clsn_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->elem.release(); c->vflags.release(); c->vbody.release(); c->body_mass.release();
-    c->xo.release(); c->xn.release(); c->av.release(); c->has.release(); c->dirty.release(); c->imp_rg.release(); c->cnt_rg.release();
+    c->xo.release(); c->xn.release(); c->av.release(); c->has.release(); c->dirty.release(); c->imp_rg.release(); c->imp_rg_keep.release(); c->xf.release(); c->cnt_rg.release();
     c->stage.release(); c->code.release(); c->code_sorted.release(); c->idx.release(); c->leaf_elem.release();
-    c->leaf_parent.release(); c->flags.release(); c->nodes.release(); c->lbox.release(); c->bounds.release();
+    c->selem.release(); c->nodes.release(); c->tree_scratch.release(); c->tree_scratch_t.release();
+    c->tree_ticket.release(); c->lbox.release(); c->bounds.release();
     c->cub_tmp.release(); c->pairs.release(); c->dbg_cand.release(); c->feats.release(); c->pair_hit.release(); c->rootrecs.release(); c->hits.release(); c->unc.release(); c->prec.release(); c->prec_sorted.release(); c->brec.release();
     c->contacts.release(); c->cnt.release(); c->offs.release(); c->fill.release(); c->perm.release();
     c->perm_sorted.release(); c->skey.release(); c->counters.release(); c->acc_imp.release(); c->acc_fric.release();
@@ -1052,7 +1072,7 @@ extern "C" int clsn_set_topology(clsn_ctx* c, int V, int T, const int32_t* tri_i
     CK(cudaMemcpy(c->vflags.p, vflags, V, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->vbody.p, vbody, V * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->body_mass.p, body_mass, nbody * sizeof(double), cudaMemcpyHostToDevice));
-    CK(c->xo.reserve(V)); CK(c->xn.reserve(V)); CK(c->av.reserve(V)); CK(c->has.reserve(V)); CK(c->dirty.reserve(V));
+    CK(c->xo.reserve(V)); CK(c->xn.reserve(V)); CK(c->xf.reserve(V)); CK(c->av.reserve(V)); CK(c->has.reserve(V)); CK(c->dirty.reserve(V));
     CK(c->imp_rg.reserve(3 * (size_t)nbody)); CK(c->cnt_rg.reserve(nbody));
     CK(cudaMemset(c->imp_rg.p, 0, 3 * (size_t)nbody * sizeof(double)));
     CK(cudaMemset(c->cnt_rg.p, 0, nbody * sizeof(int)));
@@ -1061,7 +1081,27 @@ extern "C" int clsn_set_topology(clsn_ctx* c, int V, int T, const int32_t* tri_i
     CK(c->stage.reserve(6 * (size_t)V));
     const size_t n1 = (size_t)(N > 0 ? N : 1);
     CK(c->code.reserve(n1)); CK(c->code_sorted.reserve(n1)); CK(c->idx.reserve(n1)); CK(c->leaf_elem.reserve(n1));
-    CK(c->leaf_parent.reserve(n1)); CK(c->flags.reserve(n1)); CK(c->nodes.reserve(n1)); CK(c->lbox.reserve(6 * n1));
+    CK(c->selem.reserve(n1)); CK(c->lbox.reserve(6 * n1));
+    {   // shape of the implicit 8-ary tree: a function of N alone
+        Tree8& tr = c->tree;
+        memset(&tr, 0, sizeof(tr));
+        tr.N = N;
+        tr.cnt[0] = N;
+        int total = 0, l = 0;
+        do {
+            ++l;
+            tr.cnt[l] = (tr.cnt[l - 1] + 7) / 8;
+            if (tr.cnt[l] < 1) tr.cnt[l] = 1;
+            tr.off[l] = total;
+            total += tr.cnt[l];
+        } while ((tr.cnt[l] > 1 || l < 3) && l + 1 < TREE_MAXLEV);
+        tr.nlev = l;
+        CK(c->nodes.reserve((size_t)total));
+        CK(c->tree_scratch.reserve(12 * (size_t)tr.cnt[3] + 16)); CK(c->tree_scratch_t.reserve(2 * (size_t)tr.cnt[3] + 16));
+        CK(c->tree_ticket.reserve(4));
+        CK(cudaMemset(c->tree_ticket.p, 0, 4 * sizeof(unsigned)));
+        tr.nodes = c->nodes.p;
+    }
     size_t tmp1 = 0, tmp2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp1, c->code.p, c->code_sorted.p, c->idx.p, c->leaf_elem.p, N > 0 ? N : 1, 0, 30);
     CK(c->cnt.reserve((size_t)V + 1)); CK(c->offs.reserve((size_t)V + 1)); CK(c->fill.reserve((size_t)V + 1));
@@ -1101,8 +1141,10 @@ static int begin_step(clsn_ctx* c)
     // per-step accumulators cleared as FT_Propagate's point hook / recordOriginPosition do
     // (test.cpp:192-224, dcollid.cpp:100): has_collsn; imp/fric/cnt live only inside a pass here
     CK(cudaMemsetAsync(c->has.p, 0, c->V, c->stream));
-    c->tree_built = false;
+    if (!c->keep_tree || ++c->tree_age >= 64) c->tree_built = false;
+    c->final_valid = false;
     c->records_pending = false;
+    c->pending_gate = nullptr;
     c->dirty_valid = false;
     c->last_detect_mode = -1;
     c->zone_uf_ready = false;  // makeSet: the impact zones live for one step (dcollid3d.cpp:44)
@@ -1135,7 +1177,7 @@ extern "C" int clsn_download_state_device(clsn_ctx* c, double* d_x, double* d_av
 {
     if (!c || !c->V) return CLSN_E_ARG;
     cudaSetDevice(c->device);
-    if (d_x) k_unpack<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->xn.p, d_x);
+    if (d_x) k_unpack<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->final_valid ? c->xf.p : c->xn.p, d_x);
     if (d_avgvel) k_unpack<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->av.p, d_avgvel);
     CK(cudaGetLastError());
     c->launches += (d_x ? 1 : 0) + (d_avgvel ? 1 : 0);
@@ -1173,8 +1215,7 @@ extern "C" int clsn_avg_velocity(clsn_ctx* c)
 {
     if (!c || !c->V) return CLSN_E_ARG;
     cudaSetDevice(c->device);
-    CK(cudaMemsetAsync(c->counters.p, 0, CTR_COUNT * sizeof(unsigned long long), c->stream));
-    k_avg_velocity<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->xo.p, c->xn.p, c->av.p, c->prm.dt, c->counters.p);
+    k_avg_velocity<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->xo.p, c->xn.p, c->av.p, c->prm.dt, c->counters.p + 256 + 32 * 7);
     CK(cudaGetLastError());
     c->launches += 1;
     c->dirty_valid = false;
@@ -1192,178 +1233,231 @@ static int build_tree(clsn_ctx* c)
     k_morton<<<nblk(N, 256), 256, 0, c->stream>>>(c->elem.p, N, c->xo.p, c->bounds.p, c->code.p, c->idx.p);
     size_t tmp = c->cub_tmp.n;
     CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->code.p, c->code_sorted.p, c->idx.p, c->leaf_elem.p, N, 0, 30, c->stream));
-    if (N >= 2) k_hierarchy<<<nblk(N - 1, 256), 256, 0, c->stream>>>(c->code_sorted.p, N, c->nodes.p, c->leaf_parent.p);
+    k_gather_elems<<<nblk(N, 256), 256, 0, c->stream>>>(c->elem.p, c->leaf_elem.p, N, c->selem.p);
     CK(cudaGetLastError());
-    c->launches += 2 + 4 + (N >= 2 ? 1 : 0);  // bounds, morton, radix sort (4 onesweep kernels), hierarchy
+    c->launches += 2 + 4 + 1;  // bounds, morton, radix sort (4 onesweep kernels), element gather
     mark(c, PH_BUILD);
     c->tree_built = true;
+    c->tree_age = 0;
+    c->tree_volume = -1.0;   // set from the first refit's root box
     return CLSN_OK;
 }
 
-static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st, bool timed, int ev_base)
+// Counter blocks.  Every detection pass of a step has its own block of CTR_STRIDE counters, so that a whole step can be
+// enqueued without reading anything back: slot 0 = proximity, 1..5 = CCD passes, PASS_SLOT_SOLO = a pass driven through
+// the per-phase ABI or the impact-zone loop, PASS_SLOT_STEP = step-wide error flags (avgVel, boundary ...).
+#define CTR_STRIDE 32
+#define PASS_SLOTS 8
+#define PASS_SLOT_SOLO 6
+#define PASS_SLOT_STEP 7
+#define CTR_LEGACY 256   // counters.p[0 .. 255]: import / owner-bucket scratch (multi-GPU exchange)
+static_assert(CTR_COUNT <= CTR_STRIDE, "counter block too small");
+static inline unsigned long long* pass_block(clsn_ctx* c, int slot) { return c->counters.p + CTR_LEGACY + CTR_STRIDE * slot; }
+static inline unsigned long long* host_block(clsn_ctx* c, int slot) { return c->h_counters + CTR_STRIDE * slot; }
+
+// Enqueue one detection pass (refit, self query, narrow phase, record emission) on the stream.  Nothing is read back:
+// every kernel takes its input count from the pass's counter block, clamps its output to the buffer capacity and skips
+// its work when an upstream list overflowed; finish_detect() looks at the counters later.  gate (device pointer or
+// null): the pass runs only if *gate != 0 -- detectCollision's `while (is_collision)` (dcollid.cpp:448) on the device.
+static int enqueue_detect(clsn_ctx* c, int mode, int slot, const unsigned long long* gate)
 {
     const int N = c->N, V = c->V;
     const bool moving = mode == CLSN_COLLISION;
     if (N < 1) return fail(c, CLSN_E_ARG, "no elements");
     NarrowParams P{c->prm.eps, c->prm.thickness, c->prm.dt, c->prm.k, c->prm.m, c->prm.lambda, c->prm.cr};
-    (void)timed; (void)ev_base;
     if (!c->tree_built) {
         int r = build_tree(c);
         if (r) return r;
     }
+    unsigned long long* ctr = c->ctr = pass_block(c, slot);
     if (c->dbg_candidates && c->dbg_cand.n == 0) CK(c->dbg_cand.reserve((size_t)32 * N + 1024));
     if (c->dbg_contacts && c->contacts.n == 0) CK(c->contacts.reserve((size_t)16 * N + 1024));
     const int q_lo = (int)((long long)N * c->rank / c->nranks), q_hi = (int)((long long)N * (c->rank + 1) / c->nranks);
-    for (int attempt = 0; attempt < 8; ++attempt) {
-        CK(cudaMemsetAsync(c->counters.p, 0, CTR_ERROR * sizeof(unsigned long long), c->stream));  // keep CTR_ERROR
-        CK(cudaMemsetAsync(c->counters.p + CTR_DBG_CAND, 0, (CTR_COUNT - CTR_DBG_CAND) * sizeof(unsigned long long), c->stream));  // CTR_FEATS ... CTR_EXACT
-        CK(cudaMemsetAsync(c->flags.p, 0, (size_t)N * sizeof(int), c->stream));
-        CK(cudaMemsetAsync(c->cnt.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
-        CK(cudaMemsetAsync(c->cnt_rg.p, 0, c->nbody * sizeof(int), c->stream));
-        // pairs whose points did not change since the previous CCD pass repeat their (hit-free) outcome
-        const bool skip_clean = moving && c->dirty_valid && c->last_detect_mode == CLSN_COLLISION;
-        // ... and an untouched query needs to visit touched subtrees only -- unless exact candidate counts are wanted
-        const bool prune = skip_clean && !c->exact_stats && !c->dbg_candidates;
-        if (moving)
-            k_refit<true><<<nblk(N, 128), 128, 0, c->stream>>>(c->elem.p, c->leaf_elem.p, N, c->xo.p, c->av.p, c->prm.dt,
-                                                                 c->lbox.p, c->nodes.p, c->leaf_parent.p, c->flags.p,
-                                                                 prune ? c->dirty.p : nullptr);
-        else
-            k_refit<false><<<nblk(N, 128), 128, 0, c->stream>>>(c->elem.p, c->leaf_elem.p, N, c->xo.p, c->av.p, c->prm.dt,
-                                                                  c->lbox.p, c->nodes.p, c->leaf_parent.p, c->flags.p, nullptr);
-        c->launches += 1;
-        mark(c, PH_REFIT);
-        TraverseOut to;
-        to.pairs = c->pairs.p; to.cap_pairs = (long long)c->pairs.n;
-        to.dbg_cand = c->dbg_candidates ? c->dbg_cand.p : nullptr; to.cap_dbg = (long long)c->dbg_cand.n;
-        to.counters = c->counters.p;
-        to.dirty = skip_clean ? c->dirty.p : nullptr;
-        to.node_touched = prune ? c->flags.p : nullptr;
-        if (q_hi > q_lo)
-            k_traverse<<<nblk(q_hi - q_lo, TRAV_THREADS), TRAV_THREADS, 0, c->stream>>>(c->nodes.p, c->lbox.p, c->leaf_elem.p, c->elem.p, N, q_lo, q_hi, to);
-        c->launches += (q_hi > q_lo) ? 1 : 0;
-        mark(c, PH_TRAVERSE);
-        Emit E;
-        E.prec = c->prec.p; E.brec = c->brec.p; E.contacts = c->dbg_contacts ? c->contacts.p : nullptr;
-        E.counters = c->counters.p;
-        E.cap_prec = (long long)c->prec.n; E.cap_brec = (long long)c->brec.n; E.cap_contacts = (long long)c->contacts.n;
-        E.cnt = c->cnt.p; E.cnt_rg = c->cnt_rg.p; E.body_mass = c->body_mass.p;
-        if ((size_t)c->pairs.n >= (1ull << 28)) return fail(c, CLSN_E_NOMEM, "more than 2^28 pairs in one pass");
-        const long long hit_words = (long long)(c->pairs.n / 32 + 1);
-        CK(cudaMemsetAsync(c->pair_hit.p, 0, (size_t)hit_words * sizeof(unsigned), c->stream));
-        const int grid = c->sm_count * NARROW_GRID_MULT;
-        const bool fused = c->pipeline >= 1;
-        // segments only where this context reduces its own records (multi-GPU ranks exchange the plain list)
-        const bool seg = moving && c->pipeline == 2 && c->nranks == 1;
-        if (moving) {
-            if (fused && c->hits.n == 0) CK(c->hits.reserve((size_t)4 * N + 1024));
-            if (fused && c->unc.n == 0) CK(c->unc.reserve((size_t)4 * N + 1024));
-            if (!fused && c->rootrecs.n == 0) CK(c->rootrecs.reserve((size_t)16 * N + 1024));
-            k_cull<true><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p, P,
-                                                                c->feats.p, (long long)c->feats.n, c->counters.p, fused);
-            mark(c, PH_CULL);
-            if (fused) {
-                k_fast<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E, c->hits.p,
-                                                                     (long long)c->hits.n, c->unc.p, (long long)c->unc.n);
-                k_fast<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E, c->hits.p,
-                                                                    (long long)c->hits.n, c->unc.p, (long long)c->unc.n);
-                k_exact<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->unc.p, (long long)c->unc.n, c->xo.p, c->av.p, P, E, c->hits.p,
-                                                                      (long long)c->hits.n);
-                k_exact<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->unc.p, (long long)c->unc.n, c->xo.p, c->av.p, P, E, c->hits.p,
-                                                                     (long long)c->hits.n);
-                mark(c, PH_ROOTS);
-                if (seg) {
-                    // per-point record counts of the hit list -> segment offsets -> records written in place
-                    k_count_hits<false><<<grid, 256, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->vflags.p, c->cnt.p, c->counters.p);
-                    k_count_hits<true><<<grid, 256, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->vflags.p, c->cnt.p, c->counters.p);
-                    size_t tmp = c->cub_tmp.n;
-                    CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->cnt.p, c->offs.p, V + 1, c->stream));
-                    CK(cudaMemsetAsync(c->fill.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
-                    const SegOut S{c->offs.p, c->fill.p};
-                    k_emit<false, true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p,
-                                                                               c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p, S);
-                    k_emit<true, true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p,
-                                                                              c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p, S);
-                    c->launches += 4;
-                } else {
-                    k_emit<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p,
-                                                                         c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
-                    k_emit<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p,
-                                                                        c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
-                }
+    CK(cudaMemsetAsync(c->cnt.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
+    CK(cudaMemsetAsync(c->cnt_rg.p, 0, c->nbody * sizeof(int), c->stream));
+    // pairs whose points did not change since the previous CCD pass repeat their (hit-free) outcome
+    const bool skip_clean = moving && c->dirty_valid && c->last_detect_mode == CLSN_COLLISION;
+    // ... and an untouched query needs to visit touched subtrees only -- unless exact candidate counts are wanted
+    const bool prune = skip_clean && !c->exact_stats && !c->dbg_candidates;
+    float* root_box = c->tree_scratch.p + 12 * (size_t)c->tree.cnt[3];
+    if (moving)
+        k_refit8<true><<<c->tree.cnt[3], REFIT_LEAVES, 0, c->stream>>>(c->selem.p, c->tree, c->xo.p, c->av.p, c->prm.dt, c->lbox.p,
+                                                                        prune ? c->dirty.p : nullptr, c->tree_scratch.p,
+                                                                        c->tree_scratch_t.p, c->tree_ticket.p, root_box, gate);
+    else
+        k_refit8<false><<<c->tree.cnt[3], REFIT_LEAVES, 0, c->stream>>>(c->selem.p, c->tree, c->xo.p, c->av.p, c->prm.dt, c->lbox.p,
+                                                                         nullptr, c->tree_scratch.p, c->tree_scratch_t.p,
+                                                                         c->tree_ticket.p, root_box, gate);
+    c->launches += 1;
+    mark(c, PH_REFIT);
+    TraverseOut to;
+    to.pairs = c->pairs.p; to.cap_pairs = (long long)c->pairs.n;
+    to.dbg_cand = c->dbg_candidates ? c->dbg_cand.p : nullptr; to.cap_dbg = (long long)c->dbg_cand.n;
+    to.counters = ctr;
+    to.dirty = skip_clean ? c->dirty.p : nullptr;
+    to.prune = prune ? 1 : 0;
+    to.gate = gate;
+    if (q_hi > q_lo)
+        k_traverse8<<<nblk(q_hi - q_lo, TRAV_THREADS), TRAV_THREADS, 0, c->stream>>>(c->tree, c->lbox.p, c->leaf_elem.p, c->selem.p, q_lo, q_hi, to);
+    c->launches += (q_hi > q_lo) ? 1 : 0;
+    mark(c, PH_TRAVERSE);
+    Emit E;
+    E.prec = c->prec.p; E.brec = c->brec.p; E.contacts = c->dbg_contacts ? c->contacts.p : nullptr;
+    E.counters = ctr;
+    E.cap_prec = (long long)c->prec.n; E.cap_brec = (long long)c->brec.n; E.cap_contacts = (long long)c->contacts.n;
+    E.cnt = c->cnt.p; E.cnt_rg = c->cnt_rg.p; E.body_mass = c->body_mass.p;
+    const long long hit_words = (long long)(c->pairs.n / 32 + 1);
+    CK(cudaMemsetAsync(c->pair_hit.p, 0, (size_t)hit_words * sizeof(unsigned), c->stream));
+    const int grid = c->sm_count * NARROW_GRID_MULT;
+    const bool fused = c->pipeline >= 1;
+    // segments only where this context reduces its own records (multi-GPU ranks exchange the plain list)
+    const bool seg = moving && c->pipeline == 2 && c->nranks == 1;
+    if (moving) {
+        if (fused && c->hits.n == 0) CK(c->hits.reserve((size_t)4 * N + 1024));
+        if (fused && c->unc.n == 0) CK(c->unc.reserve((size_t)4 * N + 1024));
+        if (!fused && c->rootrecs.n == 0) CK(c->rootrecs.reserve((size_t)16 * N + 1024));
+        k_cull<true><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p, P,
+                                                            c->feats.p, (long long)c->feats.n, ctr, fused);
+        mark(c, PH_CULL);
+        if (fused) {
+            k_fast<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E, c->hits.p,
+                                                                 (long long)c->hits.n, c->unc.p, (long long)c->unc.n);
+            k_fast<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E, c->hits.p,
+                                                                (long long)c->hits.n, c->unc.p, (long long)c->unc.n);
+            k_exact<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->unc.p, (long long)c->unc.n, c->xo.p, c->av.p, P, E, c->hits.p,
+                                                                  (long long)c->hits.n);
+            k_exact<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->unc.p, (long long)c->unc.n, c->xo.p, c->av.p, P, E, c->hits.p,
+                                                                 (long long)c->hits.n);
+            mark(c, PH_ROOTS);
+            if (seg) {
+                // per-point record counts of the hit list -> segment offsets -> records written in place
+                k_count_hits<false><<<grid, 256, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->vflags.p, c->cnt.p, ctr);
+                k_count_hits<true><<<grid, 256, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->vflags.p, c->cnt.p, ctr);
+                size_t tmp = c->cub_tmp.n;
+                CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->cnt.p, c->offs.p, V + 1, c->stream));
+                CK(cudaMemsetAsync(c->fill.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
+                const SegOut S{c->offs.p, c->fill.p};
+                k_emit<false, true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p,
+                                                                           c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p, S);
+                k_emit<true, true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p,
+                                                                          c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p, S);
+                c->launches += 4;
             } else {
-                k_roots<<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P.dt, c->rootrecs.p,
-                                                               (long long)c->rootrecs.n, c->counters.p);
-                mark(c, PH_ROOTS);
-                k_contact<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, c->rootrecs.p, (long long)c->rootrecs.n, c->pairs.p,
-                                                                       c->xo.p, c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+                k_emit<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p,
+                                                                     c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+                k_emit<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p,
+                                                                    c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
             }
         } else {
-            k_cull<false><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p, P,
-                                                                 c->feats.p, (long long)c->feats.n, c->counters.p, false);
-            mark(c, PH_CULL);
-            k_contact<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, c->rootrecs.p, (long long)c->feats.n, c->pairs.p,
-                                                                    c->xo.p, c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+            k_roots<<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P.dt, c->rootrecs.p,
+                                                           (long long)c->rootrecs.n, ctr);
+            mark(c, PH_ROOTS);
+            k_contact<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, c->rootrecs.p, (long long)c->rootrecs.n, c->pairs.p,
+                                                                   c->xo.p, c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
         }
-        k_count_true<<<c->sm_count * 2, 256, 0, c->stream>>>(c->pair_hit.p, hit_words, c->counters.p);
-        CK(cudaGetLastError());
-        c->launches += moving ? (fused ? 8 : 4) : 3;
-        mark(c, PH_CONTACT);
-        CK(cudaMemcpyAsync(c->h_counters, c->counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        k_cull<false><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p, P,
+                                                             c->feats.p, (long long)c->feats.n, ctr, false);
+        mark(c, PH_CULL);
+        k_contact<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, c->rootrecs.p, (long long)c->feats.n, c->pairs.p,
+                                                                c->xo.p, c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+    }
+    k_count_true<<<c->sm_count * 2, 256, 0, c->stream>>>(c->pair_hit.p, hit_words, ctr);
+    CK(cudaGetLastError());
+    c->launches += moving ? (fused ? 8 : 4) : 3;
+    mark(c, PH_CONTACT);
+    c->records_pending = true;
+    c->seg_records = seg;
+    c->imp_nprec = -1;
+    c->last_detect_mode = mode;
+    c->dirty_valid = false;  // becomes valid again once these records have been applied
+    c->pending_gate = gate;
+    return CLSN_OK;
+}
+
+// Look at a pass's counters (host copy h): grow every list that overflowed.  Returns 1 when the pass (or the step that
+// contains it) has to be repeated, 0 when its results stand, < 0 on error.
+static int grow_after_pass(clsn_ctx* c, const unsigned long long* h, bool moving)
+{
+    const bool fused = c->pipeline >= 1;
+    bool redo = false;
+    if (h[CTR_PAIRS] >= (1ull << 32)) return fail(c, CLSN_E_NOMEM, "more than 2^32 - 1 pairs in one pass");
+    if (h[CTR_PAIRS] > c->pairs.n) {
+        size_t want = (size_t)(h[CTR_PAIRS] * 5 / 4 + 1024);
+        if (want >= (1ull << 32)) want = (1ull << 32) - 1;
+        CK(c->pairs.reserve(want));
+        CK(c->pair_hit.reserve(c->pairs.n / 32 + 2));
+        redo = true;
+    }
+    if (h[CTR_FEATS] + h[CTR_FEATS_EE] > c->feats.n) {
+        CK(c->feats.reserve((size_t)((h[CTR_FEATS] + h[CTR_FEATS_EE]) * 5 / 4 + 1024)));
+        redo = true;
+    }
+    if (!fused && moving && h[CTR_ROOTS] + h[CTR_ROOTS_EE] > c->rootrecs.n) {
+        CK(c->rootrecs.reserve((size_t)((h[CTR_ROOTS] + h[CTR_ROOTS_EE]) * 5 / 4 + 1024)));
+        redo = true;
+    }
+    if (fused && moving && h[CTR_UNC] + h[CTR_UNC_EE] > c->unc.n) {
+        CK(c->unc.reserve((size_t)((h[CTR_UNC] + h[CTR_UNC_EE]) * 5 / 4 + 1024)));
+        redo = true;
+    }
+    if (fused && moving && h[CTR_HITS] + h[CTR_HITS_EE] > c->hits.n) {
+        CK(c->hits.reserve((size_t)((h[CTR_HITS] + h[CTR_HITS_EE]) * 5 / 4 + 1024)));
+        redo = true;
+    }
+    if (h[CTR_PREC] > c->prec.n) {
+        size_t want = (size_t)(h[CTR_PREC] * 5 / 4 + 1024);
+        CK(c->prec.reserve(want)); CK(c->perm.reserve(want)); CK(c->perm_sorted.reserve(want)); CK(c->skey.reserve(want));
+        redo = true;
+    }
+    if (h[CTR_BREC] > c->brec.n) { CK(c->brec.reserve((size_t)(h[CTR_BREC] * 5 / 4 + 1024))); redo = true; }
+    if (c->dbg_candidates && h[CTR_DBG_CAND] > c->dbg_cand.n) { CK(c->dbg_cand.reserve((size_t)(h[CTR_DBG_CAND] * 5 / 4 + 1024))); redo = true; }
+    if (c->dbg_contacts && h[CTR_CONTACTS] > c->contacts.n) { CK(c->contacts.reserve((size_t)(h[CTR_CONTACTS] * 5 / 4 + 1024))); redo = true; }
+    return redo ? 1 : 0;
+}
+
+static void fill_pass_stats(clsn_ctx* c, const unsigned long long* h, bool moving, clsn_pass_stats* st)
+{
+    if (!st) return;
+    const bool fused = c->pipeline >= 1;
+    st->candidates = (int64_t)h[CTR_CAND];
+    st->pairs_tested = (int64_t)h[CTR_PAIRS];
+    st->true_pairs = (int64_t)h[CTR_TRUE];
+    st->contacts = (int64_t)h[CTR_CONTACTS];
+    st->contributions = (int64_t)(h[CTR_PREC] + h[CTR_BREC]);
+    st->features = (int64_t)(h[CTR_FEATS] + h[CTR_FEATS_EE]);
+    st->box_survivors = (int64_t)h[CTR_BOXSURV];
+    st->coplanar = (int64_t)(h[CTR_ROOTS] + h[CTR_ROOTS_EE]);
+    st->exact_solves = fused && moving ? (int64_t)h[CTR_EXACT] : st->coplanar;
+}
+
+// One pass through the per-phase ABI (and the impact-zone loop): enqueue, read the counters back, repeat if a list was
+// too small.  The whole-step entry (resolve_impl) enqueues all passes first and reads every block once at the end.
+static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st)
+{
+    const bool moving = mode == CLSN_COLLISION;
+    const bool dirty_valid = c->dirty_valid;
+    const int last_mode = c->last_detect_mode;
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        unsigned long long* blk = pass_block(c, PASS_SLOT_SOLO);
+        CK(cudaMemsetAsync(blk, 0, CTR_STRIDE * sizeof(unsigned long long), c->stream));
+        c->dirty_valid = dirty_valid;   // enqueue_detect clears them; a repeated pass starts from the same flags
+        c->last_detect_mode = last_mode;
+        int r = enqueue_detect(c, mode, PASS_SLOT_SOLO, nullptr);
+        if (r) return r;
+        unsigned long long* h = host_block(c, PASS_SLOT_SOLO);
+        CK(cudaMemcpyAsync(h, blk, CTR_STRIDE * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        const unsigned long long* h = c->h_counters;
-        bool redo = false;
-        if (h[CTR_PAIRS] > c->pairs.n) {
-            CK(c->pairs.reserve((size_t)(h[CTR_PAIRS] * 5 / 4 + 1024)));
-            CK(c->pair_hit.reserve(c->pairs.n / 32 + 2));
-            redo = true;
-        }
-        if (h[CTR_FEATS] + h[CTR_FEATS_EE] > c->feats.n) {
-            CK(c->feats.reserve((size_t)((h[CTR_FEATS] + h[CTR_FEATS_EE]) * 5 / 4 + 1024)));
-            redo = true;
-        }
-        if (!fused && h[CTR_ROOTS] + h[CTR_ROOTS_EE] > c->rootrecs.n) {
-            CK(c->rootrecs.reserve((size_t)((h[CTR_ROOTS] + h[CTR_ROOTS_EE]) * 5 / 4 + 1024)));
-            redo = true;
-        }
-        if (fused && moving && h[CTR_UNC] + h[CTR_UNC_EE] > c->unc.n) {
-            CK(c->unc.reserve((size_t)((h[CTR_UNC] + h[CTR_UNC_EE]) * 5 / 4 + 1024)));
-            redo = true;
-        }
-        if (fused && moving && h[CTR_HITS] + h[CTR_HITS_EE] > c->hits.n) {
-            CK(c->hits.reserve((size_t)((h[CTR_HITS] + h[CTR_HITS_EE]) * 5 / 4 + 1024)));
-            redo = true;
-        }
-        if (h[CTR_PREC] > c->prec.n) {
-            size_t want = (size_t)(h[CTR_PREC] * 5 / 4 + 1024);
-            CK(c->prec.reserve(want)); CK(c->perm.reserve(want)); CK(c->perm_sorted.reserve(want)); CK(c->skey.reserve(want));
-            redo = true;
-        }
-        if (h[CTR_BREC] > c->brec.n) { CK(c->brec.reserve((size_t)(h[CTR_BREC] * 5 / 4 + 1024))); redo = true; }
-        if (c->dbg_candidates && h[CTR_DBG_CAND] > c->dbg_cand.n) { CK(c->dbg_cand.reserve((size_t)(h[CTR_DBG_CAND] * 5 / 4 + 1024))); redo = true; }
-        if (c->dbg_contacts && h[CTR_CONTACTS] > c->contacts.n) { CK(c->contacts.reserve((size_t)(h[CTR_CONTACTS] * 5 / 4 + 1024))); redo = true; }
-        if (redo) continue;
+        r = grow_after_pass(c, h, moving);
+        if (r < 0) return r;
+        if (r == 1) continue;
         if (h[CTR_ERROR]) return fail(c, CLSN_E_NUMERIC, "NaN/Inf or degenerate normal (reference: clean_up(ERROR))");
-        if (st) {
-            st->candidates = (int64_t)h[CTR_CAND];
-            st->pairs_tested = (int64_t)h[CTR_PAIRS];
-            st->true_pairs = (int64_t)h[CTR_TRUE];
-            st->contacts = (int64_t)h[CTR_CONTACTS];
-            st->contributions = (int64_t)(h[CTR_PREC] + h[CTR_BREC]);
-            st->features = (int64_t)(h[CTR_FEATS] + h[CTR_FEATS_EE]);
-            st->box_survivors = (int64_t)h[CTR_BOXSURV];
-            st->coplanar = (int64_t)(h[CTR_ROOTS] + h[CTR_ROOTS_EE]);
-            st->exact_solves = fused && moving ? (int64_t)h[CTR_EXACT] : st->coplanar;
-        }
+        fill_pass_stats(c, h, moving, st);
         c->last_nprec = (long long)h[CTR_PREC];
         c->last_nbrec = (long long)h[CTR_BREC];
+        c->last_true = (long long)h[CTR_TRUE];
         c->n_dbg_cand = (long long)h[CTR_DBG_CAND];
         c->n_contacts = (long long)h[CTR_CONTACTS];
-        c->records_pending = true;
-        c->seg_records = seg;
-        c->imp_nprec = -1;
-        c->last_detect_mode = mode;
-        c->dirty_valid = false;  // becomes valid again once these records have been applied
         return CLSN_OK;
     }
     return fail(c, CLSN_E_NOMEM, "pair/record buffers kept overflowing");
@@ -1373,45 +1467,48 @@ extern "C" int clsn_detect(clsn_ctx* c, int mode, clsn_pass_stats* st)
 {
     if (!c || !c->V || (mode != CLSN_PROXIMITY && mode != CLSN_COLLISION)) return CLSN_E_ARG;
     cudaSetDevice(c->device);
-    return run_detect(c, mode, st, false, 0);
+    return run_detect(c, mode, st);
 }
 
 // group + reduce the pending records.  mode 0: apply to avgVel; mode 1: into acc arrays only.
+// No host-side counts are consulted for the context's own records: every kernel reads its count from the pass's counter
+// block, so the launches are the same whether or not the pass found anything (an empty or gated pass costs a few empty
+// kernels).  An imported record set (multi-GPU exchange) carries its counts explicitly.
 static int reduce_records(clsn_ctx* c, int mode, int what = 3)  // what: bit 0 point records, bit 1 body records
 {
     const int V = c->V;
     const PointRec* prec = c->prec.p;
     const BodyRec* brec = c->brec.p;
-    long long nprec = c->last_nprec, nbrec = c->last_nbrec;
-    unsigned long long* n_prec_dev = c->counters.p + CTR_PREC;
-    unsigned long long* n_brec_dev = c->counters.p + CTR_BREC;
-    if (c->imp_nprec >= 0) {
+    const bool imported = c->imp_nprec >= 0;
+    unsigned long long* n_prec_dev = c->ctr + CTR_PREC;
+    unsigned long long* n_brec_dev = c->ctr + CTR_BREC;
+    long long cap_p = (long long)c->prec.n, cap_b = (long long)c->brec.n;
+    if (imported) {
+        // externally gathered record set: recount per point
+        prec = c->imp_prec; brec = c->imp_brec;
+        const long long nprec = c->imp_nprec, nbrec = c->imp_nbrec;
+        cap_p = nprec; cap_b = nbrec;
         n_prec_dev = c->counters.p + 32;
         n_brec_dev = c->counters.p + 33;
-    }
-    if (c->imp_nprec >= 0) {
-        // externally gathered record set: recount per point
-        prec = c->imp_prec; brec = c->imp_brec; nprec = c->imp_nprec; nbrec = c->imp_nbrec;
-    }
-    if (c->imp_nprec >= 0 && (what & 1)) {
-        unsigned long long hc[2] = {(unsigned long long)nprec, (unsigned long long)nbrec};
-        CK(cudaMemcpyAsync(c->counters.p + 32, hc, sizeof(hc), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemsetAsync(c->cnt.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
-        CK(cudaMemsetAsync(c->cnt_rg.p, 0, c->nbody * sizeof(int), c->stream));
-        if (nprec > 0 || nbrec > 0)
-            k_count_records<<<c->sm_count * 4, 256, 0, c->stream>>>(prec, nprec, brec, nbrec, c->cnt.p, c->cnt_rg.p);
-        if ((size_t)nprec > c->perm.n) {
-            CK(c->perm.reserve((size_t)nprec)); CK(c->perm_sorted.reserve((size_t)nprec)); CK(c->skey.reserve((size_t)nprec));
+        if (what & 1) {
+            unsigned long long hc[2] = {(unsigned long long)nprec, (unsigned long long)nbrec};
+            CK(cudaMemcpyAsync(c->counters.p + 32, hc, sizeof(hc), cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemsetAsync(c->cnt.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
+            CK(cudaMemsetAsync(c->cnt_rg.p, 0, c->nbody * sizeof(int), c->stream));
+            if (nprec > 0 || nbrec > 0)
+                k_count_records<<<c->sm_count * 4, 256, 0, c->stream>>>(prec, nprec, brec, nbrec, c->cnt.p, c->cnt_rg.p);
+            if ((size_t)nprec > c->perm.n) {
+                CK(c->perm.reserve((size_t)nprec)); CK(c->perm_sorted.reserve((size_t)nprec)); CK(c->skey.reserve((size_t)nprec));
+            }
         }
     }
-    const bool seg = c->seg_records && c->imp_nprec < 0;   // records already grouped per point by k_emit<., true>
-    if (nprec > 0 && (what & 1)) {
+    const bool seg = c->seg_records && !imported;   // records already grouped per point by k_emit<., true>
+    if (what & 1) {
         if (!seg) {
             size_t tmp = c->cub_tmp.n;
             CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->cnt.p, c->offs.p, V + 1, c->stream));
             CK(cudaMemsetAsync(c->fill.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
-            const long long cap = c->imp_nprec >= 0 ? nprec : (long long)c->prec.n;
-            k_scatter<<<c->sm_count * 8, 256, 0, c->stream>>>(prec, n_prec_dev, cap, c->offs.p, c->fill.p, c->perm.p, c->skey.p);
+            k_scatter<<<c->sm_count * 8, 256, 0, c->stream>>>(prec, n_prec_dev, cap_p, c->offs.p, c->fill.p, c->perm.p, c->skey.p);
         }
         if (mode == 1) {
             CK(c->acc_imp.reserve(3 * (size_t)V)); CK(c->acc_fric.reserve(3 * (size_t)V));
@@ -1421,20 +1518,16 @@ static int reduce_records(clsn_ctx* c, int mode, int what = 3)  // what: bit 0 p
         if (seg)
             k_reduce_points<true><<<c->sm_count * 8, 256, 0, c->stream>>>(prec, c->offs.p, c->cnt.p, V, c->perm.p, c->perm_sorted.p,
                                                                             c->skey.p, c->vflags.p, c->av.p, c->has.p, c->dirty.p, mode,
-                                                                            c->acc_imp.p, c->acc_fric.p, c->counters.p);
+                                                                            c->acc_imp.p, c->acc_fric.p, c->ctr, n_prec_dev, cap_p);
         else
             k_reduce_points<false><<<c->sm_count * 8, 256, 0, c->stream>>>(prec, c->offs.p, c->cnt.p, V, c->perm.p, c->perm_sorted.p,
                                                                              c->skey.p, c->vflags.p, c->av.p, c->has.p, c->dirty.p, mode,
-                                                                             c->acc_imp.p, c->acc_fric.p, c->counters.p);
+                                                                             c->acc_imp.p, c->acc_fric.p, c->ctr, n_prec_dev, cap_p);
         c->launches += 2 + 2;  // scan (init + scan), scatter, reduce
-    } else if (mode == 1 && (what & 1)) {
-        CK(c->acc_imp.reserve(3 * (size_t)V)); CK(c->acc_fric.reserve(3 * (size_t)V));
-        CK(cudaMemsetAsync(c->acc_imp.p, 0, 3 * (size_t)V * sizeof(double), c->stream));
-        CK(cudaMemsetAsync(c->acc_fric.p, 0, 3 * (size_t)V * sizeof(double), c->stream));
     }
-    if (nbrec > 0 && mode == 0 && (what & 2)) {
-        const long long cap = c->imp_nprec >= 0 ? nbrec : (long long)c->brec.n;
-        k_reduce_bodies<<<nblk(c->nbody, 64), 64, 0, c->stream>>>(brec, n_brec_dev, cap, c->nbody, c->imp_rg.p);
+    if (mode == 0 && (what & 2) && (c->has_movable || (imported && c->imp_nbrec > 0))) {
+        // body records only exist where a movable rigid body does (emit_body needs a movable point)
+        k_reduce_bodies<<<nblk(c->nbody, 64), 64, 0, c->stream>>>(brec, n_brec_dev, cap_b, c->nbody, c->imp_rg.p);
         c->launches += 1;
     }
     CK(cudaGetLastError());
@@ -1445,6 +1538,7 @@ static int reduce_records(clsn_ctx* c, int mode, int what = 3)  // what: bit 0 p
 // The multi-GPU owner-computes path runs them separately with the avgVel exchange in between.
 static int apply_impl(clsn_ctx* c, int rigidify, int stages)
 {
+    const unsigned long long* gate = c->pending_gate;   // the apply of a pass that did not run must not touch anything
     if (c->records_pending && (stages & 1)) {
         k_reset_dirty<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->vflags.p, c->dirty.p);
         c->launches += 1;
@@ -1454,12 +1548,12 @@ static int apply_impl(clsn_ctx* c, int rigidify, int stages)
     if (c->records_pending && (stages & 2)) {
         int r = reduce_records(c, 0, 2);
         if (r) return r;
-        const long long nbrec = c->imp_nprec >= 0 ? c->imp_nbrec : c->last_nbrec;
-        if (nbrec > 0 || c->has_movable) {
+        if (c->has_movable || c->cnt_rg_preset) {
             // cnt_rg > 0 can also persist from set_body_accumulators (parity tests)
             k_apply_bodies<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->vflags.p, c->vbody.p, c->imp_rg.p, c->cnt_rg.p,
                                                                     c->av.p, c->has.p, c->dirty.p);
             CK(cudaMemsetAsync(c->cnt_rg.p, 0, c->nbody * sizeof(int), c->stream));
+            c->cnt_rg_preset = false;
             c->launches += 1;
         }
         CK(cudaMemsetAsync(c->cnt.p, 0, ((size_t)c->V + 1) * sizeof(int), c->stream));
@@ -1468,10 +1562,11 @@ static int apply_impl(clsn_ctx* c, int rigidify, int stages)
         c->dirty_valid = true;
     }
     if ((stages & 2) && rigidify && c->has_movable && c->prm.dt > 0.0) {
-        int r = c->rigid.rigidify(c->xo.p, c->av.p, c->vflags.p, c->prm.m, c->prm.dt, c->counters.p, c->stream);
+        int r = c->rigid.rigidify(c->xo.p, c->av.p, c->vflags.p, c->prm.m, c->prm.dt, c->ctr, c->stream, nullptr, gate);
         if (r != 0) return fail(c, CLSN_E_CUDA, "rigid-body kernels failed");
         c->launches += c->rigid.nlists ? 2 : 0;
     }
+    if (stages & 2) c->pending_gate = nullptr;
     CK(cudaGetLastError());
     mark(c, PH_REDUCE);
     return CLSN_OK;
@@ -1511,7 +1606,8 @@ extern "C" int clsn_final_position(clsn_ctx* c)
 {
     if (!c || !c->V) return CLSN_E_ARG;
     cudaSetDevice(c->device);
-    k_final_position<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->xo.p, c->av.p, c->xn.p, c->prm.dt);
+    k_final_position<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->xo.p, c->av.p, c->xf.p, c->prm.dt);
+    c->final_valid = true;
     CK(cudaGetLastError());
     c->launches += 1;
     mark(c, PH_FINAL);
@@ -1596,7 +1692,7 @@ extern "C" int clsn_compute_impact_zone(clsn_ctx* c, int max_iter, clsn_zone_sta
     int r = CLSN_OK;
     while (is_collision) {
         clsn_pass_stats st;
-        if ((r = run_detect(c, CLSN_COLLISION, &st, false, 0))) break;
+        if ((r = run_detect(c, CLSN_COLLISION, &st))) break;
         is_collision = st.true_pairs > 0;
         zs.true_pairs += st.true_pairs;
         const size_t n = (size_t)c->n_contacts;
@@ -1626,7 +1722,7 @@ extern "C" int clsn_compute_impact_zone(clsn_ctx* c, int max_iter, clsn_zone_sta
         if ((r = clsn_apply(c, 1))) break;
         if (c->zone_lists_stale && (r = upload_zone_lists(c))) break;
         if (c->prm.dt > 0.0 && c->zone_lists.nlists) {
-            if (c->zone_lists.rigidify(c->xo.p, c->av.p, c->vflags.p, c->prm.m, c->prm.dt, c->counters.p, c->stream, c->dirty.p) != 0) {
+            if (c->zone_lists.rigidify(c->xo.p, c->av.p, c->vflags.p, c->prm.m, c->prm.dt, c->ctr, c->stream, c->dirty.p) != 0) {
                 r = fail(c, CLSN_E_CUDA, "impact-zone kernels failed");
                 break;
             }
@@ -1711,62 +1807,153 @@ extern "C" int clsn_strain_limit(clsn_ctx* c, int32_t* sweeps, int32_t* edges_la
     return CLSN_OK;
 }
 
-// resolveCollision, dcollid.cpp:317-362 (detectProximity :390-406, detectCollision :430-468)
-static int resolve_impl(clsn_ctx* c, clsn_step_stats& s)
+// resolveCollision, dcollid.cpp:317-362 (detectProximity :390-406, detectCollision :430-468).
+// The whole step is enqueued without a single read-back: the proximity pass, the five CCD passes (each gated on the
+// device by the contact count of the one before it -- `while (is_collision)`), the applies, the wall clamp and the final
+// positions, optionally the copies into the caller's host arrays.  ONE cudaStreamSynchronize at the end brings back the
+// counter blocks of all passes; only if a work list turned out too small (first step of a new scene, or a step much more
+// violent than the one before) the lists are grown and the step is enqueued again from the uploaded state, which the
+// step never overwrites (final positions go to their own buffer).  With the impact-zone fail-safe enabled there is one
+// more synchronisation after the CCD passes, because entering it is a host decision (and the fail-safe itself is
+// host-assisted).
+struct HostOut {
+    double* x = nullptr;
+    double* avgvel = nullptr;
+    uint8_t* has = nullptr;
+};
+
+static int read_blocks(clsn_ctx* c)
+{
+    CK(cudaMemcpyAsync(c->h_counters, pass_block(c, 0), PASS_SLOTS * CTR_STRIDE * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                       c->stream));
+    CK(cudaMemcpyAsync(c->h_counters + PASS_SLOTS * CTR_STRIDE, c->tree_scratch.p + 12 * (size_t)c->tree.cnt[3], 6 * sizeof(float),
+                       cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CLSN_OK;
+}
+
+// which CCD passes ran (host copy of the counter blocks): pass 1 always, pass k + 1 iff pass k hit something
+static int ccd_passes_run(clsn_ctx* c)
+{
+    int n = 1;
+    while (n < CLSN_MAX_CCD_PASSES && host_block(c, n)[CTR_CONTACTS] > 0) ++n;
+    return n;
+}
+
+static int resolve_impl(clsn_ctx* c, clsn_step_stats& s, const HostOut& out)
 {
     int r;
-    CK(cudaEventRecord(c->ev[0], c->stream));
-    mark(c, PH_OTHER);
-    if ((r = clsn_avg_velocity(c))) return r;
-    if ((r = run_detect(c, CLSN_PROXIMITY, &s.proximity, true, 0))) return r;
-    if ((r = clsn_apply(c, 1))) return r;
-    bool is_collision = true;
-    int niter = 1, cd = 0;
-    while (is_collision) {
-        if ((r = run_detect(c, CLSN_COLLISION, &s.ccd[cd], true, 0))) return r;
-        is_collision = s.ccd[cd].true_pairs > 0;
-        if (cd == 0 && is_collision) s.has_collision = 1;
-        ++cd;
-        if ((r = clsn_apply(c, 1))) return r;
-        if (++niter > CLSN_MAX_CCD_PASSES) break;
+    const size_t nb = 3 * (size_t)c->nbody;
+    CK(c->imp_rg_keep.reserve(nb));
+    CK(cudaMemcpyAsync(c->imp_rg_keep.p, c->imp_rg.p, nb * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        if (attempt) {   // back to the uploaded state
+            CK(cudaMemcpyAsync(c->imp_rg.p, c->imp_rg_keep.p, nb * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            if ((r = begin_step(c))) return r;
+            c->n_marks = 0;
+        }
+        CK(cudaEventRecord(c->ev[0], c->stream));
+        mark(c, PH_OTHER);
+        CK(cudaMemsetAsync(pass_block(c, 0), 0, PASS_SLOTS * CTR_STRIDE * sizeof(unsigned long long), c->stream));
+        if ((r = clsn_avg_velocity(c))) return r;
+        if ((r = enqueue_detect(c, CLSN_PROXIMITY, 0, nullptr))) return r;
+        if ((r = apply_impl(c, 1, 3))) return r;
+        for (int p = 1; p <= CLSN_MAX_CCD_PASSES; ++p) {
+            const unsigned long long* gate = p == 1 ? nullptr : pass_block(c, p - 1) + CTR_CONTACTS;
+            if ((r = enqueue_detect(c, CLSN_COLLISION, p, gate))) return r;
+            if ((r = apply_impl(c, 1, 3))) return r;
+        }
+        bool checked = false, redo = false;
+        auto check = [&]() -> int {
+            for (int p = 0; p <= CLSN_MAX_CCD_PASSES; ++p) {
+                const int g = grow_after_pass(c, host_block(c, p), p > 0);
+                if (g < 0) return g;
+                if (g == 1) redo = true;
+            }
+            checked = true;
+            return CLSN_OK;
+        };
+        s.zone_iterations = 0;
+        s.zones = 0;
+        if (c->impact_zones) {  // detectCollision's tail, dcollid.cpp:464-467: a host decision
+            if ((r = read_blocks(c))) return r;
+            if ((r = check())) return r;
+            if (redo) continue;
+            const int np = ccd_passes_run(c);
+            if (np == CLSN_MAX_CCD_PASSES && host_block(c, np)[CTR_TRUE] > 0) {
+                clsn_zone_stats zs;
+                if ((r = clsn_compute_impact_zone(c, c->zone_max_iter, &zs))) return r;
+                s.zone_iterations = zs.iterations;
+                s.zones = zs.zones;
+            }
+        }
+        c->ctr = pass_block(c, PASS_SLOT_STEP);
+        if ((r = clsn_boundary(c))) return r;
+        if ((r = clsn_final_position(c))) return r;
+        if (c->strain_limiting && (r = strain_enqueue(c))) return r;  // reduceSuperelast, dcollid.cpp:355
+        CK(cudaEventRecord(c->ev[1], c->stream));
+        if (out.x || out.avgvel || out.has) {
+            const size_t n = 3 * (size_t)c->V;
+            if ((r = clsn_download_state_device(c, out.x ? c->stage.p : nullptr, out.avgvel ? c->stage.p + n : nullptr))) return r;
+            if (out.x) CK(cudaMemcpyAsync(out.x, c->stage.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            if (out.avgvel) CK(cudaMemcpyAsync(out.avgvel, c->stage.p + n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            if (out.has) CK(cudaMemcpyAsync(out.has, c->has.p, c->V, cudaMemcpyDeviceToHost, c->stream));
+        }
+        if ((r = read_blocks(c))) return r;
+        if (!checked && (r = check())) return r;
+        if (redo) continue;
+        // ---- the step stands.  Keep the tree (leaf order) for the next step unless the scene box has grown by more
+        // than 20 % since it was built -- the reference's rule for its own tree (aabbCollision, dcollid.cpp:417-426) --
+        // or the order is 64 steps old (the Morton order of a moving mesh ages even at constant volume).
+        {
+            const float* rb = reinterpret_cast<const float*>(c->h_counters + PASS_SLOTS * CTR_STRIDE);
+            const double vol = (double)(rb[3] - rb[0]) * (double)(rb[4] - rb[1]) * (double)(rb[5] - rb[2]);
+            if (c->tree_volume < 0.0) c->tree_volume = vol;
+            if ((vol - c->tree_volume) > 0.2 * c->tree_volume) c->tree_built = false;
+        }
+        // statistics from the counter blocks
+        unsigned long long err = 0;
+        for (int p = 0; p < PASS_SLOTS; ++p) err |= host_block(c, p)[CTR_ERROR];
+        if (err) return fail(c, CLSN_E_NUMERIC, "NaN/Inf in the collision step (reference: clean_up(ERROR))");
+        fill_pass_stats(c, host_block(c, 0), false, &s.proximity);
+        const int np = ccd_passes_run(c);
+        for (int p = 1; p <= np; ++p) fill_pass_stats(c, host_block(c, p), true, &s.ccd[p - 1]);
+        s.n_ccd_passes = np;
+        s.has_collision = host_block(c, 1)[CTR_TRUE] > 0 ? 1 : 0;
+        s.still_colliding = host_block(c, np)[CTR_TRUE] > 0 ? 1 : 0;
+        CK(cudaEventElapsedTime(&s.ms_total, c->ev[0], c->ev[1]));
+        if (c->strain_pending) strain_finish(c, &s.strain_sweeps, &s.strain_edges);
+        static const bool trace = getenv("CLSN_TRACE") != nullptr;   // per-mark timeline on stderr (tuning runs)
+        static const char* names[PH_COUNT] = {"avgvel", "build", "refit", "traverse", "cull", "roots", "contact", "reduce", "final", "other"};
+        for (size_t i = 1; i < c->n_marks; ++i) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, c->marks[i - 1], c->marks[i]) == cudaSuccess) s.ms_phase[c->mark_phase[i]] += ms;
+            if (trace) fprintf(stderr, "%s%s=%.3f", c->mark_phase[i] == PH_REFIT ? "\n  " : " ", names[c->mark_phase[i]], ms);
+        }
+        if (trace) fprintf(stderr, "\n");
+        return CLSN_OK;
     }
-    s.n_ccd_passes = cd;
-    s.still_colliding = is_collision ? 1 : 0;
-    if (is_collision && c->impact_zones) {  // detectCollision's tail, dcollid.cpp:464-467
-        clsn_zone_stats zs;
-        if ((r = clsn_compute_impact_zone(c, c->zone_max_iter, &zs))) return r;
-        s.zone_iterations = zs.iterations;
-        s.zones = zs.zones;
-    }
-    if ((r = clsn_boundary(c))) return r;
-    if ((r = clsn_final_position(c))) return r;
-    if (c->strain_limiting && (r = strain_enqueue(c))) return r;  // reduceSuperelast, dcollid.cpp:355
-    CK(cudaEventRecord(c->ev[1], c->stream));
-    CK(cudaMemcpyAsync(c->h_counters, c->counters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    if (c->h_counters[CTR_ERROR]) return fail(c, CLSN_E_NUMERIC, "NaN/Inf in the collision step (reference: clean_up(ERROR))");
-    CK(cudaEventElapsedTime(&s.ms_total, c->ev[0], c->ev[1]));
-    if (c->strain_pending) strain_finish(c, &s.strain_sweeps, &s.strain_edges);
-    for (size_t i = 1; i < c->n_marks; ++i) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, c->marks[i - 1], c->marks[i]) == cudaSuccess) s.ms_phase[c->mark_phase[i]] += ms;
-    }
-    return CLSN_OK;
+    return fail(c, CLSN_E_NOMEM, "pair/record buffers kept overflowing");
+}
+
+static int resolve_io(clsn_ctx* c, clsn_step_stats* stats, const HostOut& out)
+{
+    clsn_step_stats s;
+    memset(&s, 0, sizeof(s));
+    c->timing = c->phase_timing;   // phase marks are only recorded inside a whole step
+    c->n_marks = 0;
+    const int r = resolve_impl(c, s, out);
+    c->timing = false;  // also on the error paths: a failed step must not leave the marks armed
+    c->strain_pending = false;
+    if (r == CLSN_OK && stats) *stats = s;
+    return r;
 }
 
 extern "C" int clsn_resolve(clsn_ctx* c, clsn_step_stats* stats)
 {
     if (!c || !c->V) return CLSN_E_ARG;
     cudaSetDevice(c->device);
-    clsn_step_stats s;
-    memset(&s, 0, sizeof(s));
-    c->timing = true;   // phase marks are only recorded inside a whole step
-    c->n_marks = 0;
-    const int r = resolve_impl(c, s);
-    c->timing = false;  // also on the error paths: a failed step must not leave the marks armed
-    c->strain_pending = false;
-    if (r == CLSN_OK && stats) *stats = s;
-    return r;
+    return resolve_io(c, stats, HostOut());
 }
 
 extern "C" int clsn_step_host(clsn_ctx* c, const double* x_old, const double* x_new, double* x_out, double* vel_inout,
@@ -1775,17 +1962,20 @@ extern "C" int clsn_step_host(clsn_ctx* c, const double* x_old, const double* x_
     if (!c || !c->V || !x_old || !x_new || !x_out) return CLSN_E_ARG;
     int r;
     if ((r = clsn_upload_state(c, x_old, x_new))) return r;
-    if ((r = clsn_resolve(c, stats))) return r;
     const size_t n = 3 * (size_t)c->V;
     // scratch for avgVel / has_collsn lives in the context's pinned buffer (3V doubles + V bytes)
-    double* av = c->h_pin;
-    uint8_t* has = has_out ? has_out : reinterpret_cast<uint8_t*>(c->h_pin + n);
-    // avgVel only travels back when the caller wants velocities updated
-    if ((r = clsn_download_state(c, x_out, vel_inout ? av : nullptr, (has_out || vel_inout) ? has : nullptr))) return r;
-    if (vel_inout)  // updateFinalVelocity, dcollid.cpp:598-624
+    HostOut out;
+    out.x = x_out;
+    out.avgvel = vel_inout ? c->h_pin : nullptr;   // avgVel only travels back when the caller wants velocities updated
+    out.has = has_out ? has_out : (vel_inout ? reinterpret_cast<uint8_t*>(c->h_pin + n) : nullptr);
+    if ((r = resolve_io(c, stats, out))) return r;   // upload, step and download: one synchronisation
+    if (vel_inout) {  // updateFinalVelocity, dcollid.cpp:598-624
+        const double* av = out.avgvel;
+        const uint8_t* has = out.has;
         for (int p = 0; p < c->V; ++p)
             if (has[p])
                 for (int j = 0; j < 3; ++j) vel_inout[3 * (size_t)p + j] = av[3 * (size_t)p + j];
+    }
     return CLSN_OK;
 }
 
@@ -1831,7 +2021,7 @@ extern "C" int clsn_export_records(clsn_ctx* c, void** d_prec, int64_t* n_prec, 
     if (n_prec) *n_prec = c->last_nprec;
     if (d_brec) *d_brec = c->brec.p;
     if (n_brec) *n_brec = c->last_nbrec;
-    if (true_pairs) *true_pairs = (int64_t)c->h_counters[CTR_TRUE];
+    if (true_pairs) *true_pairs = (int64_t)c->last_true;
     return CLSN_OK;
 }
 
@@ -1919,7 +2109,7 @@ extern "C" int clsn_get_accumulators(clsn_ctx* c, double* imp, double* fric, int
         CK(cudaMemcpy(tmp.p, c->imp_rg.p, 3 * (size_t)c->nbody * sizeof(double), cudaMemcpyDeviceToDevice));
         const long long nbrec = c->imp_nprec >= 0 ? c->imp_nbrec : c->last_nbrec;
         if (nbrec > 0) {
-            unsigned long long* n_dev = c->imp_nprec >= 0 ? c->counters.p + 33 : c->counters.p + CTR_BREC;
+            unsigned long long* n_dev = c->imp_nprec >= 0 ? c->counters.p + 33 : c->ctr + CTR_BREC;
             const BodyRec* brec = c->imp_nprec >= 0 ? c->imp_brec : c->brec.p;
             const long long cap = c->imp_nprec >= 0 ? nbrec : (long long)c->brec.n;
             k_reduce_bodies<<<nblk(c->nbody, 64), 64, 0, c->stream>>>(brec, n_dev, cap, c->nbody, tmp.p);
@@ -1939,5 +2129,6 @@ extern "C" int clsn_set_body_accumulators(clsn_ctx* c, const double* imp_rg, con
     CK(cudaStreamSynchronize(c->stream));
     if (imp_rg) CK(cudaMemcpy(c->imp_rg.p, imp_rg, 3 * (size_t)c->nbody * sizeof(double), cudaMemcpyHostToDevice));
     if (cnt_rg) CK(cudaMemcpy(c->cnt_rg.p, cnt_rg, (size_t)c->nbody * sizeof(int), cudaMemcpyHostToDevice));
+    if (cnt_rg) c->cnt_rg_preset = true;
     return CLSN_OK;
 }

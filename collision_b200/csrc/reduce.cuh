@@ -18,8 +18,8 @@ __global__ void k_scatter(const PointRec* __restrict__ rec, const unsigned long 
                           long long cap, const int* __restrict__ offs, int* fill, int* __restrict__ perm,
                           unsigned long long* __restrict__ skey)
 {
-    long long n = (long long)*n_rec_ptr;
-    if (n > cap) n = cap;
+    const long long n = (long long)*n_rec_ptr;
+    if (n > cap) return;   // the record list overflowed: offs[] describes records that were never stored; the step is repeated
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
         const ulonglong2 h = *reinterpret_cast<const ulonglong2*>(rec + r);
         const int p = (int)(unsigned)h.y;
@@ -90,8 +90,10 @@ __global__ void __launch_bounds__(256)
 k_reduce_points(const PointRec* __restrict__ rec, const int* __restrict__ offs, const int* __restrict__ cnt, int V,
                 const int* __restrict__ perm, int* __restrict__ perm_sorted, const unsigned long long* __restrict__ skey,
                 const uint8_t* __restrict__ vflags, Vec4* av, uint8_t* has, uint8_t* dirty, int mode, double* __restrict__ acc_imp,
-                double* __restrict__ acc_fric, unsigned long long* counters)
+                double* __restrict__ acc_fric, unsigned long long* counters, const unsigned long long* __restrict__ n_rec_ptr,
+                long long cap)
 {
+    if ((long long)*n_rec_ptr > cap) return;   // overflowed list (see k_scatter)
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     for (int p = blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < V; p += gridDim.x * warps_per_block) {

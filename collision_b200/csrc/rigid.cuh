@@ -90,8 +90,9 @@ __global__ void k_rigid_sums(int nlists, const int* __restrict__ list_offs, cons
 __global__ void k_rigid_apply(int npts, const int* __restrict__ list_pts, const int* __restrict__ pt_list,
                               const RigidBodyState* __restrict__ st, const Vec4* __restrict__ xo, Vec4* av,
                               const uint8_t* __restrict__ vflags, double dt, unsigned long long* counters,
-                              uint8_t* dirty)
+                              uint8_t* dirty, const unsigned long long* __restrict__ gate)
 {
+    if (gate && *gate == 0ull) return;   // the pass this belongs to did not run (see enqueue_detect in clsn.cu)
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= npts) return;
     const int p = list_pts[t];
@@ -230,11 +231,11 @@ struct RigidTopo {
     }
 
     int rigidify(const Vec4* xo, Vec4* av, const uint8_t* vflags, double m, double dt, unsigned long long* counters, cudaStream_t st,
-                 uint8_t* dirty = nullptr)
+                 uint8_t* dirty = nullptr, const unsigned long long* gate = nullptr)
     {
         if (nlists == 0) return 0;
         k_rigid_sums<<<(nlists + 31) / 32, 32, 0, st>>>(nlists, d_offs, d_pts, xo, av, m, dt, d_state);
-        k_rigid_apply<<<(npts + 255) / 256, 256, 0, st>>>(npts, d_pts, d_pt_list, d_state, xo, av, vflags, dt, counters, dirty);
+        k_rigid_apply<<<(npts + 255) / 256, 256, 0, st>>>(npts, d_pts, d_pt_list, d_state, xo, av, vflags, dt, counters, dirty, gate);
         return cudaGetLastError() == cudaSuccess ? 0 : -1;
     }
 };
