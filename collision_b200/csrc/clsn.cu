@@ -128,11 +128,23 @@ __device__ __forceinline__ FBox fbox_union(const FBox& a, const FBox& b)
 // FP32 with directed rounding: the gap is rounded down, the margin up, so the cull stays conservative.
 __device__ __forceinline__ bool boxes_far(const FBox& a, const FBox& b, float h2, float rel)
 {
+    float ext[3], emax = 0.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        ext[d] = fmaxf(__fsub_ru(a.hi[d], a.lo[d]), __fsub_ru(b.hi[d], b.lo[d]));
+        emax = fmaxf(emax, ext[d]);
+    }
+    // The 2e-3 term covers the noise of the reference's barycentric coordinates on the slivers that still pass its
+    // ABSOLUTE degeneracy gate |det| >= 1000 MACH_EPS (dcollid3d.cpp:797-799): relative error <= eps L^4 / det <= L^4 / 1000
+    // for edge length L, i.e. it is a unit-scale figure.  For features larger than 1 the slack grows with L^4.
+    if (emax > 1.f) {
+        const float e2 = __fmul_ru(emax, emax);
+        rel = __fmul_ru(rel, __fmul_ru(e2, e2));
+    }
     bool far = false;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        const float ext = fmaxf(__fsub_ru(a.hi[d], a.lo[d]), __fsub_ru(b.hi[d], b.lo[d]));
-        const float m = __fmaf_ru(rel, ext, h2);
+        const float m = __fmaf_ru(rel, ext[d], h2);
         far = far || (__fsub_rd(a.lo[d], b.hi[d]) > m) || (__fsub_rd(b.lo[d], a.hi[d]) > m);
     }
     return far;
@@ -800,6 +812,12 @@ struct clsn_ctx {
     DevBuf<int> vbody;
     DevBuf<double> body_mass;
     RigidTopo rigid;
+    // updateFinalForRG (dcollid.cpp:626-675): movable points of every body in hseList walk order (first occurrences)
+    std::vector<int> rg_offs, rg_pts;      // CSR over bodies
+    DevBuf<int> d_rg_pts;
+    DevBuf<double> d_rg_state;             // gathered per listed point: avgVel xyz + has_collsn (4 doubles)
+    std::vector<double> mrg_com;           // CollisionSolver::mrg_com (collid.h:174): lives across steps
+    std::vector<uint8_t> mrg_valid;
     // impact zones (host fail-safe): host topology + union-find, device lists
     std::vector<int> h_tri, h_tri_surf, h_bond;
     std::vector<uint8_t> h_vflags;
@@ -971,7 +989,7 @@ extern "C" void clsn_destroy(clsn_ctx* c)
     c->cub_tmp.release(); c->pairs.release(); c->dbg_cand.release(); c->feats.release(); c->pair_hit.release(); c->rootrecs.release(); c->hits.release(); c->unc.release(); c->prec.release(); c->prec_sorted.release(); c->brec.release();
     c->contacts.release(); c->cnt.release(); c->offs.release(); c->fill.release(); c->perm.release();
     c->perm_sorted.release(); c->skey.release(); c->counters.release(); c->acc_imp.release(); c->acc_fric.release();
-    c->rigid.release(); c->zone_lists.release(); c->strain.release();
+    c->rigid.release(); c->zone_lists.release(); c->strain.release(); c->d_rg_pts.release(); c->d_rg_state.release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     for (auto& e : c->ev) cudaEventDestroy(e);
@@ -1125,6 +1143,53 @@ extern "C" int clsn_set_topology(clsn_ctx* c, int V, int T, const int32_t* tri_i
     c->zone_uf_ready = false;
     c->strain.release_schedule();  // rest lengths belong to the old elements: clsn_set_rest_lengths again
     c->strain.have_len0 = false;
+    {   // Rigid-rigid impulses are kept per hyper-surface (k_reduce_bodies / k_apply_bodies), the reference spreads them over
+        // the union-find list of the hit point (SpreadImpactZoneImpulse, dcollid.cpp:1101-1115).  The two agree iff every
+        // movable hyper-surface is ONE connected triangle component and holds movable points only: checked here.
+        HostUF uf;
+        uf.reset(V);
+        uf.merge_movable_bodies(T, tri_idx, tri_surf, vflags);
+        std::vector<int> body_root((size_t)nbody, -1);
+        std::vector<uint8_t> body_movable((size_t)nbody, 0), body_other((size_t)nbody, 0);
+        for (int v = 0; v < V; ++v) {
+            if (vflags[v] & 2) {
+                body_movable[vbody[v]] = 1;
+                const int r = uf.find(v);
+                if (body_root[vbody[v]] < 0) body_root[vbody[v]] = r;
+                else if (body_root[vbody[v]] != r)
+                    return fail(c, CLSN_E_UNSUPPORTED, "a movable rigid hyper-surface must be one connected component (vbody spans several)");
+            } else if (!(vflags[v] & 1)) {
+                body_other[vbody[v]] = 1;
+            }
+        }
+        for (int b = 0; b < nbody; ++b)
+            if (body_movable[b] && body_other[b])
+                return fail(c, CLSN_E_UNSUPPORTED, "a hyper-surface mixes movable rigid points with fabric points");
+    }
+    {   // movable points per body in the order updateFinalForRG meets them (hseList order, points in element order)
+        std::vector<std::vector<int>> per((size_t)nbody);
+        std::vector<uint8_t> seen((size_t)V, 0);
+        auto visit = [&](int p) {
+            if (!(vflags[p] & 2) || seen[p]) return;
+            seen[p] = 1;
+            per[vbody[p]].push_back(p);
+        };
+        for (size_t i = 0; i < 3 * (size_t)T; ++i) visit(tri_idx[i]);
+        for (size_t i = 0; i < 2 * (size_t)B; ++i) visit(bond_idx[i]);
+        c->rg_offs.assign(1, 0);
+        c->rg_pts.clear();
+        for (int b = 0; b < nbody; ++b) {
+            c->rg_pts.insert(c->rg_pts.end(), per[b].begin(), per[b].end());
+            c->rg_offs.push_back((int)c->rg_pts.size());
+        }
+        if (!c->rg_pts.empty()) {
+            CK(c->d_rg_pts.reserve(c->rg_pts.size()));
+            CK(c->d_rg_state.reserve(4 * c->rg_pts.size()));
+            CK(cudaMemcpy(c->d_rg_pts.p, c->rg_pts.data(), c->rg_pts.size() * sizeof(int), cudaMemcpyHostToDevice));
+        }
+        c->mrg_com.assign(3 * (size_t)nbody, 0.0);
+        c->mrg_valid.assign((size_t)nbody, 0);
+    }
     // host-side restatement of createImpZoneForRG's union-find lists (topology only)
     int r = c->rigid.build(V, T, tri_idx, tri_surf, vflags);
     if (r != 0) return fail(c, CLSN_E_CUDA, "rigid-body topology upload failed");
@@ -1599,6 +1664,7 @@ extern "C" int clsn_boundary(clsn_ctx* c)
                                                          p.lo[1], p.lo[2], p.hi[0], p.hi[1], p.hi[2]);
     CK(cudaGetLastError());
     c->launches += 1;
+    c->dirty_valid = false;   // the clamp rewrites avgVel outside the impulse reduction: no pair may be skipped as untouched
     return CLSN_OK;
 }
 
@@ -1975,6 +2041,64 @@ extern "C" int clsn_step_host(clsn_ctx* c, const double* x_old, const double* x_
         for (int p = 0; p < c->V; ++p)
             if (has[p])
                 for (int j = 0; j < 3; ++j) vel_inout[3 * (size_t)p + j] = av[3 * (size_t)p + j];
+    }
+    return CLSN_OK;
+}
+
+// ------------------------------------------------------------------ updateFinalForRG
+__global__ void k_gather_rg(int n, const int* __restrict__ pts, const Vec4* __restrict__ av, const uint8_t* __restrict__ has,
+                            double* __restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int p = pts[t];
+    const Vec4 v = av[p];
+    out[4 * (size_t)t] = v.x; out[4 * (size_t)t + 1] = v.y; out[4 * (size_t)t + 2] = v.z;
+    out[4 * (size_t)t + 3] = has[p] ? 1.0 : 0.0;
+}
+
+// dcollid.cpp:626-675, run by updateFinalVelocity at the end of resolveCollision.  Per movable body, with its points in
+// the order the reference's hseList walk meets them: q = the first point, p* = the first point with has_collsn.
+//   p* exists:  center_of_mass_velo = avgVel[p*];  center_of_mass = avgVel[p*] * dt + C,  C = mrg_com[body] if p* == q
+//               (the value left by the previous call) else the incoming center_of_mass;  mrg_com[body] = new centre
+//   otherwise:  mrg_com[body] = incoming center_of_mass
+// A body met for the first time reads mrg_com before the reference ever wrote it (an empty std::vector there): seeded with
+// the incoming centre of mass.  Only the listed points' avgVel / has_collsn cross PCIe (32 B per movable point).
+extern "C" int clsn_update_rigid_bodies(clsn_ctx* c, double* center_of_mass, double* center_of_mass_velo)
+{
+    if (!c || !c->V || !center_of_mass || !center_of_mass_velo) return CLSN_E_ARG;
+    const size_t M = c->rg_pts.size();
+    if (M == 0) return CLSN_OK;
+    cudaSetDevice(c->device);
+    k_gather_rg<<<nblk((long long)M, 256), 256, 0, c->stream>>>((int)M, c->d_rg_pts.p, c->av.p, c->has.p, c->d_rg_state.p);
+    CK(cudaGetLastError());
+    c->launches += 1;
+    std::vector<double> st(4 * M);
+    CK(cudaMemcpyAsync(st.data(), c->d_rg_state.p, 4 * M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const double dt = c->prm.dt;
+    for (int b = 0; b < c->nbody; ++b) {
+        const int beg = c->rg_offs[b], end = c->rg_offs[b + 1];
+        if (beg == end) continue;
+        double* com = center_of_mass + 3 * (size_t)b;
+        double* mrg = &c->mrg_com[3 * (size_t)b];
+        if (!c->mrg_valid[b]) {
+            for (int j = 0; j < 3; ++j) mrg[j] = com[j];
+            c->mrg_valid[b] = 1;
+        }
+        int hit = -1;
+        for (int t = beg; t < end && hit < 0; ++t)
+            if (st[4 * (size_t)t + 3] != 0.0) hit = t;
+        if (hit != beg)   // the walk meets a point without a collision first: mrg_com <- the incoming centre of mass
+            for (int j = 0; j < 3; ++j) mrg[j] = com[j];
+        if (hit >= 0) {
+            for (int j = 0; j < 3; ++j) {
+                const double v = st[4 * (size_t)hit + j];
+                center_of_mass_velo[3 * (size_t)b + j] = v;
+                com[j] = v * dt + mrg[j];
+            }
+            for (int j = 0; j < 3; ++j) mrg[j] = com[j];
+        }
     }
     return CLSN_OK;
 }

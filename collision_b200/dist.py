@@ -93,6 +93,7 @@ class DistributedSolver:
         self.small_pass_records = 65536   # passes with fewer records (all ranks together) skip the all-to-all
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        assert self.world <= 64, "clsn_bucket_records keeps 64 owner buckets"
         c = solver.ctx
         c.check(c.L.clsn_set_slice(c.h, self.rank, self.world))
         self.device = torch.device("cuda", torch.cuda.current_device())
@@ -164,9 +165,10 @@ class DistributedSolver:
         c.check(c.L.clsn_apply_stage(c.h, 1, 0))
         # every rank now holds the final avgVel / flags of its own vertex range: one all-gather of packed slices
         av, has, dirty = self._state_views()
-        lo, hi = self.rank * per, min(V, (self.rank + 1) * per)
+        lo = min(V, self.rank * per)      # V < per * (G - 1): the last ranks own nothing
+        hi = min(V, (self.rank + 1) * per)
         mine = torch.zeros(per * 34, dtype=torch.uint8, device=self.device)
-        n = hi - lo
+        n = max(0, hi - lo)
         mine[: n * 32] = av[lo * 32: hi * 32]
         mine[per * 32: per * 32 + n] = has[lo:hi]
         mine[per * 33: per * 33 + n] = dirty[lo:hi]

@@ -154,6 +154,8 @@ void CollisionSolver::gatherTopology(const INTERFACE* intfc)
     }
     m_points.swap(points); m_point_id.swap(ids); m_tri.swap(tri); m_tri_surf.swap(tri_surf); m_bond.swap(bond);
     m_flags.swap(flags); m_body.swap(body); m_body_mass.swap(body_mass);
+    m_body_hs.assign(m_body_mass.size(), nullptr);
+    for (auto& kv : body_of) m_body_hs[kv.second] = const_cast<HYPER_SURF*>(kv.first);
     const int V = (int)m_points.size();
     int rc = clsn_set_topology(m_ctx, V, (int)m_tri_surf.size(), m_tri.data(), m_tri_surf.data(), (int)m_bond.size() / 2,
                                m_bond.data(), m_flags.data(), m_body.data(), (int)m_body_mass.size(), m_body_mass.data());
@@ -221,6 +223,24 @@ void CollisionSolver::resolveCollision()  // dcollid.cpp:317-362
         }
         sl->collsn_num = 0;
     }
+    // updateFinalForRG, dcollid.cpp:626-675: centre of mass and its velocity of every movable body that was hit
+    // (mrg_com lives inside the context); HYPER_SURF data is caller-owned, so it is gathered and scattered here
+    const size_t nb = m_body_hs.size();
+    std::vector<double> com(3 * nb, 0.0), velo(3 * nb, 0.0);
+    for (size_t b = 0; b < nb; ++b)
+        if (m_body_hs[b])
+            for (int j = 0; j < 3; ++j) {
+                com[3 * b + j] = m_body_hs[b]->center_of_mass[j];
+                velo[3 * b + j] = m_body_hs[b]->center_of_mass_velo[j];
+            }
+    rc = clsn_update_rigid_bodies(m_ctx, com.data(), velo.data());
+    if (rc != CLSN_OK) fail(rc, "clsn_update_rigid_bodies");
+    for (size_t b = 0; b < nb; ++b)
+        if (m_body_hs[b])
+            for (int j = 0; j < 3; ++j) {
+                m_body_hs[b]->center_of_mass[j] = com[3 * b + j];
+                m_body_hs[b]->center_of_mass_velo[j] = velo[3 * b + j];
+            }
 }
 
 // Single-pair entry points of the reference (collid.h:199-200).  They run the same kernels on a

@@ -158,6 +158,7 @@ protected:
     std::vector<uint8_t> m_flags;
     std::vector<int32_t> m_body;
     std::vector<double> m_body_mass;
+    std::vector<HYPER_SURF*> m_body_hs;   // body index -> the caller's HYPER_SURF (center_of_mass / center_of_mass_velo)
     std::vector<double> m_xold, m_xnew, m_xout, m_vel;
     std::vector<uint8_t> m_has;
     clsn_step_stats m_stats;

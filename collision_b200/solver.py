@@ -137,6 +137,7 @@ def load_library():
     L.clsn_set_strain_limiting.argtypes = [V, I]
     L.clsn_strain_limit.argtypes = [V, P(C.c_int32), P(C.c_int32)]
     L.clsn_compute_impact_zone.argtypes = [V, I, P(clsn_zone_stats)]
+    L.clsn_update_rigid_bodies.argtypes = [V, P(D), P(D)]
     _lib = L
     return L
 
@@ -326,9 +327,18 @@ class CollisionSolver3d:
             self._x_old[~keep] = x[~keep]
 
     # ---- the step
-    def resolveCollision(self, x_old, x, vel, x_out=None):
+    def updateFinalForRG(self, center_of_mass, center_of_mass_velo):
+        """dcollid.cpp:626-675: (nbody,3) arrays of the caller's HYPER_SURF data, updated in place for every movable body
+        that collided in the last step (the reference calls this at the end of updateFinalVelocity)."""
+        a, b = center_of_mass, center_of_mass_velo
+        assert a.dtype == np.float64 and a.flags.c_contiguous and b.dtype == np.float64 and b.flags.c_contiguous
+        assert a.shape == (self.ctx.nbody, 3) and b.shape == (self.ctx.nbody, 3)
+        self.ctx.check(self.ctx.L.clsn_update_rigid_bodies(self.ctx.h, _dp(a), _dp(b)))
+
+    def resolveCollision(self, x_old, x, vel, x_out=None, bodies=None):
         """x_old: start-of-step positions; x: candidate positions on entry, final positions on return
-        (or written to x_out when given); vel: updated where has_collsn (updateFinalVelocity).
+        (or written to x_out when given); vel: updated where has_collsn (updateFinalVelocity);
+        bodies: optional (center_of_mass, center_of_mass_velo), (nbody,3) each, updated like updateFinalForRG does.
         Returns has_collsn (V,) uint8."""
         c = self.ctx
         self._push_params()
@@ -341,6 +351,8 @@ class CollisionSolver3d:
         c.check(c.L.clsn_step_host(c.h, _dp(xo), _dp(x), _dp(out), _dp(vel), _bp(has), C.byref(st)))
         self.has_collision = bool(st.has_collision)
         self.last_stats = st.as_dict()
+        if bodies is not None:
+            self.updateFinalForRG(*bodies)
         return has
 
     # ---- single phases / readbacks (parity tests)

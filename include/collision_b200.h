@@ -150,6 +150,13 @@ int clsn_download_state(clsn_ctx*, double* x, double* avgvel, uint8_t* has_colls
 int clsn_step_host(clsn_ctx*, const double* x_old, const double* x_new, double* x_out, double* vel_inout,
                    uint8_t* has_collsn_out, clsn_step_stats* stats);
 
+/* updateFinalForRG (dcollid.cpp:626-675, the tail of updateFinalVelocity): for every movable rigid body with a point
+ * that collided in this step, write the body's centre-of-mass velocity (avgVel of the first such point in hseList order)
+ * and centre of mass (that velocity * dt + the centre recorded at the end of the previous call, CollisionSolver::mrg_com,
+ * kept inside the context) into the caller's HYPER_SURF data.  Arrays are [3 * nbody], indexed like body_mass; entries of
+ * bodies that were not hit are left alone.  Call after clsn_resolve / clsn_step_host. */
+int clsn_update_rigid_bodies(clsn_ctx*, double* center_of_mass, double* center_of_mass_velo);
+
 /* ---- per step, device buffers (inputs already resident in HBM; 3V doubles, xyz per vertex) */
 int clsn_upload_state_device(clsn_ctx*, const double* d_x_old, const double* d_x_new);
 int clsn_download_state_device(clsn_ctx*, double* d_x, double* d_avgvel);

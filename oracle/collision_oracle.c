@@ -44,6 +44,8 @@ struct orc_ctx {
     double* bond_len0; /* BOND::length0 */
     int have_len0, strain_limiting;
     /* results of the last detect */
+    double* mrg_com;          /* 3*nhs: CollisionSolver::mrg_com (collid.h:174), lives across steps */
+    unsigned char* mrg_valid; /* nhs */
     int* cand; long n_cand, cap_cand;
     int* truep; long n_true, cap_true;
     orc_contact* con; long n_con, cap_con;
@@ -1032,6 +1034,49 @@ void orc_final_velocity(orc_ctx* c, double* vel) /* dcollid.cpp:598-624 */
             for (int j = 0; j < 3; ++j) vel[3 * p + j] = c->av[3 * p + j];
 }
 
+/* updateFinalForRG, dcollid.cpp:626-675 (called at the end of updateFinalVelocity): walk hseList, points in element
+ * order; the first point of a movable body that has has_collsn sets that body's centre-of-mass velocity to its avgVel and
+ * the centre of mass to avgVel * dt + mrg_com[body]; mrg_com[body] is refreshed from the (possibly just updated) centre of
+ * mass the first time the body is met and again right after such an update.  com / com_velo: 3*nhs, caller-owned
+ * (HYPER_SURF::center_of_mass / center_of_mass_velo), in/out.  A body met for the very first time whose first point already
+ * collides reads mrg_com before the reference ever wrote it (an empty std::vector there): seeded with the incoming centre
+ * of mass, as oracle/ref_wrapper.cpp seeds the reference. */
+void orc_update_final_for_rg(orc_ctx* c, double* com, double* com_velo)
+{
+    unsigned char* in_mrg = (unsigned char*)calloc((size_t)c->nhs + 1, 1);
+    signed char* visited = (signed char*)malloc((size_t)c->nhs + 1);   /* -1 absent, 0 false, 1 true */
+    memset(visited, -1, (size_t)c->nhs + 1);
+    for (int e = 0; e < c->N; ++e) {
+        const int np = e < c->T ? 3 : 2;
+        const int* pts = e < c->T ? c->tri + 3 * e : c->bond + 2 * (e - c->T);
+        for (int i = 0; i < np; ++i) {
+            const int p = pts[i];
+            if (!(c->flags[p] & 2)) continue;
+            const int rg = c->vhs[p];
+            if (!c->mrg_valid[rg]) {
+                for (int j = 0; j < 3; ++j) c->mrg_com[3 * rg + j] = com[3 * rg + j];
+                c->mrg_valid[rg] = 1;
+            }
+            if (c->has[p] && !in_mrg[rg]) {
+                in_mrg[rg] = 1;
+                for (int j = 0; j < 3; ++j) {
+                    com_velo[3 * rg + j] = c->av[3 * p + j];
+                    com[3 * rg + j] = c->av[3 * p + j] * c->dt + c->mrg_com[3 * rg + j];
+                }
+                visited[rg] = 0;
+            }
+            if (visited[rg] <= 0) {
+                for (int j = 0; j < 3; ++j) c->mrg_com[3 * rg + j] = com[3 * rg + j];
+                visited[rg] = 1;
+            }
+        }
+    }
+    free(in_mrg);
+    free(visited);
+}
+
+void orc_set_has_collsn(orc_ctx* c, const unsigned char* has) { memcpy(c->has, has, (size_t)c->V); }
+
 /* resolveCollision, dcollid.cpp:317-362, with detectProximity :390-406 and detectCollision :430-468 */
 void orc_resolve(orc_ctx* c, double* vel, long* stats)
 {
@@ -1087,6 +1132,8 @@ orc_ctx* orc_create(int V, int T, const int* tri_idx, const int* tri_surf, int B
     memcpy(c->hs_mass, hs_mass, (size_t)nhs * sizeof(double));
     c->eps = 1e-6; c->thickness = 1e-4; c->k = 1000; c->m = 0.01; c->lambda = 0.02; c->cr = 0.0; c->dt = 1e-3;
     for (int i = 0; i < 3; ++i) { c->lo[i] = -1e30; c->hi[i] = 1e30; }
+    c->mrg_com = (double*)calloc((size_t)3 * nhs + 1, sizeof(double));
+    c->mrg_valid = (unsigned char*)calloc((size_t)nhs + 1, 1);
     size_t n3 = (size_t)3 * V + 1;
     c->xo = (double*)calloc(n3, sizeof(double));
     c->x = (double*)calloc(n3, sizeof(double));
@@ -1113,7 +1160,7 @@ void orc_destroy(orc_ctx* c)
     free(c->tri); free(c->tri_surf); free(c->bond); free(c->flags); free(c->vhs); free(c->hs_mass);
     free(c->xo); free(c->x); free(c->av); free(c->imp); free(c->fric); free(c->cnt); free(c->has);
     free(c->imp_rg); free(c->cnt_rg); free(c->uf_root); free(c->uf_next); free(c->uf_tail); free(c->uf_weight); free(c->sorted); free(c->tri_len0); free(c->bond_len0);
-    free(c->cand); free(c->truep); free(c->con);
+    free(c->cand); free(c->truep); free(c->con); free(c->mrg_com); free(c->mrg_valid);
     free(c);
 }
 

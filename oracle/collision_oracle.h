@@ -87,6 +87,9 @@ int orc_strain_limit(orc_ctx*, long* num_edges);
 
 /* readbacks */
 void orc_get_f64(orc_ctx*, int field, double* out); /* 0 x_old 1 x 2 avgVel 3 imp 4 fric (3V each) */
+/* updateFinalForRG (dcollid.cpp:626-675): com / com_velo [3*nhs] in/out, mrg_com kept inside the context */
+void orc_update_final_for_rg(orc_ctx*, double* com, double* com_velo);
+void orc_set_has_collsn(orc_ctx*, const unsigned char* has);   /* V flags (tests: state taken from the reference) */
 void orc_get_i32(orc_ctx*, int field, int* out);    /* 0 cnt 1 has_collsn (V each) */
 void orc_get_body(orc_ctx*, double* imp_rg /*3*nhs*/, int* cnt_rg /*nhs*/);
 void orc_set_body(orc_ctx*, const double* imp_rg, const int* cnt_rg);

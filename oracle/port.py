@@ -71,6 +71,8 @@ def lib():
         L.orc_final_position.argtypes = [V]
         L.orc_final_velocity.argtypes = [V, P(D)]
         L.orc_resolve.argtypes = [V, P(D), P(C.c_long)]
+        L.orc_update_final_for_rg.argtypes = [V, P(D), P(D)]
+        L.orc_set_has_collsn.argtypes = [V, P(C.c_ubyte)]
         L.orc_enable_impact_zones.argtypes = [V, I]
         L.orc_set_imp_zone.argtypes = [V, I]
         L.orc_zone_velocity.argtypes = [V]
@@ -176,6 +178,15 @@ class OracleSolver:
     def final_velocity(self, vel):
         assert vel.dtype == np.float64 and vel.flags.c_contiguous
         lib().orc_final_velocity(self.h, _dp(vel))
+
+    def set_has_collsn(self, has):
+        a = np.ascontiguousarray(has, dtype=np.uint8)
+        lib().orc_set_has_collsn(self.h, _bp(a))
+
+    def update_final_for_rg(self, com, com_velo):
+        """updateFinalForRG (dcollid.cpp:626-675) on caller-owned (nhs,3) centre-of-mass arrays, in place."""
+        assert com.dtype == np.float64 and com.flags.c_contiguous and com_velo.dtype == np.float64 and com_velo.flags.c_contiguous
+        lib().orc_update_final_for_rg(self.h, _dp(com), _dp(com_velo))
 
     def resolve(self, vel):
         assert vel.dtype == np.float64 and vel.flags.c_contiguous

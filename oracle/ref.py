@@ -87,6 +87,8 @@ def lib(flavour: str | None = None):
                                        C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.clsn_ref_clock_reset.argtypes = []
+        L.clsn_ref_set_body.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.clsn_ref_get_body.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.clsn_ref_feature_batch.restype = C.c_long
         L.clsn_ref_feature_batch.argtypes = [C.c_long, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
                                              C.POINTER(C.c_double), C.POINTER(C.c_ubyte), C.POINTER(C.c_double),
@@ -156,6 +158,21 @@ class RefSolver:
     def puti(self, field, a):
         a = np.ascontiguousarray(a, dtype=np.int32)
         self.L.clsn_ref_set_i32(self.h, field, _ip(a))
+
+    def set_bodies(self, com, com_velo):
+        """HYPER_SURF::center_of_mass / center_of_mass_velo of every hyper-surface ((nhs,3) arrays; caller-owned in the reference)"""
+        com = np.ascontiguousarray(com, dtype=np.float64)
+        vel = np.ascontiguousarray(com_velo, dtype=np.float64)
+        for i in range(len(com)):
+            self.L.clsn_ref_set_body(self.h, i, _dp(com[i]), _dp(vel[i]))
+
+    def get_bodies(self, nhs):
+        com, vel = np.zeros((nhs, 3)), np.zeros((nhs, 3))
+        for i in range(nhs):
+            a, b = np.zeros(3), np.zeros(3)
+            self.L.clsn_ref_get_body(self.h, i, _dp(a), _dp(b))
+            com[i], vel[i] = a, b
+        return com, vel
 
     # ---- driving
     def assemble(self, dt):

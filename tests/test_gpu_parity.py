@@ -67,15 +67,25 @@ def test_whole_step_parity(name):
     gpu, orc = make_pair(sc)
     gpu.set_debug(False, False)
     x, vel = sc.x.copy(), sc.vel.copy()
+    # updateFinalForRG (dcollid.cpp:626-675): the caller's centre-of-mass data of every hyper-surface, moved between
+    # the steps the way the application's propagation would
+    nhs = len(sc.hs_mass)
+    com_g = np.stack([sc.x[sc.vhs == b].mean(axis=0) if (sc.vhs == b).any() else np.zeros(3) for b in range(nhs)])
+    velo_g = np.zeros((nhs, 3))
+    com_o, velo_o = com_g.copy(), velo_g.copy()
     for step in range(4):
         gpu.set_exact_stats(step % 2 == 0)   # pruned traversal on odd steps: same results, fewer candidates counted
         xn = x + sc.dt * vel
         orc.set_state(x, xn)
         vo = vel.copy()
         st_o = orc.resolve(vo)
+        orc.update_final_for_rg(com_o, velo_o)
         xg = xn.copy()
         vg = vel.copy()
-        has = gpu.resolveCollision(x, xg, vg)
+        has = gpu.resolveCollision(x, xg, vg, bodies=(com_g, velo_g))
+        assert same_bits(com_g, com_o) and same_bits(velo_g, velo_o), "updateFinalForRG: centre of mass / velocity differ"
+        com_g += sc.dt * velo_g
+        com_o += sc.dt * velo_o
         st = gpu.last_stats
         assert st["proximity"]["true_pairs"] == st_o[0]
         assert st["n_ccd_passes"] == st_o[1]

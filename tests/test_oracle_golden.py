@@ -261,3 +261,65 @@ def test_whole_step_matches_reference_when_available():
         assert np.abs(xr - o.get(port.F_X)).max() <= 1e-8 * np.abs(xr).max()
         assert np.abs(vr - vo).max() <= 1e-5 * max(np.abs(vr).max(), 1.0)
         x, vel = xr, vr
+
+
+def test_update_final_for_rg_matches_reference():
+    """updateFinalForRG (dcollid.cpp:626-675: centre of mass / its velocity of every hit movable body, mrg_com bookkeeping)
+    restated, against the compiled reference over several steps of the ball_plane deck with the application moving the
+    centres of mass between steps like FronTier's propagation does.  The restatement is fed the reference's own avgVel and
+    has_collsn, so the comparison is bit for bit.  Variants: natural flags (the body's first point in hseList order has no
+    collision, a later one has), every point flagged (first point collides), nothing flagged."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built here")
+    sc = scenes.ball_plane(level=2, gap=2e-4)
+    nhs = len(sc.hs_mass)
+    movable = (sc.vflags & 2) != 0
+    assert movable.any()
+    r = ref.RefSolver(sc)
+    o = port.OracleSolver(sc, impact_zones=False, strain_limiting=False)
+    com = np.zeros((nhs, 3))
+    for b in range(nhs):
+        com[b] = sc.x[sc.vhs == b].mean(axis=0)
+    velo = np.zeros((nhs, 3))
+    com_o, velo_o = com.copy(), velo.copy()
+    x, vel = sc.x.copy(), sc.vel.copy()
+    hit_steps = 0
+    for step in range(6):
+        xn = x + sc.dt * vel
+        r.set_bodies(com, velo)
+        r.set_state(x, xn, vel)
+        r.assemble(sc.dt)
+        r.puti(ref.I_HAS_COLLSN, np.zeros(sc.V, np.int32))
+        # resolveCollision phase by phase (dcollid.cpp:317-362), so that the flags can be overridden before the last one
+        r.phase(ref.PH_AVG_VELOCITY)
+        r.phase(ref.PH_PROXIMITY_DETECT)
+        r.phase(ref.PH_APPLY)
+        for _ in range(5):
+            n = r.phase(ref.PH_COLLISION_DETECT)
+            r.phase(ref.PH_APPLY)
+            if n == 0:
+                break
+        r.phase(ref.PH_BOUNDARY)
+        r.phase(ref.PH_FINAL_POSITION)
+        variant = step % 3
+        if variant == 1:      # first point of every body collides
+            r.puti(ref.I_HAS_COLLSN, np.ones(sc.V, np.int32))
+        has = r.geti(ref.I_HAS_COLLSN) != 0
+        av = r.get(ref.F_AVGVEL)
+        r.phase(ref.PH_FINAL_VELOCITY)     # updateFinalVelocity + updateFinalForRG
+        com_r, velo_r = r.get_bodies(nhs)
+        o.set_state(x, xn)
+        o.set_dt(sc.dt)
+        o.set_avgvel(av)
+        o.set_has_collsn(has)
+        o.update_final_for_rg(com_o, velo_o)
+        assert same_bits(com_o, com_r), f"step {step}: centre of mass"
+        assert same_bits(velo_o, velo_r), f"step {step}: centre-of-mass velocity"
+        hit_steps += int((has & movable).any())
+        # the application's propagation of the bodies between two collision steps
+        com = com_r + sc.dt * velo_r
+        velo = velo_r
+        com_o, velo_o = com.copy(), velo.copy()
+        x, vel = r.get(ref.F_COORDS), r.get(ref.F_VEL)
+    assert hit_steps >= 2
