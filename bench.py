@@ -258,8 +258,13 @@ def run_b200(args):
     d_xn = torch.from_numpy(x_new).to(dev)
     stepper = None
     if world > 1:
-        from collision_b200.dist import DistributedSolver
-        stepper = DistributedSolver(solver)
+        if args.exchange == "library":
+            # the in-library multi-GPU step (csrc/dist.cuh): same calls as on one GPU from here on
+            from collision_b200.dist import enable_library_exchange
+            enable_library_exchange(solver)
+        else:
+            from collision_b200.dist import DistributedSolver
+            stepper = DistributedSolver(solver, mode=args.exchange)
 
     def one_step():
         solver.upload_device(d_xo.data_ptr(), d_xn.data_ptr())
@@ -308,7 +313,7 @@ def run_b200(args):
     h_vel = torch.from_numpy(scene.vel.copy()).pin_memory().numpy()
 
     def one_step_host():
-        if stepper is None:
+        if stepper is None:   # one GPU, or the in-library multi-GPU step: the drop-in call itself
             return solver.resolveCollision(h_xo, h_xn, h_vel, x_out=h_out)
         solver.upload(h_xo, h_xn)
         stepper.resolve_device()
@@ -327,7 +332,8 @@ def run_b200(args):
 
     # ---- aggregate over ranks: time = max, pairs = every rank's slice
     ccd_pairs = sum(p["candidates"] for p in st_exact["ccd"])
-    agg = torch.tensor([ms, e2e_ms, wall_ms, float(ccd_pairs)], dtype=torch.float64, device=dev)
+    lib_dist = world > 1 and stepper is None     # the library's statistics are already global then
+    agg = torch.tensor([ms, e2e_ms, wall_ms, float(ccd_pairs) / (world if lib_dist else 1)], dtype=torch.float64, device=dev)
     if world > 1:
         mx = agg.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -347,7 +353,12 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": desc, "parallelism": f"replicated mesh+BVH, {world}-way query slices, record all-gather",
+        "config": {"workload": desc, "parallelism": (
+                       "one GPU" if world == 1 else
+                       f"replicated mesh+tree, {world}-way query slices, owner-computes: " + (
+                           "records stored into the owner's memory over NVLink from inside the kernels, NCCL all-reduce of the "
+                           "pass counters + all-gather of avgVel, no host read-back (csrc/dist.cuh)" if lib_dist else
+                           f"python-driven NCCL exchange ({args.exchange})")),
                    "l2": "no explicit flush: the step's working set (vertex state, BVH, pair and record buffers) is "
                          "several times the 126 MB L2", "ccd_passes": st["n_ccd_passes"],
                    "ccd_pairs_per_step": ccd_pairs, "still_colliding": bool(st["still_colliding"]),
@@ -413,6 +424,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-spin", action="store_true", help="profiling runs: skip the untimed spin-up steps")
     ap.add_argument("--pipeline", type=int, default=None, help="CCD narrow-phase pipeline (default: the library's)")
+    ap.add_argument("--exchange", default="library", choices=["library", "owner", "gather"],
+                    help="multi-GPU exchange: inside the library (default) or the python-driven NCCL protocols")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

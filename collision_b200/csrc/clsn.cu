@@ -27,6 +27,7 @@
 #include "reduce.cuh"
 #include "rigid.cuh"
 #include "strain.cuh"
+#include "dist.cuh"
 
 using namespace clsn;
 
@@ -888,6 +889,29 @@ struct clsn_ctx {
     bool records_pending = false;
     long long last_nprec = 0, last_nbrec = 0;
     int rank = 0, nranks = 1;
+    // in-library multi-GPU (dist.cuh): owner-computes exchange through peer memory + NCCL
+    struct Dist {
+        bool on = false;
+        int per_rank = 0;
+        NcclApi api;
+        ncclComm_t comm = nullptr;
+        long long cap_region = 0;
+        DevBuf<PointRec> recv;                   // nranks regions of cap_region records, written by the peers
+        DevBuf<unsigned long long> hdr;          // [nranks] records per region of the current pass (written by the peers)
+        void* peer_recv[CLSN_MAX_RANKS];         // peers' recv / hdr buffers mapped into this process (own rank: local pointer)
+        void* peer_hdr[CLSN_MAX_RANKS];
+        bool peer_ipc = false;
+        DevBuf<PointRec*> d_peer_region;
+        DevBuf<unsigned long long*> d_peer_hdr;
+        DevBuf<unsigned long long> send_cnt;     // [nranks] cursors of the current pass
+        DevBuf<unsigned long long> gsum;         // PASS_SLOTS all-reduced counter blocks
+        DevBuf<unsigned long long> maxblk;       // [4] local maxima of the pass; all-gathered into ...
+        DevBuf<unsigned long long> allmax;       // ... PASS_SLOTS x nranks x 4
+        long long cap_brec_x = 65536;            // body records exchanged per rank (fixed-size all-gather)
+        DevBuf<BodyRec> brec_all, brec_dense;
+        DevBuf<unsigned long long> brec_n;       // dense body-record count + a zero word
+        unsigned long long* h_gsum = nullptr;    // pinned: gsum blocks + allmax
+    } dist;
     bool dbg_candidates = false, dbg_contacts = false;
     long long n_dbg_cand = 0, n_contacts = 0;
     cudaEvent_t ev[2 * PH_COUNT + 2];
@@ -910,6 +934,18 @@ struct clsn_ctx {
             return _e == cudaErrorMemoryAllocation ? CLSN_E_NOMEM : CLSN_E_CUDA;              \
         }                                                                                     \
     } while (0)
+
+// Counter blocks.  Every detection pass of a step has its own block of CTR_STRIDE counters, so that a whole step can be
+// enqueued without reading anything back: slot 0 = proximity, 1..5 = CCD passes, PASS_SLOT_SOLO = a pass driven through
+// the per-phase ABI or the impact-zone loop, PASS_SLOT_STEP = step-wide error flags (avgVel, boundary ...).
+#define CTR_STRIDE 32
+#define PASS_SLOTS 8
+#define PASS_SLOT_SOLO 6
+#define PASS_SLOT_STEP 7
+#define CTR_LEGACY 256   // counters.p[0 .. 255]: import / owner-bucket scratch (multi-GPU exchange)
+static_assert(CTR_COUNT <= CTR_STRIDE, "counter block too small");
+static inline unsigned long long* pass_block(clsn_ctx* c, int slot) { return c->counters.p + CTR_LEGACY + CTR_STRIDE * slot; }
+static inline unsigned long long* host_block(clsn_ctx* c, int slot) { return c->h_counters + CTR_STRIDE * slot; }
 
 // record "everything enqueued since the previous mark belongs to `phase`"
 static void mark(clsn_ctx* c, int phase)
@@ -990,6 +1026,16 @@ extern "C" void clsn_destroy(clsn_ctx* c)
     c->contacts.release(); c->cnt.release(); c->offs.release(); c->fill.release(); c->perm.release();
     c->perm_sorted.release(); c->skey.release(); c->counters.release(); c->acc_imp.release(); c->acc_fric.release();
     c->rigid.release(); c->zone_lists.release(); c->strain.release(); c->d_rg_pts.release(); c->d_rg_state.release();
+    if (c->dist.on) {
+        clsn_ctx::Dist& d = c->dist;
+        if (d.peer_ipc)
+            for (int r = 0; r < c->nranks; ++r)
+                if (r != c->rank && d.peer_recv[r]) { cudaIpcCloseMemHandle(d.peer_recv[r]); cudaIpcCloseMemHandle(d.peer_hdr[r]); }
+        if (d.comm) d.api.CommDestroy(d.comm);
+        d.recv.release(); d.hdr.release(); d.d_peer_region.release(); d.d_peer_hdr.release(); d.send_cnt.release();
+        d.gsum.release(); d.maxblk.release(); d.allmax.release(); d.brec_all.release(); d.brec_dense.release(); d.brec_n.release();
+        if (d.h_gsum) cudaFreeHost(d.h_gsum);
+    }
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     for (auto& e : c->ev) cudaEventDestroy(e);
@@ -1016,6 +1062,117 @@ extern "C" int clsn_set_slice(clsn_ctx* c, int rank, int nranks)
     c->nranks = nranks;
     return CLSN_OK;
 }
+
+// ------------------------------------------------------------------ in-library multi-GPU (dist.cuh)
+#define NCK(call)                                                                                   \
+    do {                                                                                            \
+        ncclResult_t _r = (call);                                                                   \
+        if (_r != ncclSuccess) {                                                                    \
+            c->err = std::string(#call) + ": " + c->dist.api.GetErrorString(_r);                    \
+            return CLSN_E_CUDA;                                                                     \
+        }                                                                                           \
+    } while (0)
+
+static inline unsigned long long* gsum_block(clsn_ctx* c, int slot) { return c->dist.gsum.p + CTR_STRIDE * slot; }
+
+extern "C" int clsn_dist_unique_id(void* id128)
+{
+    if (!id128) return CLSN_E_ARG;
+    static NcclApi api;
+    std::string err;
+    if (!api.load(err)) return CLSN_E_UNSUPPORTED;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId");
+    return api.GetUniqueId(reinterpret_cast<ncclUniqueId*>(id128)) == ncclSuccess ? CLSN_OK : CLSN_E_CUDA;
+}
+
+// (re)allocate the receive regions and exchange their addresses: COLLECTIVE over the communicator.  Between processes
+// the buffers are mapped with cudaIpc; the handles travel through an NCCL all-gather.
+static int dist_alloc_regions(clsn_ctx* c, long long cap_region)
+{
+    clsn_ctx::Dist& d = c->dist;
+    const int G = c->nranks, me = c->rank;
+    CK(cudaStreamSynchronize(c->stream));
+    if (d.peer_ipc)
+        for (int r = 0; r < G; ++r)
+            if (r != me && d.peer_recv[r]) { cudaIpcCloseMemHandle(d.peer_recv[r]); cudaIpcCloseMemHandle(d.peer_hdr[r]); }
+    for (int r = 0; r < CLSN_MAX_RANKS; ++r) d.peer_recv[r] = d.peer_hdr[r] = nullptr;
+    d.recv.release();
+    d.hdr.release();
+    d.cap_region = cap_region;
+    CK(d.recv.reserve((size_t)G * (size_t)cap_region));
+    CK(d.hdr.reserve(CLSN_MAX_RANKS));
+    CK(cudaMemset(d.hdr.p, 0, CLSN_MAX_RANKS * sizeof(unsigned long long)));
+    // handles: [recv handle | hdr handle] per rank
+    struct Handles { cudaIpcMemHandle_t recv, hdr; };
+    Handles mine;
+    CK(cudaIpcGetMemHandle(&mine.recv, d.recv.p));
+    CK(cudaIpcGetMemHandle(&mine.hdr, d.hdr.p));
+    DevBuf<Handles> dh;
+    CK(dh.reserve((size_t)G));
+    CK(cudaMemcpy(dh.p + me, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    NCK(d.api.AllGather(dh.p + me, dh.p, sizeof(Handles), ncclUint8, d.comm, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::vector<Handles> all((size_t)G);
+    CK(cudaMemcpy(all.data(), dh.p, (size_t)G * sizeof(Handles), cudaMemcpyDeviceToHost));
+    dh.release();
+    d.peer_ipc = true;
+    std::vector<PointRec*> region((size_t)G);
+    std::vector<unsigned long long*> hdrp((size_t)G);
+    for (int r = 0; r < G; ++r) {
+        if (r == me) {
+            d.peer_recv[r] = d.recv.p;
+            d.peer_hdr[r] = d.hdr.p;
+        } else {
+            CK(cudaIpcOpenMemHandle(&d.peer_recv[r], all[r].recv, cudaIpcMemLazyEnablePeerAccess));
+            CK(cudaIpcOpenMemHandle(&d.peer_hdr[r], all[r].hdr, cudaIpcMemLazyEnablePeerAccess));
+        }
+        region[r] = reinterpret_cast<PointRec*>(d.peer_recv[r]) + (size_t)me * (size_t)cap_region;   // my region inside rank r
+        hdrp[r] = reinterpret_cast<unsigned long long*>(d.peer_hdr[r]);
+    }
+    CK(d.d_peer_region.reserve(CLSN_MAX_RANKS));
+    CK(d.d_peer_hdr.reserve(CLSN_MAX_RANKS));
+    CK(cudaMemcpy(d.d_peer_region.p, region.data(), (size_t)G * sizeof(PointRec*), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.d_peer_hdr.p, hdrp.data(), (size_t)G * sizeof(unsigned long long*), cudaMemcpyHostToDevice));
+    const size_t tot = (size_t)G * (size_t)cap_region;
+    CK(c->perm.reserve(tot)); CK(c->perm_sorted.reserve(tot)); CK(c->skey.reserve(tot));
+    return CLSN_OK;
+}
+
+// Join a communicator of `nranks` contexts, one per GPU of this node (one process or thread each).  id128: the 128 bytes
+// of clsn_dist_unique_id() called once by any rank and handed to all of them (MPI_Bcast, torch.distributed ...).
+// Call after clsn_set_topology.  Afterwards clsn_resolve / clsn_step_host run the sliced step: every rank uploads the
+// same state and ends with the same, complete state (bit-identical to one GPU).
+extern "C" int clsn_dist_init(clsn_ctx* c, int rank, int nranks, const void* id128)
+{
+    if (!c || !c->V || !id128 || nranks < 1 || nranks > CLSN_MAX_RANKS || rank < 0 || rank >= nranks) return CLSN_E_ARG;
+    cudaSetDevice(c->device);
+    clsn_ctx::Dist& d = c->dist;
+    if (d.on) return fail(c, CLSN_E_ARG, "clsn_dist_init called twice");
+    if (!d.api.load(c->err)) return CLSN_E_UNSUPPORTED;
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    NCK(d.api.CommInitRank(&d.comm, nranks, id, rank));
+    c->rank = rank;
+    c->nranks = nranks;
+    d.per_rank = (c->V + nranks - 1) / nranks;
+    CK(d.send_cnt.reserve(CLSN_MAX_RANKS));
+    CK(d.gsum.reserve((size_t)PASS_SLOTS * CTR_STRIDE));
+    CK(d.maxblk.reserve(4));
+    CK(d.allmax.reserve((size_t)PASS_SLOTS * CLSN_MAX_RANKS * 4));
+    CK(d.brec_all.reserve((size_t)nranks * (size_t)d.cap_brec_x));
+    CK(d.brec_dense.reserve((size_t)nranks * (size_t)d.cap_brec_x));
+    CK(d.brec_n.reserve(4));
+    CK(cudaMemset(d.brec_n.p, 0, 4 * sizeof(unsigned long long)));
+    CK(cudaMemset(d.gsum.p, 0, (size_t)PASS_SLOTS * CTR_STRIDE * sizeof(unsigned long long)));
+    CK(cudaMallocHost((void**)&d.h_gsum, ((size_t)PASS_SLOTS * CTR_STRIDE + (size_t)PASS_SLOTS * CLSN_MAX_RANKS * 4) * sizeof(unsigned long long)));
+    if (c->brec.n < (size_t)d.cap_brec_x) CK(c->brec.reserve((size_t)d.cap_brec_x));
+    d.on = true;
+    // receive regions: ~64 records per element spread over G x G (source, owner) regions; grown on demand
+    const long long cap = std::max<long long>(1 << 14, (64ll * c->N) / ((long long)nranks * nranks) + 1024);
+    return dist_alloc_regions(c, cap);
+}
+
+extern "C" int clsn_dist_nranks(const clsn_ctx* c) { return c && c->dist.on ? c->nranks : 1; }
 
 // Run on the caller's stream (e.g. torch.cuda.current_stream().cuda_stream) so that the caller's own
 // device work -- the NCCL exchange of the multi-GPU step -- is ordered with the library's kernels without
@@ -1090,7 +1247,9 @@ extern "C" int clsn_set_topology(clsn_ctx* c, int V, int T, const int32_t* tri_i
     CK(cudaMemcpy(c->vflags.p, vflags, V, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->vbody.p, vbody, V * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->body_mass.p, body_mass, nbody * sizeof(double), cudaMemcpyHostToDevice));
-    CK(c->xo.reserve(V)); CK(c->xn.reserve(V)); CK(c->xf.reserve(V)); CK(c->av.reserve(V)); CK(c->has.reserve(V)); CK(c->dirty.reserve(V));
+    CK(c->xo.reserve(V)); CK(c->xn.reserve(V)); CK(c->xf.reserve(V));
+    // + CLSN_MAX_RANKS: the in-place all-gather of the multi-GPU step works on ceil(V / G) * G entries
+    CK(c->av.reserve((size_t)V + CLSN_MAX_RANKS)); CK(c->has.reserve((size_t)V + CLSN_MAX_RANKS)); CK(c->dirty.reserve((size_t)V + CLSN_MAX_RANKS));
     CK(c->imp_rg.reserve(3 * (size_t)nbody)); CK(c->cnt_rg.reserve(nbody));
     CK(cudaMemset(c->imp_rg.p, 0, 3 * (size_t)nbody * sizeof(double)));
     CK(cudaMemset(c->cnt_rg.p, 0, nbody * sizeof(int)));
@@ -1308,18 +1467,6 @@ static int build_tree(clsn_ctx* c)
     return CLSN_OK;
 }
 
-// Counter blocks.  Every detection pass of a step has its own block of CTR_STRIDE counters, so that a whole step can be
-// enqueued without reading anything back: slot 0 = proximity, 1..5 = CCD passes, PASS_SLOT_SOLO = a pass driven through
-// the per-phase ABI or the impact-zone loop, PASS_SLOT_STEP = step-wide error flags (avgVel, boundary ...).
-#define CTR_STRIDE 32
-#define PASS_SLOTS 8
-#define PASS_SLOT_SOLO 6
-#define PASS_SLOT_STEP 7
-#define CTR_LEGACY 256   // counters.p[0 .. 255]: import / owner-bucket scratch (multi-GPU exchange)
-static_assert(CTR_COUNT <= CTR_STRIDE, "counter block too small");
-static inline unsigned long long* pass_block(clsn_ctx* c, int slot) { return c->counters.p + CTR_LEGACY + CTR_STRIDE * slot; }
-static inline unsigned long long* host_block(clsn_ctx* c, int slot) { return c->h_counters + CTR_STRIDE * slot; }
-
 // Enqueue one detection pass (refit, self query, narrow phase, record emission) on the stream.  Nothing is read back:
 // every kernel takes its input count from the pass's counter block, clamps its output to the buffer capacity and skips
 // its work when an upstream list overflowed; finish_detect() looks at the counters later.  gate (device pointer or
@@ -1371,6 +1518,12 @@ static int enqueue_detect(clsn_ctx* c, int mode, int slot, const unsigned long l
     E.counters = ctr;
     E.cap_prec = (long long)c->prec.n; E.cap_brec = (long long)c->brec.n; E.cap_contacts = (long long)c->contacts.n;
     E.cnt = c->cnt.p; E.cnt_rg = c->cnt_rg.p; E.body_mass = c->body_mass.p;
+    E.D.nranks = 1; E.D.per_rank = V; E.D.cap_region = 0; E.D.peer_region = nullptr; E.D.send_cnt = nullptr;
+    if (c->dist.on) {
+        E.D.nranks = c->nranks; E.D.per_rank = c->dist.per_rank; E.D.cap_region = c->dist.cap_region;
+        E.D.peer_region = c->dist.d_peer_region.p; E.D.send_cnt = c->dist.send_cnt.p;
+        CK(cudaMemsetAsync(c->dist.send_cnt.p, 0, CLSN_MAX_RANKS * sizeof(unsigned long long), c->stream));
+    }
     const long long hit_words = (long long)(c->pairs.n / 32 + 1);
     CK(cudaMemsetAsync(c->pair_hit.p, 0, (size_t)hit_words * sizeof(unsigned), c->stream));
     const int grid = c->sm_count * NARROW_GRID_MULT;
@@ -1430,6 +1583,25 @@ static int enqueue_detect(clsn_ctx* c, int mode, int slot, const unsigned long l
     k_count_true<<<c->sm_count * 2, 256, 0, c->stream>>>(c->pair_hit.p, hit_words, ctr);
     CK(cudaGetLastError());
     c->launches += moving ? (fused ? 8 : 4) : 3;
+    if (c->dist.on) {
+        // counts to the owners, then the all-reduce of the pass's counter block: global counts for the device-side gate
+        // of the next pass, and the barrier after which every record pushed to this rank has landed
+        clsn_ctx::Dist& d = c->dist;
+        PublishCaps caps;
+        caps.pairs = (long long)c->pairs.n; caps.feats = (long long)c->feats.n;
+        caps.unc = moving && fused ? (long long)c->unc.n : (1ll << 62);
+        caps.hits = moving && fused ? (long long)c->hits.n : (1ll << 62);
+        caps.brec = std::min<long long>((long long)c->brec.n, d.cap_brec_x); caps.region = d.cap_region;
+        k_publish<<<1, CLSN_MAX_RANKS, 0, c->stream>>>(c->nranks, c->rank, d.send_cnt.p, d.d_peer_hdr.p, ctr, d.maxblk.p, caps);
+        CK(cudaGetLastError());
+        c->launches += 1;
+        NCK(d.api.GroupStart());
+        NCK(d.api.AllReduce(ctr, gsum_block(c, slot), CTR_STRIDE, ncclUint64, ncclSum, d.comm, c->stream));
+        NCK(d.api.AllGather(d.maxblk.p, d.allmax.p + (size_t)slot * CLSN_MAX_RANKS * 4, 4, ncclUint64, d.comm, c->stream));
+        if (c->has_movable)
+            NCK(d.api.AllGather(c->brec.p, d.brec_all.p, (size_t)d.cap_brec_x * sizeof(BodyRec), ncclUint8, d.comm, c->stream));
+        NCK(d.api.GroupEnd());
+    }
     mark(c, PH_CONTACT);
     c->records_pending = true;
     c->seg_records = seg;
@@ -1496,6 +1668,9 @@ static void fill_pass_stats(clsn_ctx* c, const unsigned long long* h, bool movin
     st->exact_solves = fused && moving ? (int64_t)h[CTR_EXACT] : st->coplanar;
 }
 
+static int read_blocks(clsn_ctx* c);
+static int dist_grow(clsn_ctx* c, int first_slot, int last_slot);
+
 // One pass through the per-phase ABI (and the impact-zone loop): enqueue, read the counters back, repeat if a list was
 // too small.  The whole-step entry (resolve_impl) enqueues all passes first and reads every block once at the end.
 static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st)
@@ -1511,11 +1686,21 @@ static int run_detect(clsn_ctx* c, int mode, clsn_pass_stats* st)
         int r = enqueue_detect(c, mode, PASS_SLOT_SOLO, nullptr);
         if (r) return r;
         unsigned long long* h = host_block(c, PASS_SLOT_SOLO);
-        CK(cudaMemcpyAsync(h, blk, CTR_STRIDE * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        r = grow_after_pass(c, h, moving);
-        if (r < 0) return r;
-        if (r == 1) continue;
+        if (c->dist.on) {
+            if ((r = read_blocks(c))) return r;
+            r = grow_after_pass(c, h, moving);
+            if (r < 0) return r;
+            r = dist_grow(c, PASS_SLOT_SOLO, PASS_SLOT_SOLO);
+            if (r < 0) return r;
+            if (r == 1) continue;
+            h = c->dist.h_gsum + CTR_STRIDE * PASS_SLOT_SOLO;   // global counts
+        } else {
+            CK(cudaMemcpyAsync(h, blk, CTR_STRIDE * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            r = grow_after_pass(c, h, moving);
+            if (r < 0) return r;
+            if (r == 1) continue;
+        }
         if (h[CTR_ERROR]) return fail(c, CLSN_E_NUMERIC, "NaN/Inf or degenerate normal (reference: clean_up(ERROR))");
         fill_pass_stats(c, h, moving, st);
         c->last_nprec = (long long)h[CTR_PREC];
@@ -1599,10 +1784,72 @@ static int reduce_records(clsn_ctx* c, int mode, int what = 3)  // what: bit 0 p
     return CLSN_OK;
 }
 
+// updateAverageVelocity of the multi-GPU step (dist.cuh): this rank reduces the records the peers pushed into its receive
+// regions (its own vertex range), one in-place all-gather makes avgVel / has_collsn / touched whole again on every rank,
+// then the few rigid-rigid body records (all-gathered by enqueue_detect) and the rigid bodies are handled identically
+// everywhere.  No host read-back: region counts come from the headers the peers wrote.
+static int apply_dist(clsn_ctx* c, int rigidify)
+{
+    clsn_ctx::Dist& d = c->dist;
+    const int V = c->V, G = c->nranks;
+    const unsigned long long* gate = c->pending_gate;
+    if (c->records_pending) {
+        k_reset_dirty<<<nblk(V, 256), 256, 0, c->stream>>>(V, c->vflags.p, c->dirty.p);
+        const dim3 grid(c->sm_count * 2, G);
+        k_count_regions<<<grid, 256, 0, c->stream>>>(d.recv.p, d.cap_region, d.hdr.p, c->cnt.p);
+        size_t tmp = c->cub_tmp.n;
+        CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->cnt.p, c->offs.p, V + 1, c->stream));
+        CK(cudaMemsetAsync(c->fill.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
+        k_scatter_regions<<<grid, 256, 0, c->stream>>>(d.recv.p, d.cap_region, d.hdr.p, c->offs.p, c->fill.p, c->perm.p, c->skey.p);
+        k_reduce_points<false><<<c->sm_count * 8, 256, 0, c->stream>>>(d.recv.p, c->offs.p, c->cnt.p, V, c->perm.p, c->perm_sorted.p,
+                                                                         c->skey.p, c->vflags.p, c->av.p, c->has.p, c->dirty.p, 0,
+                                                                         nullptr, nullptr, c->ctr, d.brec_n.p + 1 /* a zero word */, 1);
+        CK(cudaGetLastError());
+        c->launches += 6;
+        // the state is whole again: every rank contributes the slice it owns (in place)
+        const size_t per = (size_t)d.per_rank;
+        NCK(d.api.GroupStart());
+        NCK(d.api.AllGather(c->av.p + per * c->rank, c->av.p, per * sizeof(Vec4), ncclUint8, d.comm, c->stream));
+        NCK(d.api.AllGather(c->has.p + per * c->rank, c->has.p, per, ncclUint8, d.comm, c->stream));
+        NCK(d.api.AllGather(c->dirty.p + per * c->rank, c->dirty.p, per, ncclUint8, d.comm, c->stream));
+        NCK(d.api.GroupEnd());
+        if (c->has_movable) {
+            // rigid-rigid contacts: every rank reduces the union of all ranks' body records (ranks in order)
+            CK(cudaMemsetAsync(c->cnt_rg.p, 0, c->nbody * sizeof(int), c->stream));
+            const int slot = (int)((c->ctr - pass_block(c, 0)) / CTR_STRIDE);
+            k_compact_bodies<<<1, 256, 0, c->stream>>>(G, d.cap_brec_x, d.brec_all.p, d.allmax.p + (size_t)slot * CLSN_MAX_RANKS * 4,
+                                                       d.brec_dense.p, d.brec_n.p, c->cnt_rg.p);
+            k_reduce_bodies<<<nblk(c->nbody, 64), 64, 0, c->stream>>>(d.brec_dense.p, d.brec_n.p, (long long)d.brec_dense.n, c->nbody,
+                                                                       c->imp_rg.p);
+            k_apply_bodies<<<nblk(V, 256), 256, 0, c->stream>>>(V, c->vflags.p, c->vbody.p, c->imp_rg.p, c->cnt_rg.p, c->av.p,
+                                                                 c->has.p, c->dirty.p);
+            CK(cudaMemsetAsync(c->cnt_rg.p, 0, c->nbody * sizeof(int), c->stream));
+            c->launches += 3;
+        }
+        CK(cudaMemsetAsync(c->cnt.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
+        c->records_pending = false;
+        c->imp_nprec = -1;
+        c->dirty_valid = true;
+    }
+    if (rigidify && c->has_movable && c->prm.dt > 0.0) {
+        int r = c->rigid.rigidify(c->xo.p, c->av.p, c->vflags.p, c->prm.m, c->prm.dt, c->ctr, c->stream, nullptr, gate);
+        if (r != 0) return fail(c, CLSN_E_CUDA, "rigid-body kernels failed");
+        c->launches += c->rigid.nlists ? 2 : 0;
+    }
+    c->pending_gate = nullptr;
+    CK(cudaGetLastError());
+    mark(c, PH_REDUCE);
+    return CLSN_OK;
+}
+
 // stages: bit 0 = reduce the point records into avgVel; bit 1 = body records, rigid bodies, bookkeeping.
 // The multi-GPU owner-computes path runs them separately with the avgVel exchange in between.
 static int apply_impl(clsn_ctx* c, int rigidify, int stages)
 {
+    if (c->dist.on) {
+        if (stages != 3) return fail(c, CLSN_E_ARG, "clsn_apply_stage is the external-exchange protocol; not with clsn_dist_init");
+        return apply_dist(c, rigidify);
+    }
     const unsigned long long* gate = c->pending_gate;   // the apply of a pass that did not run must not touch anything
     if (c->records_pending && (stages & 1)) {
         k_reset_dirty<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->vflags.p, c->dirty.p);
@@ -1894,16 +2141,56 @@ static int read_blocks(clsn_ctx* c)
                        c->stream));
     CK(cudaMemcpyAsync(c->h_counters + PASS_SLOTS * CTR_STRIDE, c->tree_scratch.p + 12 * (size_t)c->tree.cnt[3], 6 * sizeof(float),
                        cudaMemcpyDeviceToHost, c->stream));
+    if (c->dist.on) {   // the all-reduced blocks (global counts) and every rank's maxima
+        CK(cudaMemcpyAsync(c->dist.h_gsum, c->dist.gsum.p, PASS_SLOTS * CTR_STRIDE * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                           c->stream));
+        CK(cudaMemcpyAsync(c->dist.h_gsum + PASS_SLOTS * CTR_STRIDE, c->dist.allmax.p,
+                           (size_t)PASS_SLOTS * CLSN_MAX_RANKS * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    }
     CK(cudaStreamSynchronize(c->stream));
     return CLSN_OK;
 }
 
-// which CCD passes ran (host copy of the counter blocks): pass 1 always, pass k + 1 iff pass k hit something
+// host copy of a pass's counters as the step's statistics see them: the all-reduced block when the step is distributed
+static inline const unsigned long long* stat_block(clsn_ctx* c, int slot)
+{
+    return c->dist.on ? c->dist.h_gsum + CTR_STRIDE * slot : host_block(c, slot);
+}
+
+// which CCD passes ran: pass 1 always, pass k + 1 iff pass k hit something
 static int ccd_passes_run(clsn_ctx* c)
 {
     int n = 1;
-    while (n < CLSN_MAX_CCD_PASSES && host_block(c, n)[CTR_CONTACTS] > 0) ++n;
+    while (n < CLSN_MAX_CCD_PASSES && stat_block(c, n)[CTR_CONTACTS] > 0) ++n;
     return n;
+}
+
+// multi-GPU: after the step's read-back, grow what the all-gathered maxima ask for (every rank sees the same numbers, so
+// the collective re-allocation is entered by all of them or by none).  Returns 1 when the step has to be repeated.
+static int dist_grow(clsn_ctx* c, int first_slot, int last_slot)
+{
+    clsn_ctx::Dist& d = c->dist;
+    unsigned long long need_region = 0, need_brec = 0, ovf = 0;
+    const unsigned long long* am = d.h_gsum + PASS_SLOTS * CTR_STRIDE;
+    for (int p = first_slot; p <= last_slot; ++p) {
+        ovf |= (d.h_gsum + CTR_STRIDE * p)[CTR_OVF];
+        for (int r = 0; r < c->nranks; ++r) {
+            need_region = std::max(need_region, am[((size_t)p * CLSN_MAX_RANKS + r) * 4]);
+            need_brec = std::max(need_brec, am[((size_t)p * CLSN_MAX_RANKS + r) * 4 + 1]);
+        }
+    }
+    if (!ovf) return 0;
+    if (need_brec > (unsigned long long)d.cap_brec_x) {
+        d.cap_brec_x = (long long)(need_brec * 5 / 4 + 1024);
+        CK(c->brec.reserve((size_t)d.cap_brec_x));
+        CK(d.brec_all.reserve((size_t)c->nranks * (size_t)d.cap_brec_x));
+        CK(d.brec_dense.reserve((size_t)c->nranks * (size_t)d.cap_brec_x));
+    }
+    if (need_region > (unsigned long long)d.cap_region) {
+        int r = dist_alloc_regions(c, (long long)(need_region * 5 / 4 + 1024));
+        if (r) return r;
+    }
+    return 1;
 }
 
 static int resolve_impl(clsn_ctx* c, clsn_step_stats& s, const HostOut& out)
@@ -1925,16 +2212,21 @@ static int resolve_impl(clsn_ctx* c, clsn_step_stats& s, const HostOut& out)
         if ((r = enqueue_detect(c, CLSN_PROXIMITY, 0, nullptr))) return r;
         if ((r = apply_impl(c, 1, 3))) return r;
         for (int p = 1; p <= CLSN_MAX_CCD_PASSES; ++p) {
-            const unsigned long long* gate = p == 1 ? nullptr : pass_block(c, p - 1) + CTR_CONTACTS;
+            const unsigned long long* gate = p == 1 ? nullptr : (c->dist.on ? gsum_block(c, p - 1) : pass_block(c, p - 1)) + CTR_CONTACTS;
             if ((r = enqueue_detect(c, CLSN_COLLISION, p, gate))) return r;
             if ((r = apply_impl(c, 1, 3))) return r;
         }
         bool checked = false, redo = false;
         auto check = [&]() -> int {
             for (int p = 0; p <= CLSN_MAX_CCD_PASSES; ++p) {
-                const int g = grow_after_pass(c, host_block(c, p), p > 0);
+                const int g = grow_after_pass(c, host_block(c, p), p > 0);   // this rank's own work lists
                 if (g < 0) return g;
-                if (g == 1) redo = true;
+                if (g == 1 && !c->dist.on) redo = true;
+            }
+            if (c->dist.on) {   // the decision to repeat is global (CTR_OVF of the all-reduced blocks)
+                const int g = dist_grow(c, 0, CLSN_MAX_CCD_PASSES);
+                if (g < 0) return g;
+                redo = g == 1;
             }
             checked = true;
             return CLSN_OK;
@@ -1946,7 +2238,8 @@ static int resolve_impl(clsn_ctx* c, clsn_step_stats& s, const HostOut& out)
             if ((r = check())) return r;
             if (redo) continue;
             const int np = ccd_passes_run(c);
-            if (np == CLSN_MAX_CCD_PASSES && host_block(c, np)[CTR_TRUE] > 0) {
+            if (np == CLSN_MAX_CCD_PASSES && stat_block(c, np)[CTR_TRUE] > 0) {
+                if (c->dist.on) return fail(c, CLSN_E_UNSUPPORTED, "the impact-zone fail-safe is not available in the multi-GPU step");
                 clsn_zone_stats zs;
                 if ((r = clsn_compute_impact_zone(c, c->zone_max_iter, &zs))) return r;
                 s.zone_iterations = zs.iterations;
@@ -1979,14 +2272,14 @@ static int resolve_impl(clsn_ctx* c, clsn_step_stats& s, const HostOut& out)
         }
         // statistics from the counter blocks
         unsigned long long err = 0;
-        for (int p = 0; p < PASS_SLOTS; ++p) err |= host_block(c, p)[CTR_ERROR];
+        for (int p = 0; p < PASS_SLOTS; ++p) err |= host_block(c, p)[CTR_ERROR] | (c->dist.on ? stat_block(c, p)[CTR_ERROR] : 0ull);
         if (err) return fail(c, CLSN_E_NUMERIC, "NaN/Inf in the collision step (reference: clean_up(ERROR))");
-        fill_pass_stats(c, host_block(c, 0), false, &s.proximity);
+        fill_pass_stats(c, stat_block(c, 0), false, &s.proximity);
         const int np = ccd_passes_run(c);
-        for (int p = 1; p <= np; ++p) fill_pass_stats(c, host_block(c, p), true, &s.ccd[p - 1]);
+        for (int p = 1; p <= np; ++p) fill_pass_stats(c, stat_block(c, p), true, &s.ccd[p - 1]);
         s.n_ccd_passes = np;
-        s.has_collision = host_block(c, 1)[CTR_TRUE] > 0 ? 1 : 0;
-        s.still_colliding = host_block(c, np)[CTR_TRUE] > 0 ? 1 : 0;
+        s.has_collision = stat_block(c, 1)[CTR_TRUE] > 0 ? 1 : 0;
+        s.still_colliding = stat_block(c, np)[CTR_TRUE] > 0 ? 1 : 0;
         CK(cudaEventElapsedTime(&s.ms_total, c->ev[0], c->ev[1]));
         if (c->strain_pending) strain_finish(c, &s.strain_sweeps, &s.strain_edges);
         static const bool trace = getenv("CLSN_TRACE") != nullptr;   // per-mark timeline on stderr (tuning runs)

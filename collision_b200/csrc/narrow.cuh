@@ -42,6 +42,28 @@ struct NarrowParams {
     double eps, thickness, dt, k, m, lambda, cr;
 };
 
+// what the record-emitting kernels need to push a record to its owner (passed by value inside Emit)
+struct DistEmit {
+    int nranks;                          // 1 = single GPU: records go to the local list
+    int per_rank;                        // owner of vertex v = v / per_rank
+    long long cap_region;                // records per (source, owner) region
+    PointRec* const* peer_region;        // [owner] -> this source's region inside the owner's receive buffer
+    unsigned long long* send_cnt;        // [owner] cursor of this pass
+};
+
+// one cursor bump per distinct owner among the converged lanes (a same-address atomic is serialised at the L2)
+__device__ __forceinline__ unsigned long long reserve_owner(unsigned long long* cursors, int owner)
+{
+    const unsigned act = __activemask();
+    const unsigned grp = __match_any_sync(act, owner);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(grp) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(&cursors[owner], (unsigned long long)__popc(grp));
+    base = __shfl_sync(grp, base, leader);
+    return base + __popc(grp & ((1u << lane) - 1u));
+}
+
 struct Emit {
     PointRec* prec;
     BodyRec* brec;
@@ -51,11 +73,12 @@ struct Emit {
     int* cnt;                    // per-point record count (this pass)
     int* cnt_rg;                 // per-body record count (this pass)
     const double* body_mass;
+    DistEmit D;                  // D.nranks > 1: point records go to their owners' receive buffers (dist.cuh)
 };
 
 enum { CTR_PAIRS = 0, CTR_CAND = 1, CTR_PREC = 2, CTR_BREC = 3, CTR_TRUE = 4, CTR_CONTACTS = 5, CTR_ERROR = 6,
        CTR_DBG_CAND = 7, CTR_FEATS = 8, CTR_BOXSURV = 9, CTR_ROOTS = 10, CTR_FEATS_EE = 11, CTR_ROOTS_EE = 12,
-       CTR_HITS = 13, CTR_HITS_EE = 14, CTR_EXACT = 15, CTR_UNC = 16, CTR_UNC_EE = 17, CTR_COUNT = 18 };
+       CTR_HITS = 13, CTR_HITS_EE = 14, CTR_EXACT = 15, CTR_UNC = 16, CTR_UNC_EE = 17, CTR_OVF = 18, CTR_COUNT = 19 };
 
 __device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 __device__ __forceinline__ double mag3(const double* a) { return sqrt(dot3(a, a)); }
@@ -148,7 +171,12 @@ template <bool SEG>
 __device__ __forceinline__ void put_prec(const Emit& E, const SegOut& S, unsigned long long& slot, unsigned long long key, int point,
                                          const double* imp, const double* fric)
 {
-    if (SEG) {
+    if (!SEG && E.D.nranks > 1) {
+        // multi-GPU: straight into the owner's receive buffer over NVLink (dist.cuh); the owner counts per point
+        const int owner = point / E.D.per_rank;
+        const long long s = (long long)reserve_owner(E.D.send_cnt, owner);
+        if (s < E.D.cap_region) store_prec(E.D.peer_region[owner] + s, key, point, imp, fric);
+    } else if (SEG) {
         const long long s = (long long)S.offs[point] + atomicAdd(&S.fill[point], 1);
         if (s < E.cap_prec) store_prec(E.prec + s, key, point, imp, fric);
     } else {
@@ -251,7 +279,7 @@ __device__ __forceinline__ void point_to_tri_impulse(const NarrowParams& P, cons
     int n = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) n += q_static(q, i) ? 0 : 1;
-    unsigned long long slot = SEG ? 0ull : reserve(&E.counters[CTR_PREC], n);
+    unsigned long long slot = (SEG || E.D.nranks > 1) ? 0ull : reserve(&E.counters[CTR_PREC], n);
     const bool has_fric = fabs(vt) > CLSN_ROUND_EPS;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -336,7 +364,7 @@ __device__ __forceinline__ void edge_to_edge_impulse(const NarrowParams& P, cons
     int n = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) n += q_static(q, i) ? 0 : 1;
-    unsigned long long slot = SEG ? 0ull : reserve(&E.counters[CTR_PREC], n);
+    unsigned long long slot = (SEG || E.D.nranks > 1) ? 0ull : reserve(&E.counters[CTR_PREC], n);
     const bool has_fric = fabs(vt) > CLSN_ROUND_EPS;
     const double wgt[4] = {wa0, wa1, wb0, wb1};
 #pragma unroll

@@ -82,6 +82,17 @@ def exchange_by_owner(send: torch.Tensor, send_counts, group=None):
     return recv, recv_counts
 
 
+def enable_library_exchange(solver: CollisionSolver3d, group=None):
+    """Switch `solver` (already assembled) to the in-library multi-GPU step (csrc/dist.cuh): torch.distributed is only
+    used to hand rank 0's NCCL unique id to the other ranks; records then travel through NVLink peer memory from inside
+    the narrow-phase kernels and NCCL collectives issued by the library itself."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [CollisionSolver3d.dist_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    solver.dist_init(rank, world, box[0])
+    return solver
+
+
 class DistributedSolver:
     """resolveCollision across the ranks of a process group (dcollid.cpp:317-362 restated as a host
     loop over the per-phase C ABI, with one record exchange per pass)."""

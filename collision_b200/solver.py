@@ -138,6 +138,9 @@ def load_library():
     L.clsn_strain_limit.argtypes = [V, P(C.c_int32), P(C.c_int32)]
     L.clsn_compute_impact_zone.argtypes = [V, I, P(clsn_zone_stats)]
     L.clsn_update_rigid_bodies.argtypes = [V, P(D), P(D)]
+    L.clsn_dist_unique_id.argtypes = [V]
+    L.clsn_dist_init.argtypes = [V, I, I, V]
+    L.clsn_dist_nranks.argtypes = [V]
     _lib = L
     return L
 
@@ -246,6 +249,26 @@ class CollisionSolver3d:
         """Convenience: copy a scenes.Params into the statics."""
         cls.s_eps, cls.s_thickness, cls.s_k = params.eps, params.thickness, params.k
         cls.s_m, cls.s_lambda, cls.s_cr = params.m, params.friction, params.cr
+
+    # ---- multi-GPU inside the library (include/collision_b200.h: clsn_dist_*)
+    @staticmethod
+    def dist_unique_id() -> bytes:
+        """128 bytes to hand to every rank (called by one rank)."""
+        buf = C.create_string_buffer(128)
+        rc = load_library().clsn_dist_unique_id(C.cast(buf, C.c_void_p))
+        if rc != 0:
+            raise CollisionError(f"clsn_dist_unique_id failed ({rc}): NCCL not available")
+        return buf.raw
+
+    def dist_init(self, rank: int, nranks: int, unique_id: bytes):
+        """Join `nranks` contexts (one per GPU of this node); call after assembleFromInterface.  resolveCollision then
+        runs the distributed step and every rank returns the complete, identical result."""
+        assert len(unique_id) == 128
+        buf = C.create_string_buffer(unique_id, 128)
+        self.ctx.check(self.ctx.L.clsn_dist_init(self.ctx.h, int(rank), int(nranks), C.cast(buf, C.c_void_p)))
+
+    def dist_nranks(self) -> int:
+        return int(self.ctx.L.clsn_dist_nranks(self.ctx.h))
 
     def setDomainBoundary(self, L, U):
         self._lo = np.asarray(L, dtype=np.float64).copy()

@@ -175,7 +175,22 @@ int clsn_timer_stop(clsn_ctx*, float* ms);
 int64_t clsn_launch_count(clsn_ctx*, int reset);
 int clsn_synchronize(clsn_ctx*);
 
-/* ---- multi-GPU: this rank traverses query leaves [rank*N/nranks, (rank+1)*N/nranks) of the
+/* ---- multi-GPU inside the library (csrc/dist.cuh): one context per GPU of a node, one process or thread each (the
+ * natural fit for the reference's MPI-based host application: one MPI rank per GPU).  Any rank calls clsn_dist_unique_id
+ * once and hands the 128 bytes to all ranks (MPI_Bcast / torch.distributed / a file); after clsn_set_topology every rank
+ * calls clsn_dist_init.  From then on clsn_resolve / clsn_step_host run the distributed step: every rank is given the
+ * same x_old / x_new and returns the same, complete result -- bit-identical to one GPU.  Mesh and tree are replicated, rank
+ * r traverses its slice of the Morton-ordered query leaves, impulse records are stored straight into the receive buffer of
+ * the rank that owns the point (NVLink peer stores from inside the narrow-phase kernels, mapped with cudaIpc), each rank
+ * reduces its own vertex range, NCCL all-reduces the pass counters (the device-side `while (is_collision)`) and
+ * all-gathers avgVel / has_collsn.  No host read-back inside the step.  Not available in this mode: the impact-zone
+ * fail-safe (CLSN_E_UNSUPPORTED if a step still collides after MAX_ITER passes with clsn_set_impact_zones on). */
+int clsn_dist_unique_id(void* id128);
+int clsn_dist_init(clsn_ctx*, int rank, int nranks, const void* id128);
+int clsn_dist_nranks(const clsn_ctx*);
+
+/* ---- multi-GPU, external exchange (the caller moves the records, e.g. with its own NCCL communicator): this rank
+ * traverses query leaves [rank*N/nranks, (rank+1)*N/nranks) of the
  * Morton order; contribution records are exchanged by the caller (NCCL all-gather of the buffers
  * below) and every rank reduces the union in canonical order -> identical state on all ranks. */
 int clsn_set_slice(clsn_ctx*, int rank, int nranks);

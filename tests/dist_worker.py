@@ -55,6 +55,41 @@ def main():
             assert name != "mixed" or zone_iters > 0   # the mixed scene enters the impact-zone fail-safe in step 2
             one.close()
             many.close()
+    # ---- the in-library multi-GPU step (csrc/dist.cuh): records pushed to their owners through NVLink peer memory from
+    # inside the kernels, NCCL issued by the library, one read-back per step -- against the single-GPU step, bit for bit
+    from collision_b200.dist import enable_library_exchange
+    for name, sc in (("layered", scenes.layered_cloth(4, 24, seed=99)), ("two_sheets", scenes.two_sheets(n=20)),
+                     ("spheres", scenes.cloth_spheres(n_layers=2, n=17, n_side=2, level=1, seed=31)),
+                     ("ball_plane", scenes.ball_plane(gap=2e-4))):
+        CollisionSolver3d.set_params_from(sc.params)
+        one = CollisionSolver3d(device=local, impact_zones=False)
+        one.assembleFromInterface(sc, sc.dt)
+        many = CollisionSolver3d(device=local, impact_zones=False)
+        many.assembleFromInterface(sc, sc.dt)
+        enable_library_exchange(many)
+        assert many.dist_nranks() == dist.get_world_size()
+        x, vel = sc.x.copy(), sc.vel.copy()
+        contacts = 0
+        for step in range(4):
+            xn = x + sc.dt * vel
+            xg, vg = xn.copy(), vel.copy()
+            has1 = one.resolveCollision(x, xg, vg)
+            xm, vm = xn.copy(), vel.copy()
+            hasm = many.resolveCollision(x, xm, vm)
+            assert same_bits(xm, xg), (name, "library", step, "positions")
+            assert same_bits(vm, vg), (name, "library", step, "velocities")
+            assert np.array_equal(has1, hasm)
+            a, b = many.last_stats, one.last_stats
+            assert a["n_ccd_passes"] == b["n_ccd_passes"] and a["still_colliding"] == b["still_colliding"]
+            for pa, pb in zip([a["proximity"]] + a["ccd"], [b["proximity"]] + b["ccd"]):
+                for k in ("true_pairs", "contacts", "contributions"):
+                    assert pa[k] == pb[k], (name, "library", step, k, pa[k], pb[k])
+            assert (a["strain_sweeps"], a["strain_edges"]) == (b["strain_sweeps"], b["strain_edges"])
+            contacts += sum(p["true_pairs"] for p in a["ccd"])
+            x, vel = xg, vg
+        assert contacts > 0, name
+        one.close()
+        many.close()
     dist.barrier()
     print("dist ok", dist.get_rank(), flush=True)
     dist.destroy_process_group()
