@@ -285,8 +285,15 @@ def run_b200(args):
         st = one_step()
     sampler = ClockSampler(local)
     sampler.start()
-    t_spin = time.perf_counter()
-    while time.perf_counter() - t_spin < 0.8 and not args.no_spin:   # keep the GPU under load while nvidia-smi spins up; untimed
+    # keep the GPU under load for ~0.8 s while nvidia-smi spins up (untimed).  The number of steps must be the SAME on every
+    # rank -- a step contains collectives -- so it is derived from the slowest rank's step time, not from each rank's clock.
+    t_one = time.perf_counter()
+    one_step()
+    t_one = torch.tensor([time.perf_counter() - t_one], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_one, op=dist.ReduceOp.MAX)
+    n_spin = 0 if args.no_spin else max(1, min(400, int(0.8 / max(float(t_one.item()), 1e-3))))
+    for _ in range(n_spin):
         one_step()
     barrier()
     n_before = len(sampler.lines)  # samples from here on fall inside the timed region

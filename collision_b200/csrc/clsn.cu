@@ -901,7 +901,10 @@ struct clsn_ctx {
         void* peer_recv[CLSN_MAX_RANKS];         // peers' recv / hdr buffers mapped into this process (own rank: local pointer)
         void* peer_hdr[CLSN_MAX_RANKS];
         bool peer_ipc = false;
-        DevBuf<PointRec*> d_peer_region;
+        bool direct = false;
+        DevBuf<PointRec*> d_peer_region;         // [r] -> this rank's region inside rank r's receive buffer (peer mapping)
+        DevBuf<PointRec> stage;                  // records staged per owner before k_push_regions
+        DevBuf<PointRec*> d_stage_region;        // [r] -> where the emitting kernels put records owned by r
         DevBuf<unsigned long long*> d_peer_hdr;
         DevBuf<unsigned long long> send_cnt;     // [nranks] cursors of the current pass
         DevBuf<unsigned long long> gsum;         // PASS_SLOTS all-reduced counter blocks
@@ -1033,6 +1036,7 @@ extern "C" void clsn_destroy(clsn_ctx* c)
                 if (r != c->rank && d.peer_recv[r]) { cudaIpcCloseMemHandle(d.peer_recv[r]); cudaIpcCloseMemHandle(d.peer_hdr[r]); }
         if (d.comm) d.api.CommDestroy(d.comm);
         d.recv.release(); d.hdr.release(); d.d_peer_region.release(); d.d_peer_hdr.release(); d.send_cnt.release();
+        d.stage.release(); d.d_stage_region.release();
         d.gsum.release(); d.maxblk.release(); d.allmax.release(); d.brec_all.release(); d.brec_dense.release(); d.brec_n.release();
         if (d.h_gsum) cudaFreeHost(d.h_gsum);
     }
@@ -1132,6 +1136,13 @@ static int dist_alloc_regions(clsn_ctx* c, long long cap_region)
     CK(d.d_peer_region.reserve(CLSN_MAX_RANKS));
     CK(d.d_peer_hdr.reserve(CLSN_MAX_RANKS));
     CK(cudaMemcpy(d.d_peer_region.p, region.data(), (size_t)G * sizeof(PointRec*), cudaMemcpyHostToDevice));
+    d.stage.release();
+    CK(d.stage.reserve((size_t)G * (size_t)cap_region));
+    d.direct = getenv("CLSN_DIST_DIRECT") != nullptr;   // A/B: store every record straight into the owner's memory, no staging
+    if (!d.direct)
+        for (int r = 0; r < G; ++r) region[r] = r == me ? d.recv.p + (size_t)me * (size_t)cap_region : d.stage.p + (size_t)r * (size_t)cap_region;
+    CK(d.d_stage_region.reserve(CLSN_MAX_RANKS));
+    CK(cudaMemcpy(d.d_stage_region.p, region.data(), (size_t)G * sizeof(PointRec*), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d.d_peer_hdr.p, hdrp.data(), (size_t)G * sizeof(unsigned long long*), cudaMemcpyHostToDevice));
     const size_t tot = (size_t)G * (size_t)cap_region;
     CK(c->perm.reserve(tot)); CK(c->perm_sorted.reserve(tot)); CK(c->skey.reserve(tot));
@@ -1521,7 +1532,7 @@ static int enqueue_detect(clsn_ctx* c, int mode, int slot, const unsigned long l
     E.D.nranks = 1; E.D.per_rank = V; E.D.cap_region = 0; E.D.peer_region = nullptr; E.D.send_cnt = nullptr;
     if (c->dist.on) {
         E.D.nranks = c->nranks; E.D.per_rank = c->dist.per_rank; E.D.cap_region = c->dist.cap_region;
-        E.D.peer_region = c->dist.d_peer_region.p; E.D.send_cnt = c->dist.send_cnt.p;
+        E.D.peer_region = c->dist.d_stage_region.p; E.D.send_cnt = c->dist.send_cnt.p;
         CK(cudaMemsetAsync(c->dist.send_cnt.p, 0, CLSN_MAX_RANKS * sizeof(unsigned long long), c->stream));
     }
     const long long hit_words = (long long)(c->pairs.n / 32 + 1);
@@ -1592,9 +1603,12 @@ static int enqueue_detect(clsn_ctx* c, int mode, int slot, const unsigned long l
         caps.unc = moving && fused ? (long long)c->unc.n : (1ll << 62);
         caps.hits = moving && fused ? (long long)c->hits.n : (1ll << 62);
         caps.brec = std::min<long long>((long long)c->brec.n, d.cap_brec_x); caps.region = d.cap_region;
+        if (!d.direct)
+            k_push_regions<<<dim3((unsigned)std::max(1, c->sm_count * 8 / c->nranks), (unsigned)c->nranks), 256, 0, c->stream>>>(
+                c->rank, d.cap_region, d.stage.p, d.d_peer_region.p, d.send_cnt.p);
         k_publish<<<1, CLSN_MAX_RANKS, 0, c->stream>>>(c->nranks, c->rank, d.send_cnt.p, d.d_peer_hdr.p, ctr, d.maxblk.p, caps);
         CK(cudaGetLastError());
-        c->launches += 1;
+        c->launches += 2;
         NCK(d.api.GroupStart());
         NCK(d.api.AllReduce(ctr, gsum_block(c, slot), CTR_STRIDE, ncclUint64, ncclSum, d.comm, c->stream));
         NCK(d.api.AllGather(d.maxblk.p, d.allmax.p + (size_t)slot * CLSN_MAX_RANKS * 4, 4, ncclUint64, d.comm, c->stream));

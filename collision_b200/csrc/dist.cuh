@@ -5,10 +5,13 @@
 // every record of a point reaches the rank that reduces that point ("owner computes": vertex v belongs to rank
 // v / ceil(V / G)).  Data path of one pass:
 //
-//   k_emit / k_contact   every impulse record is stored straight into the OWNER's receive buffer: a plain 64-byte store
-//                        through an NVLink peer mapping (cudaIpc between processes, peer access inside one process),
-//                        slot from a local per-owner cursor -- the exchange IS the emission, no staging copy, no
-//                        all-to-all afterwards, and the transfer overlaps the narrow phase record by record;
+//   k_emit / k_contact   every impulse record goes to a per-owner region (slot from a per-owner cursor, one atomic per
+//                        distinct owner and warp): the rank's own records straight into its receive buffer, the others
+//                        into a local staging buffer;
+//   k_push_regions       the staged regions are written into the OWNERS' receive buffers through NVLink peer mappings
+//                        (cudaIpc between processes): plain coalesced 16-byte stores, 512 B per warp instruction, all
+//                        ranks pushing to all owners at once -- an all-to-all without a library call, sizes known only
+//                        on the device;
 //   k_publish            the per-owner counts go to the owners' headers (8-byte peer stores), overflow flags are folded;
 //   ncclAllReduce        of the pass's counter block: the global contact / true-pair counts gate the next pass on the
 //                        device, and the collective doubles as the barrier after which every peer store has landed;
@@ -100,6 +103,23 @@ __global__ void k_publish(int nranks, int me, const unsigned long long* __restri
         maxblk[0] = mx;              // all-reduced with MAX: the region capacity every rank needs
         maxblk[1] = ctr[CTR_BREC];   // ... and the body-record capacity
     }
+}
+
+// Records staged per owner in local memory -> the owners' receive regions, as long contiguous runs: every warp
+// instruction writes 512 consecutive bytes, which is what NVLink wants (measured: 64-byte records stored one by one from
+// the emitting kernels reached ~140 GB/s per GPU, a fraction of the link).  blockIdx.y = owner; the own region was
+// written in place by the emitting kernels.
+__global__ void k_push_regions(int me, long long cap_region, const PointRec* __restrict__ stage, PointRec* const* peer_region,
+                               const unsigned long long* __restrict__ send_cnt)
+{
+    const int r = blockIdx.y;
+    if (r == me) return;
+    long long n = (long long)send_cnt[r];
+    if (n > cap_region) n = cap_region;
+    const uint4* src = reinterpret_cast<const uint4*>(stage + (size_t)r * cap_region);
+    uint4* dst = reinterpret_cast<uint4*>(peer_region[r]);
+    const long long n16 = n * 4;   // 16-byte chunks
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
 // ---- owner side: the received records live in nranks regions of cap_region slots, region s holding hdr[s] records
