@@ -60,6 +60,8 @@ def workload(name: str):
         return scenes.layered_cloth(8, 33), "layered_cloth 8x33^2: 16 384 tris (bounded sample of config 4)"
     if name == "config5":
         return scenes.cloth_spheres(8, 501, 4, 3), "cloth_spheres 8x501^2 + 64 icospheres: 4 081 920 tris (config 5)"
+    if name == "config5s":
+        return scenes.cloth_spheres(8, 126, 4, 3), "cloth_spheres 8x126^2 + 64 icospheres: 331 920 tris (1/16-area member of the config-5 family)"
     if name == "tiny":
         return scenes.layered_cloth(4, 33), "layered_cloth 4x33^2: 8 192 tris (smoke)"
     raise SystemExit(f"unknown workload {name}")

@@ -163,7 +163,7 @@ template <bool MOVING>
 __global__ void __launch_bounds__(CULL_THREADS, CULL_MIN_BLOCKS)
 k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restrict__ elem, const Vec4* __restrict__ xo,
        const Vec4* __restrict__ av, NarrowParams P, FeatRec* __restrict__ feats, long long cap_feats,
-       unsigned long long* counters, bool split_by_kind)
+       unsigned long long* counters, bool split_by_kind, long long pair_lo, long long pair_hi)
 {
     __shared__ double s_x[CULL_THREADS][CULL_ROW];
     __shared__ double s_v[MOVING ? CULL_THREADS : 1][CULL_ROW];
@@ -174,13 +174,14 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
     const int tid = threadIdx.x, lane = tid & 31, wb = tid & ~31;
     long long n_pairs = (long long)counters[CTR_PAIRS];
     if (n_pairs > cap_pairs) n_pairs = cap_pairs;
+    if (n_pairs > pair_hi) n_pairs = pair_hi;   // this launch handles the chunk [pair_lo, pair_hi) of the pair list
     // contact distance with 0.1 % head-room (covers the rounding of the distance itself), and the relative
     // slack: 3 eps for the barycentric tolerance + 2e-3 for the error of the barycentric coordinates of a
     // nearly degenerate triangle (cond <= L^4 / (1000 MACH_EPS), i.e. <= 4.5e-4 for L <= 1)
     const float h2 = __double2float_ru(1.001 * (MOVING ? P.eps : P.thickness));
     const float rel = __double2float_ru(3.0 * P.eps + 2e-3);
     unsigned long long n_box = 0;
-    for (long long base = (long long)blockIdx.x * CULL_THREADS; base < n_pairs; base += (long long)gridDim.x * CULL_THREADS) {
+    for (long long base = pair_lo + (long long)blockIdx.x * CULL_THREADS; base < n_pairs; base += (long long)gridDim.x * CULL_THREADS) {
         const long long pi = base + tid;
         unsigned mask = 0;
         if (pi < n_pairs) {
@@ -774,6 +775,22 @@ __global__ void k_count_true(const unsigned* __restrict__ pair_hit, long long n_
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(&counters[CTR_TRUE], c);
 }
 
+// End of a chunk of the pair list: remember the sums of the six list cursors and the largest chunk, restart the cursors
+// (last chunk: leave the sums in them, which is what the statistics report).
+__global__ void k_fold_chunk(unsigned long long* ctr, int last)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int cur[6] = {CTR_FEATS, CTR_FEATS_EE, CTR_UNC, CTR_UNC_EE, CTR_HITS, CTR_HITS_EE};
+    const unsigned long long f = ctr[CTR_FEATS] + ctr[CTR_FEATS_EE], u = ctr[CTR_UNC] + ctr[CTR_UNC_EE], h = ctr[CTR_HITS] + ctr[CTR_HITS_EE];
+    if (f > ctr[CTR_MAX_FEATS]) ctr[CTR_MAX_FEATS] = f;
+    if (u > ctr[CTR_MAX_UNC]) ctr[CTR_MAX_UNC] = u;
+    if (h > ctr[CTR_MAX_HITS]) ctr[CTR_MAX_HITS] = h;
+    for (int i = 0; i < 6; ++i) {
+        ctr[CTR_TOT + i] += ctr[cur[i]];
+        ctr[cur[i]] = last ? ctr[CTR_TOT + i] : 0ull;
+    }
+}
+
 // ------------------------------------------------------------------ context
 template <class T>
 struct DevBuf {
@@ -866,13 +883,17 @@ struct clsn_ctx {
     DevBuf<HitRec> hits;
     DevBuf<FeatRec> unc;        // pipeline 1: features the fast path could not settle
     bool seg_records = false;   // pipeline 2: the pending records already sit in per-point segments (offs valid)
+    long long pair_chunk = 1ll << 24;   // pairs per narrow-phase chunk (CLSN_PAIR_CHUNK; see enqueue_detect)
     int pipeline = 1;           // 1 = fast path first (k_fast + k_exact + k_emit), 0 = staged (k_roots + k_contact),
                                 // 2 = 1 + records emitted into per-point segments (experimental)
     DevBuf<PointRec> prec, prec_sorted;
     DevBuf<BodyRec> brec;
     DevBuf<Contact> contacts;
     DevBuf<int> cnt, offs, fill, perm, perm_sorted;
-    DevBuf<unsigned long long> skey;
+    DevBuf<unsigned long long> skey, skey_sorted;
+    DevBuf<unsigned char> cub_tmp2;   // cub::DeviceSegmentedSort (movable-body scenes)
+    DevBuf<unsigned long long> bkey;  // body records in (body, key) order: reduce_bodies()
+    DevBuf<int> bidx, bbody;
     DevBuf<unsigned long long> counters;
     DevBuf<double> acc_imp, acc_fric;
     unsigned long long* h_counters = nullptr;  // pinned: PASS_SLOTS blocks of CTR_STRIDE counters
@@ -1005,6 +1026,7 @@ extern "C" int clsn_create(clsn_ctx** out, int device)
     p.eps = 1e-6; p.thickness = 1e-4; p.dt = 1e-3; p.k = 1000; p.m = 0.01; p.lambda = 0.02; p.cr = 0.0;
     for (int i = 0; i < 3; ++i) { p.lo[i] = -1e30; p.hi[i] = 1e30; }
     c->prm = p;
+    if (const char* e = getenv("CLSN_PAIR_CHUNK")) c->pair_chunk = std::max<long long>(1024, atoll(e));
     if (const char* e = getenv("CLSN_KEEP_TREE")) c->keep_tree = atoi(e) != 0;
     if (const char* e = getenv("CLSN_PHASE_TIMING")) c->phase_timing = atoi(e) != 0;
     if (const char* e = getenv("CLSN_PIPELINE")) {
@@ -1027,7 +1049,7 @@ extern "C" void clsn_destroy(clsn_ctx* c)
     c->tree_ticket.release(); c->lbox.release(); c->bounds.release();
     c->cub_tmp.release(); c->pairs.release(); c->dbg_cand.release(); c->feats.release(); c->pair_hit.release(); c->rootrecs.release(); c->hits.release(); c->unc.release(); c->prec.release(); c->prec_sorted.release(); c->brec.release();
     c->contacts.release(); c->cnt.release(); c->offs.release(); c->fill.release(); c->perm.release();
-    c->perm_sorted.release(); c->skey.release(); c->counters.release(); c->acc_imp.release(); c->acc_fric.release();
+    c->perm_sorted.release(); c->skey.release(); c->skey_sorted.release(); c->cub_tmp2.release(); c->bkey.release(); c->bidx.release(); c->bbody.release(); c->counters.release(); c->acc_imp.release(); c->acc_fric.release();
     c->rigid.release(); c->zone_lists.release(); c->strain.release(); c->d_rg_pts.release(); c->d_rg_state.release();
     if (c->dist.on) {
         clsn_ctx::Dist& d = c->dist;
@@ -1541,59 +1563,73 @@ static int enqueue_detect(clsn_ctx* c, int mode, int slot, const unsigned long l
     const bool fused = c->pipeline >= 1;
     // segments only where this context reduces its own records (multi-GPU ranks exchange the plain list)
     const bool seg = moving && c->pipeline == 2 && c->nranks == 1;
+    // The pair list is processed in chunks of `pair_chunk` pairs, so that the feature / hit lists stay bounded however many
+    // pairs a pass produces (fast rigid bodies in a cloth stack: 10^8 pairs, 15 surviving features each).  The number of
+    // chunks follows from the CAPACITY of the pair list (the count lives on the device); a chunk beyond the count is a
+    // handful of empty launches.  One chunk covers every scene of the size of config 4.
+    const long long cap_pairs = (long long)c->pairs.n;
+    const int nchunk = (c->pipeline == 1 || !moving) ? (int)std::max<long long>(1, (cap_pairs + c->pair_chunk - 1) / c->pair_chunk) : 1;
     if (moving) {
         if (fused && c->hits.n == 0) CK(c->hits.reserve((size_t)4 * N + 1024));
         if (fused && c->unc.n == 0) CK(c->unc.reserve((size_t)4 * N + 1024));
         if (!fused && c->rootrecs.n == 0) CK(c->rootrecs.reserve((size_t)16 * N + 1024));
-        k_cull<true><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p, P,
-                                                            c->feats.p, (long long)c->feats.n, ctr, fused);
-        mark(c, PH_CULL);
-        if (fused) {
-            k_fast<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E, c->hits.p,
-                                                                 (long long)c->hits.n, c->unc.p, (long long)c->unc.n);
-            k_fast<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E, c->hits.p,
-                                                                (long long)c->hits.n, c->unc.p, (long long)c->unc.n);
-            k_exact<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->unc.p, (long long)c->unc.n, c->xo.p, c->av.p, P, E, c->hits.p,
-                                                                  (long long)c->hits.n);
-            k_exact<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->unc.p, (long long)c->unc.n, c->xo.p, c->av.p, P, E, c->hits.p,
-                                                                 (long long)c->hits.n);
-            mark(c, PH_ROOTS);
-            if (seg) {
-                // per-point record counts of the hit list -> segment offsets -> records written in place
-                k_count_hits<false><<<grid, 256, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->vflags.p, c->cnt.p, ctr);
-                k_count_hits<true><<<grid, 256, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->vflags.p, c->cnt.p, ctr);
-                size_t tmp = c->cub_tmp.n;
-                CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->cnt.p, c->offs.p, V + 1, c->stream));
-                CK(cudaMemsetAsync(c->fill.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
-                const SegOut S{c->offs.p, c->fill.p};
-                k_emit<false, true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p,
-                                                                           c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p, S);
-                k_emit<true, true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p,
-                                                                          c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p, S);
-                c->launches += 4;
+    }
+    for (int ch = 0; ch < nchunk; ++ch) {
+        const long long lo = nchunk == 1 ? 0 : (long long)ch * c->pair_chunk;
+        const long long hi = nchunk == 1 ? cap_pairs : std::min<long long>(cap_pairs, lo + c->pair_chunk);
+        if (moving) {
+            k_cull<true><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, cap_pairs, c->elem.p, c->xo.p, c->av.p, P, c->feats.p,
+                                                                (long long)c->feats.n, ctr, fused, lo, hi);
+            if (ch == nchunk - 1) mark(c, PH_CULL);
+            if (fused) {
+                k_fast<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E, c->hits.p,
+                                                                     (long long)c->hits.n, c->unc.p, (long long)c->unc.n);
+                k_fast<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P, E, c->hits.p,
+                                                                    (long long)c->hits.n, c->unc.p, (long long)c->unc.n);
+                k_exact<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->unc.p, (long long)c->unc.n, c->xo.p, c->av.p, P, E, c->hits.p,
+                                                                      (long long)c->hits.n);
+                k_exact<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->unc.p, (long long)c->unc.n, c->xo.p, c->av.p, P, E, c->hits.p,
+                                                                     (long long)c->hits.n);
+                if (ch == nchunk - 1) mark(c, PH_ROOTS);
+                if (seg) {
+                    // per-point record counts of the hit list -> segment offsets -> records written in place
+                    k_count_hits<false><<<grid, 256, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->vflags.p, c->cnt.p, ctr);
+                    k_count_hits<true><<<grid, 256, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->vflags.p, c->cnt.p, ctr);
+                    size_t tmp = c->cub_tmp.n;
+                    CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->cnt.p, c->offs.p, V + 1, c->stream));
+                    CK(cudaMemsetAsync(c->fill.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
+                    const SegOut S{c->offs.p, c->fill.p};
+                    k_emit<false, true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p,
+                                                                               c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p, S);
+                    k_emit<true, true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p,
+                                                                              c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p, S);
+                    c->launches += 4;
+                } else {
+                    k_emit<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p,
+                                                                         c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+                    k_emit<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p,
+                                                                        c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+                }
             } else {
-                k_emit<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p,
-                                                                     c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
-                k_emit<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->hits.p, (long long)c->hits.n, c->pairs.p, c->xo.p, c->av.p,
-                                                                    c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+                k_roots<<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P.dt, c->rootrecs.p,
+                                                               (long long)c->rootrecs.n, ctr);
+                mark(c, PH_ROOTS);
+                k_contact<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, c->rootrecs.p, (long long)c->rootrecs.n, c->pairs.p,
+                                                                       c->xo.p, c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
             }
         } else {
-            k_roots<<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, (long long)c->feats.n, c->xo.p, c->av.p, P.dt, c->rootrecs.p,
-                                                           (long long)c->rootrecs.n, ctr);
-            mark(c, PH_ROOTS);
-            k_contact<true><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, c->rootrecs.p, (long long)c->rootrecs.n, c->pairs.p,
-                                                                   c->xo.p, c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+            k_cull<false><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, cap_pairs, c->elem.p, c->xo.p, c->av.p, P, c->feats.p,
+                                                                 (long long)c->feats.n, ctr, false, lo, hi);
+            if (ch == nchunk - 1) mark(c, PH_CULL);
+            k_contact<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, c->rootrecs.p, (long long)c->feats.n, c->pairs.p,
+                                                                    c->xo.p, c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
         }
-    } else {
-        k_cull<false><<<grid, CULL_THREADS, 0, c->stream>>>(c->pairs.p, (long long)c->pairs.n, c->elem.p, c->xo.p, c->av.p, P,
-                                                             c->feats.p, (long long)c->feats.n, ctr, false);
-        mark(c, PH_CULL);
-        k_contact<false><<<grid, FEAT_THREADS, 0, c->stream>>>(c->feats.p, c->rootrecs.p, (long long)c->feats.n, c->pairs.p,
-                                                                c->xo.p, c->av.p, c->vflags.p, c->vbody.p, P, E, c->pair_hit.p);
+        k_fold_chunk<<<1, 32, 0, c->stream>>>(ctr, ch == nchunk - 1 ? 1 : 0);
+        c->launches += 1 + (moving ? (fused ? 7 : 3) : 2);
     }
     k_count_true<<<c->sm_count * 2, 256, 0, c->stream>>>(c->pair_hit.p, hit_words, ctr);
     CK(cudaGetLastError());
-    c->launches += moving ? (fused ? 8 : 4) : 3;
+    c->launches += 1;
     if (c->dist.on) {
         // counts to the owners, then the all-reduce of the pass's counter block: global counts for the device-side gate
         // of the next pass, and the barrier after which every record pushed to this rank has landed
@@ -1640,20 +1676,20 @@ static int grow_after_pass(clsn_ctx* c, const unsigned long long* h, bool moving
         CK(c->pair_hit.reserve(c->pairs.n / 32 + 2));
         redo = true;
     }
-    if (h[CTR_FEATS] + h[CTR_FEATS_EE] > c->feats.n) {
-        CK(c->feats.reserve((size_t)((h[CTR_FEATS] + h[CTR_FEATS_EE]) * 5 / 4 + 1024)));
+    if (h[CTR_MAX_FEATS] > c->feats.n) {   // lists that restart with every chunk of the pair list: the largest chunk counts
+        CK(c->feats.reserve((size_t)(h[CTR_MAX_FEATS] * 5 / 4 + 1024)));
         redo = true;
     }
     if (!fused && moving && h[CTR_ROOTS] + h[CTR_ROOTS_EE] > c->rootrecs.n) {
         CK(c->rootrecs.reserve((size_t)((h[CTR_ROOTS] + h[CTR_ROOTS_EE]) * 5 / 4 + 1024)));
         redo = true;
     }
-    if (fused && moving && h[CTR_UNC] + h[CTR_UNC_EE] > c->unc.n) {
-        CK(c->unc.reserve((size_t)((h[CTR_UNC] + h[CTR_UNC_EE]) * 5 / 4 + 1024)));
+    if (fused && moving && h[CTR_MAX_UNC] > c->unc.n) {
+        CK(c->unc.reserve((size_t)(h[CTR_MAX_UNC] * 5 / 4 + 1024)));
         redo = true;
     }
-    if (fused && moving && h[CTR_HITS] + h[CTR_HITS_EE] > c->hits.n) {
-        CK(c->hits.reserve((size_t)((h[CTR_HITS] + h[CTR_HITS_EE]) * 5 / 4 + 1024)));
+    if (fused && moving && h[CTR_MAX_HITS] > c->hits.n) {
+        CK(c->hits.reserve((size_t)(h[CTR_MAX_HITS] * 5 / 4 + 1024)));
         redo = true;
     }
     if (h[CTR_PREC] > c->prec.n) {
@@ -1734,6 +1770,67 @@ extern "C" int clsn_detect(clsn_ctx* c, int mode, clsn_pass_stats* st)
     return run_detect(c, mode, st);
 }
 
+// collsnImpulse_RG += the body records of the pass, per body in canonical key order (reduce.cuh)
+static int reduce_bodies(clsn_ctx* c, const BodyRec* rec, const unsigned long long* n_dev, long long cap, double* imp_rg)
+{
+    if (cap <= 0) return CLSN_OK;
+    const size_t n = (size_t)cap;
+    CK(c->bkey.reserve(2 * n)); CK(c->bidx.reserve(3 * n)); CK(c->bbody.reserve(2 * n));
+    unsigned long long *k0 = c->bkey.p, *k1 = c->bkey.p + n;
+    int *i0 = c->bidx.p, *i1 = c->bidx.p + n, *i2 = c->bidx.p + 2 * n, *b0 = c->bbody.p, *b1 = c->bbody.p + n;
+    size_t t1 = 0, t2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, k0, k1, i0, i1, (int)n, 0, 64, c->stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, t2, b0, b1, i1, i2, (int)n, 0, 31, c->stream);
+    CK(c->cub_tmp2.reserve(std::max(t1, t2) + 256));
+    const int grid = std::max(1, std::min(c->sm_count * 4, (int)((n + 255) / 256)));
+    k_body_keys<<<grid, 256, 0, c->stream>>>(rec, n_dev, cap, k0, i0);
+    size_t tmp = c->cub_tmp2.n;
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp2.p, tmp, k0, k1, i0, i1, (int)n, 0, 64, c->stream));
+    k_body_ids<<<grid, 256, 0, c->stream>>>(rec, i1, cap, b0);
+    tmp = c->cub_tmp2.n;
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp2.p, tmp, b0, b1, i1, i2, (int)n, 0, 31, c->stream));
+    k_reduce_bodies_sorted<<<nblk(c->nbody, 64), 64, 0, c->stream>>>(rec, b1, i2, cap, c->nbody, imp_rg);
+    CK(cudaGetLastError());
+    c->launches += 3 + 2 * 9;
+    return CLSN_OK;
+}
+
+// Sum the grouped records per point in canonical key order and apply / store the sums (k_reduce_points).  With movable
+// rigid bodies a single vertex can own tens of thousands of records (a sphere sweeping through a cloth stack): the
+// per-point order then comes from cub::DeviceSegmentedSort over (key, record index) instead of the warp's all-pairs
+// ranking, which is quadratic in the records of one point.
+static int launch_reduce_points(clsn_ctx* c, const PointRec* rec, bool seg, int mode, const unsigned long long* n_rec_ptr, long long cap)
+{
+    const int V = c->V;
+    const bool sorted = c->has_movable && !seg;
+    const int* perm = c->perm.p;
+    if (sorted) {
+        CK(c->skey_sorted.reserve(c->skey.n));
+        size_t need = 0;
+        cub::DeviceSegmentedSort::SortPairs(nullptr, need, c->skey.p, c->skey_sorted.p, c->perm.p, c->perm_sorted.p, (long long)c->perm.n, V,
+                                            c->offs.p, c->offs.p + 1, c->stream);
+        CK(c->cub_tmp2.reserve(need + 256));
+        k_clamp_offsets<<<nblk(V + 1, 256), 256, 0, c->stream>>>(V + 1, c->offs.p, (int)std::min<size_t>(c->perm.n, 0x7fffffff));
+        size_t tmp = c->cub_tmp2.n;
+        CK(cub::DeviceSegmentedSort::SortPairs(c->cub_tmp2.p, tmp, c->skey.p, c->skey_sorted.p, c->perm.p, c->perm_sorted.p,
+                                               (long long)c->perm.n, V, c->offs.p, c->offs.p + 1, c->stream));
+        perm = c->perm_sorted.p;
+        k_reduce_points<false, true><<<c->sm_count * 8, 256, 0, c->stream>>>(rec, c->offs.p, c->cnt.p, V, perm, nullptr, c->skey.p, c->vflags.p,
+                                                                               c->av.p, c->has.p, c->dirty.p, mode, c->acc_imp.p,
+                                                                               c->acc_fric.p, c->ctr, n_rec_ptr, cap);
+    } else if (seg) {
+        k_reduce_points<true><<<c->sm_count * 8, 256, 0, c->stream>>>(rec, c->offs.p, c->cnt.p, V, perm, c->perm_sorted.p, c->skey.p,
+                                                                        c->vflags.p, c->av.p, c->has.p, c->dirty.p, mode, c->acc_imp.p,
+                                                                        c->acc_fric.p, c->ctr, n_rec_ptr, cap);
+    } else {
+        k_reduce_points<false><<<c->sm_count * 8, 256, 0, c->stream>>>(rec, c->offs.p, c->cnt.p, V, perm, c->perm_sorted.p, c->skey.p,
+                                                                         c->vflags.p, c->av.p, c->has.p, c->dirty.p, mode, c->acc_imp.p,
+                                                                         c->acc_fric.p, c->ctr, n_rec_ptr, cap);
+    }
+    CK(cudaGetLastError());
+    return CLSN_OK;
+}
+
 // group + reduce the pending records.  mode 0: apply to avgVel; mode 1: into acc arrays only.
 // No host-side counts are consulted for the context's own records: every kernel reads its count from the pass's counter
 // block, so the launches are the same whether or not the pass found anything (an empty or gated pass costs a few empty
@@ -1779,20 +1876,16 @@ static int reduce_records(clsn_ctx* c, int mode, int what = 3)  // what: bit 0 p
             CK(cudaMemsetAsync(c->acc_imp.p, 0, 3 * (size_t)V * sizeof(double), c->stream));
             CK(cudaMemsetAsync(c->acc_fric.p, 0, 3 * (size_t)V * sizeof(double), c->stream));
         }
-        if (seg)
-            k_reduce_points<true><<<c->sm_count * 8, 256, 0, c->stream>>>(prec, c->offs.p, c->cnt.p, V, c->perm.p, c->perm_sorted.p,
-                                                                            c->skey.p, c->vflags.p, c->av.p, c->has.p, c->dirty.p, mode,
-                                                                            c->acc_imp.p, c->acc_fric.p, c->ctr, n_prec_dev, cap_p);
-        else
-            k_reduce_points<false><<<c->sm_count * 8, 256, 0, c->stream>>>(prec, c->offs.p, c->cnt.p, V, c->perm.p, c->perm_sorted.p,
-                                                                             c->skey.p, c->vflags.p, c->av.p, c->has.p, c->dirty.p, mode,
-                                                                             c->acc_imp.p, c->acc_fric.p, c->ctr, n_prec_dev, cap_p);
+        {
+            int r = launch_reduce_points(c, prec, seg, mode, n_prec_dev, cap_p);
+            if (r) return r;
+        }
         c->launches += 2 + 2;  // scan (init + scan), scatter, reduce
     }
     if (mode == 0 && (what & 2) && (c->has_movable || (imported && c->imp_nbrec > 0))) {
         // body records only exist where a movable rigid body does (emit_body needs a movable point)
-        k_reduce_bodies<<<nblk(c->nbody, 64), 64, 0, c->stream>>>(brec, n_brec_dev, cap_b, c->nbody, c->imp_rg.p);
-        c->launches += 1;
+        int r = reduce_bodies(c, brec, n_brec_dev, cap_b, c->imp_rg.p);
+        if (r) return r;
     }
     CK(cudaGetLastError());
     return CLSN_OK;
@@ -1815,9 +1908,10 @@ static int apply_dist(clsn_ctx* c, int rigidify)
         CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->cnt.p, c->offs.p, V + 1, c->stream));
         CK(cudaMemsetAsync(c->fill.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
         k_scatter_regions<<<grid, 256, 0, c->stream>>>(d.recv.p, d.cap_region, d.hdr.p, c->offs.p, c->fill.p, c->perm.p, c->skey.p);
-        k_reduce_points<false><<<c->sm_count * 8, 256, 0, c->stream>>>(d.recv.p, c->offs.p, c->cnt.p, V, c->perm.p, c->perm_sorted.p,
-                                                                         c->skey.p, c->vflags.p, c->av.p, c->has.p, c->dirty.p, 0,
-                                                                         nullptr, nullptr, c->ctr, d.brec_n.p + 1 /* a zero word */, 1);
+        {
+            int r = launch_reduce_points(c, d.recv.p, false, 0, d.brec_n.p + 1 /* a zero word */, 1);
+            if (r) return r;
+        }
         CK(cudaGetLastError());
         c->launches += 6;
         // the state is whole again: every rank contributes the slice it owns (in place)
@@ -1833,8 +1927,10 @@ static int apply_dist(clsn_ctx* c, int rigidify)
             const int slot = (int)((c->ctr - pass_block(c, 0)) / CTR_STRIDE);
             k_compact_bodies<<<1, 256, 0, c->stream>>>(G, d.cap_brec_x, d.brec_all.p, d.allmax.p + (size_t)slot * CLSN_MAX_RANKS * 4,
                                                        d.brec_dense.p, d.brec_n.p, c->cnt_rg.p);
-            k_reduce_bodies<<<nblk(c->nbody, 64), 64, 0, c->stream>>>(d.brec_dense.p, d.brec_n.p, (long long)d.brec_dense.n, c->nbody,
-                                                                       c->imp_rg.p);
+            {
+                int r = reduce_bodies(c, d.brec_dense.p, d.brec_n.p, (long long)d.brec_dense.n, c->imp_rg.p);
+                if (r) return r;
+            }
             k_apply_bodies<<<nblk(V, 256), 256, 0, c->stream>>>(V, c->vflags.p, c->vbody.p, c->imp_rg.p, c->cnt_rg.p, c->av.p,
                                                                  c->has.p, c->dirty.p);
             CK(cudaMemsetAsync(c->cnt_rg.p, 0, c->nbody * sizeof(int), c->stream));
@@ -2296,7 +2392,7 @@ static int resolve_impl(clsn_ctx* c, clsn_step_stats& s, const HostOut& out)
         s.still_colliding = stat_block(c, np)[CTR_TRUE] > 0 ? 1 : 0;
         CK(cudaEventElapsedTime(&s.ms_total, c->ev[0], c->ev[1]));
         if (c->strain_pending) strain_finish(c, &s.strain_sweeps, &s.strain_edges);
-        static const bool trace = getenv("CLSN_TRACE") != nullptr;   // per-mark timeline on stderr (tuning runs)
+        const bool trace = getenv("CLSN_TRACE") != nullptr && c->rank == 0;   // per-mark timeline on stderr (tuning runs)
         static const char* names[PH_COUNT] = {"avgvel", "build", "refit", "traverse", "cull", "roots", "contact", "reduce", "final", "other"};
         for (size_t i = 1; i < c->n_marks; ++i) {
             float ms = 0.f;
@@ -2543,7 +2639,8 @@ extern "C" int clsn_get_accumulators(clsn_ctx* c, double* imp, double* fric, int
             unsigned long long* n_dev = c->imp_nprec >= 0 ? c->counters.p + 33 : c->ctr + CTR_BREC;
             const BodyRec* brec = c->imp_nprec >= 0 ? c->imp_brec : c->brec.p;
             const long long cap = c->imp_nprec >= 0 ? nbrec : (long long)c->brec.n;
-            k_reduce_bodies<<<nblk(c->nbody, 64), 64, 0, c->stream>>>(brec, n_dev, cap, c->nbody, tmp.p);
+            int rr = reduce_bodies(c, brec, n_dev, cap, tmp.p);
+            if (rr) return rr;
             CK(cudaStreamSynchronize(c->stream));
         }
         if (imp_rg) CK(cudaMemcpy(imp_rg, tmp.p, 3 * (size_t)c->nbody * sizeof(double), cudaMemcpyDeviceToHost));

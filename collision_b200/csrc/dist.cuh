@@ -95,9 +95,9 @@ __global__ void k_publish(int nranks, int me, const unsigned long long* __restri
         ctr[CTR_PREC] = tot;
         bool ovf = mx > (unsigned long long)caps.region;
         ovf = ovf || ctr[CTR_PAIRS] > (unsigned long long)caps.pairs;
-        ovf = ovf || ctr[CTR_FEATS] + ctr[CTR_FEATS_EE] > (unsigned long long)caps.feats;
-        ovf = ovf || ctr[CTR_UNC] + ctr[CTR_UNC_EE] > (unsigned long long)caps.unc;
-        ovf = ovf || ctr[CTR_HITS] + ctr[CTR_HITS_EE] > (unsigned long long)caps.hits;
+        ovf = ovf || ctr[CTR_MAX_FEATS] > (unsigned long long)caps.feats;   // per chunk of the pair list (k_fold_chunk)
+        ovf = ovf || ctr[CTR_MAX_UNC] > (unsigned long long)caps.unc;
+        ovf = ovf || ctr[CTR_MAX_HITS] > (unsigned long long)caps.hits;
         ovf = ovf || ctr[CTR_BREC] > (unsigned long long)caps.brec;
         ctr[CTR_OVF] = ovf ? 1ull : 0ull;
         maxblk[0] = mx;              // all-reduced with MAX: the region capacity every rank needs

@@ -78,7 +78,10 @@ struct Emit {
 
 enum { CTR_PAIRS = 0, CTR_CAND = 1, CTR_PREC = 2, CTR_BREC = 3, CTR_TRUE = 4, CTR_CONTACTS = 5, CTR_ERROR = 6,
        CTR_DBG_CAND = 7, CTR_FEATS = 8, CTR_BOXSURV = 9, CTR_ROOTS = 10, CTR_FEATS_EE = 11, CTR_ROOTS_EE = 12,
-       CTR_HITS = 13, CTR_HITS_EE = 14, CTR_EXACT = 15, CTR_UNC = 16, CTR_UNC_EE = 17, CTR_OVF = 18, CTR_COUNT = 19 };
+       CTR_HITS = 13, CTR_HITS_EE = 14, CTR_EXACT = 15, CTR_UNC = 16, CTR_UNC_EE = 17, CTR_OVF = 18,
+       // the pair list is processed in chunks (clsn.cu: enqueue_detect): the six list cursors above restart with every chunk;
+       // k_fold_chunk keeps their sums (CTR_TOT + 0..5: FEATS, FEATS_EE, UNC, UNC_EE, HITS, HITS_EE) and the largest chunk
+       CTR_MAX_FEATS = 19, CTR_MAX_UNC = 20, CTR_MAX_HITS = 21, CTR_TOT = 22, CTR_COUNT = 28 };
 
 __device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 __device__ __forceinline__ double mag3(const double* a) { return sqrt(dot3(a, a)); }

@@ -85,7 +85,10 @@ __global__ void k_owner_scatter(const PointRec* __restrict__ rec, long long n, i
 // One warp per point.  Rank the point's keys (all-pairs compare, keys are unique), store the
 // records in rank order, then lanes 0..5 each sum one of imp.xyz / fric.xyz sequentially.
 // mode 0: apply to avgVel (updateAverageVelocity :707-724); mode 1: write the sums to acc arrays.
-template <bool SEG>
+// SEG: the records sit in per-point segments already (pipeline 2).  SORTED: perm[] is already in key order per point
+// (cub::DeviceSegmentedSort, used when movable rigid bodies are present: a sphere vertex that sweeps through a cloth stack
+// collects tens of thousands of records, and the all-pairs ranking is quadratic in that number).
+template <bool SEG, bool SORTED = false>
 __global__ void __launch_bounds__(256)
 k_reduce_points(const PointRec* __restrict__ rec, const int* __restrict__ offs, const int* __restrict__ cnt, int V,
                 const int* __restrict__ perm, int* __restrict__ perm_sorted, const unsigned long long* __restrict__ skey,
@@ -100,19 +103,24 @@ k_reduce_points(const PointRec* __restrict__ rec, const int* __restrict__ offs, 
         const int n = cnt[p];
         if (n == 0) continue;
         const int base = offs[p];
-        // rank = number of smaller keys
-        for (int t = lane; t < n; t += 32) {
-            // SEG: the point's records are the contiguous segment rec[base .. base + n) (written there by k_emit<., true>)
-            const unsigned long long k = SEG ? rec[base + t].key : skey[base + t];
-            int rank = 0;
-            for (int u = 0; u < n; ++u) rank += (SEG ? rec[base + u].key : skey[base + u]) < k ? 1 : 0;
-            perm_sorted[base + rank] = SEG ? base + t : perm[base + t];
+        const int* order = perm_sorted;
+        if (SORTED) {
+            order = perm;
+        } else {
+            // rank = number of smaller keys
+            for (int t = lane; t < n; t += 32) {
+                // SEG: the point's records are the contiguous segment rec[base .. base + n) (written there by k_emit<., true>)
+                const unsigned long long k = SEG ? rec[base + t].key : skey[base + t];
+                int rank = 0;
+                for (int u = 0; u < n; ++u) rank += (SEG ? rec[base + u].key : skey[base + u]) < k ? 1 : 0;
+                perm_sorted[base + rank] = SEG ? base + t : perm[base + t];
+            }
+            __syncwarp();
         }
-        __syncwarp();
         double sum = 0.0;
         if (lane < 6) {
             for (int t = 0; t < n; ++t) {
-                const int r = perm_sorted[base + t];
+                const int r = order[base + t];
                 const double* val = reinterpret_cast<const double*>(rec + r) + 2;  // imp[3], fric[3]
                 sum += val[lane];
             }
@@ -135,34 +143,49 @@ k_reduce_points(const PointRec* __restrict__ rec, const int* __restrict__ offs, 
 }
 
 
-// Rigid-rigid contacts: per-body sums in key order.  One thread per body; records are few.
-// imp_rg accumulates across passes and steps -- the reference never zeroes collsnImpulse_RG
-// (dcollid.cpp:726-733).
-__global__ void k_reduce_bodies(const BodyRec* __restrict__ rec, const unsigned long long* __restrict__ n_rec_ptr,
-                                long long cap, int nbody, double* imp_rg)
+// keep the segment offsets inside the record buffers when a list overflowed (the step is repeated then, but the segmented
+// sort must not run past the end of its arrays in the meantime)
+__global__ void k_clamp_offsets(int n, int* offs, int cap)
 {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nbody) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && offs[i] > cap) offs[i] = cap;
+}
+
+// Rigid-rigid contacts: per-body sums in key order.  imp_rg accumulates across passes and steps -- the reference never
+// zeroes collsnImpulse_RG (dcollid.cpp:726-733).  The records are brought into (body, key) order by two stable radix
+// sorts (key, then body; clsn.cu: reduce_bodies), then one thread per body walks its contiguous run sequentially --
+// the summation order is part of the result, the search for it need not be quadratic (a lattice of fast spheres
+// produces 10^5 sphere-sphere records per pass).
+__global__ void k_body_keys(const BodyRec* __restrict__ rec, const unsigned long long* __restrict__ n_rec_ptr, long long cap,
+                            unsigned long long* __restrict__ key, int* __restrict__ idx)
+{
     long long n = (long long)*n_rec_ptr;
     if (n > cap) n = cap;
-    unsigned long long last = 0;
-    bool first = true;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < cap; r += (long long)gridDim.x * blockDim.x) {
+        key[r] = r < n ? rec[r].key : ~0ull;   // padding sorts behind every record
+        idx[r] = r < n ? (int)r : -1;
+    }
+}
+__global__ void k_body_ids(const BodyRec* __restrict__ rec, const int* __restrict__ idx, long long cap, int* __restrict__ body)
+{
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < cap; r += (long long)gridDim.x * blockDim.x)
+        body[r] = idx[r] >= 0 ? rec[idx[r]].body : 0x7fffffff;
+}
+// body[] ascending (stable in key), idx[] = record index
+__global__ void k_reduce_bodies_sorted(const BodyRec* __restrict__ rec, const int* __restrict__ body, const int* __restrict__ idx,
+                                       long long cap, int nbody, double* imp_rg)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbody) return;
+    long long lo = 0, hi = cap;   // first position with body[pos] >= b
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (body[mid] < b) lo = mid + 1; else hi = mid;
+    }
     double s[3] = {imp_rg[3 * b], imp_rg[3 * b + 1], imp_rg[3 * b + 2]};
-    while (true) {
-        // next record of this body in (key, slot-of-point) order; a key can appear twice for one body
-        // only if both sides of a contact are the same body, which the same-surface filter excludes
-        long long best = -1;
-        unsigned long long bk = ~0ull;
-        for (long long r = 0; r < n; ++r) {
-            if (rec[r].body != b) continue;
-            unsigned long long k = rec[r].key;
-            if (!first && k <= last) continue;
-            if (k < bk) { bk = k; best = r; }
-        }
-        if (best < 0) break;
-        s[0] += rec[best].v[0]; s[1] += rec[best].v[1]; s[2] += rec[best].v[2];
-        last = bk;
-        first = false;
+    for (long long i = lo; i < cap && body[i] == b; ++i) {
+        const BodyRec& r = rec[idx[i]];
+        s[0] += r.v[0]; s[1] += r.v[1]; s[2] += r.v[2];
     }
     imp_rg[3 * b] = s[0]; imp_rg[3 * b + 1] = s[1]; imp_rg[3 * b + 2] = s[2];
 }

@@ -356,10 +356,17 @@ def cloth_spheres(n_layers: int = 8, n: int = 501, n_side: int = 4, level: int =
         b.add_surface(base.x[vids], remap[base.tri_idx[sel]].astype(np.int32), (0, 0, 0))
         b.vel[-1] = base.vel[vids].copy()
     g = (np.arange(n_side) + 0.5) / n_side
+    # z levels: symmetric about the stack (z = 0.3 +- 0.02 of fold + 5 mm of layers), the inner pair 4 cm off its mid-plane
+    # (3.5 mm clear of the highest fold: in reach within one step at |v| >= 5), further levels 6.5 cm apart -- more than twice
+    # the reach of a sphere in one step (radius 1.2 cm + 2 cm of travel), so that the swept volumes of two spheres never
+    # meet: the scene is about fast rigid bodies in a cloth stack, not about rigid bodies ramming each other.
+    half = [0.04 + 0.065 * i for i in range((n_side + 1) // 2)]
+    zs = sorted([0.3025 - h for h in half] + [0.3025 + h for h in half])[: n_side] if n_side % 2 == 0 else \
+        sorted([0.3025] + [0.3025 - h - 0.025 for h in half[: n_side // 2]] + [0.3025 + h + 0.025 for h in half[: n_side // 2]])
     for cx in g:
         for cy in g:
-            for cz in g:
-                c = np.array([0.05 + 0.9 * cx, 0.05 + 0.9 * cy, 0.25 + 0.12 * cz]) + 0.01 * rng.uniform(-1, 1, 3)
+            for cz in zs:
+                c = np.array([0.05 + 0.9 * cx, 0.05 + 0.9 * cy, cz]) + np.array([0.01, 0.01, 0.0005]) * rng.uniform(-1, 1, 3)
                 d = rng.normal(size=3)
                 d /= np.linalg.norm(d)
                 sp, st = icosphere(level, c, 0.012)
