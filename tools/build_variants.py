@@ -27,7 +27,8 @@ VARIANTS = {
     "fa5": ["-DFAST_MIN_BLOCKS=5"],
     "ex5": ["-DEXACT_MIN_BLOCKS=5"],
     "r6": ["-DROOTS_MIN_BLOCKS=6"],
-    "pf": ["-DCULL_PREFILTER=1"],   # FP32 Bernstein pre-filter in k_cull (cubic.cuh: coplanar_prefilter32)
+    "pf": ["-DCULL_PREFILTER=1"],
+    "nosat": ["-DCULL_SAT=0"],      # without the normal-axis separating test in k_cull   # FP32 Bernstein pre-filter in k_cull (cubic.cuh: coplanar_prefilter32)
 }
 
 
