@@ -16,6 +16,7 @@
 #include <cub/cub.cuh>
 #include <math.h>
 #include <stdio.h>
+#include <unistd.h>
 #include <stdlib.h>
 #include <string.h>
 #include <string>
@@ -899,6 +900,7 @@ struct clsn_ctx {
     int pipeline = 1;           // 1 = fast path first (k_fast + k_exact + k_emit), 0 = staged (k_roots + k_contact),
                                 // 2 = 1 + records emitted into per-point segments (experimental)
     DevBuf<PointRec> prec, prec_sorted;
+    DevBuf<ulonglong2> phdr;    // (key, point) headers of prec[], dense
     DevBuf<BodyRec> brec;
     DevBuf<Contact> contacts;
     DevBuf<int> cnt, offs, fill, perm, perm_sorted;
@@ -934,6 +936,7 @@ struct clsn_ctx {
         void* peer_recv[CLSN_MAX_RANKS];         // peers' recv / hdr buffers mapped into this process (own rank: local pointer)
         void* peer_hdr[CLSN_MAX_RANKS];
         bool peer_ipc = false;
+        bool peer_local[CLSN_MAX_RANKS];         // peer context in this process: no IPC mapping to close
         bool direct = false;
         DevBuf<PointRec*> d_peer_region;         // [r] -> this rank's region inside rank r's receive buffer (peer mapping)
         DevBuf<PointRec> stage;                  // records staged per owner before k_push_regions
@@ -1059,7 +1062,7 @@ extern "C" void clsn_destroy(clsn_ctx* c)
     c->stage.release(); c->code.release(); c->code_sorted.release(); c->idx.release(); c->leaf_elem.release();
     c->selem.release(); c->nodes.release(); c->tree_scratch.release(); c->tree_scratch_t.release();
     c->tree_ticket.release(); c->lbox.release(); c->bounds.release();
-    c->cub_tmp.release(); c->pairs.release(); c->dbg_cand.release(); c->feats.release(); c->pair_hit.release(); c->rootrecs.release(); c->hits.release(); c->unc.release(); c->prec.release(); c->prec_sorted.release(); c->brec.release();
+    c->cub_tmp.release(); c->pairs.release(); c->dbg_cand.release(); c->feats.release(); c->pair_hit.release(); c->rootrecs.release(); c->hits.release(); c->unc.release(); c->prec.release(); c->prec_sorted.release(); c->phdr.release(); c->brec.release();
     c->contacts.release(); c->cnt.release(); c->offs.release(); c->fill.release(); c->perm.release();
     c->perm_sorted.release(); c->skey.release(); c->skey_sorted.release(); c->cub_tmp2.release(); c->bkey.release(); c->bidx.release(); c->bbody.release(); c->counters.release(); c->acc_imp.release(); c->acc_fric.release();
     c->rigid.release(); c->zone_lists.release(); c->strain.release(); c->d_rg_pts.release(); c->d_rg_state.release();
@@ -1067,7 +1070,7 @@ extern "C" void clsn_destroy(clsn_ctx* c)
         clsn_ctx::Dist& d = c->dist;
         if (d.peer_ipc)
             for (int r = 0; r < c->nranks; ++r)
-                if (r != c->rank && d.peer_recv[r]) { cudaIpcCloseMemHandle(d.peer_recv[r]); cudaIpcCloseMemHandle(d.peer_hdr[r]); }
+                if (r != c->rank && d.peer_recv[r] && !d.peer_local[r]) { cudaIpcCloseMemHandle(d.peer_recv[r]); cudaIpcCloseMemHandle(d.peer_hdr[r]); }
         if (d.comm) d.api.CommDestroy(d.comm);
         d.recv.release(); d.hdr.release(); d.d_peer_region.release(); d.d_peer_hdr.release(); d.send_cnt.release();
         d.stage.release(); d.d_stage_region.release();
@@ -1132,7 +1135,7 @@ static int dist_alloc_regions(clsn_ctx* c, long long cap_region)
     CK(cudaStreamSynchronize(c->stream));
     if (d.peer_ipc)
         for (int r = 0; r < G; ++r)
-            if (r != me && d.peer_recv[r]) { cudaIpcCloseMemHandle(d.peer_recv[r]); cudaIpcCloseMemHandle(d.peer_hdr[r]); }
+            if (r != me && d.peer_recv[r] && !d.peer_local[r]) { cudaIpcCloseMemHandle(d.peer_recv[r]); cudaIpcCloseMemHandle(d.peer_hdr[r]); }
     for (int r = 0; r < CLSN_MAX_RANKS; ++r) d.peer_recv[r] = d.peer_hdr[r] = nullptr;
     d.recv.release();
     d.hdr.release();
@@ -1141,10 +1144,15 @@ static int dist_alloc_regions(clsn_ctx* c, long long cap_region)
     CK(d.hdr.reserve(CLSN_MAX_RANKS));
     CK(cudaMemset(d.hdr.p, 0, CLSN_MAX_RANKS * sizeof(unsigned long long)));
     // handles: [recv handle | hdr handle] per rank
-    struct Handles { cudaIpcMemHandle_t recv, hdr; };
+    struct Handles { cudaIpcMemHandle_t recv, hdr; long long pid; int device; int pad; void* recv_ptr; void* hdr_ptr; };
     Handles mine;
+    memset(&mine, 0, sizeof(mine));
     CK(cudaIpcGetMemHandle(&mine.recv, d.recv.p));
     CK(cudaIpcGetMemHandle(&mine.hdr, d.hdr.p));
+    mine.pid = (long long)getpid();
+    mine.device = c->device;
+    mine.recv_ptr = d.recv.p;
+    mine.hdr_ptr = d.hdr.p;
     DevBuf<Handles> dh;
     CK(dh.reserve((size_t)G));
     CK(cudaMemcpy(dh.p + me, &mine, sizeof(mine), cudaMemcpyHostToDevice));
@@ -1154,12 +1162,22 @@ static int dist_alloc_regions(clsn_ctx* c, long long cap_region)
     CK(cudaMemcpy(all.data(), dh.p, (size_t)G * sizeof(Handles), cudaMemcpyDeviceToHost));
     dh.release();
     d.peer_ipc = true;
+    bool* same_process = d.peer_local;
+    for (int r = 0; r < CLSN_MAX_RANKS; ++r) same_process[r] = false;
     std::vector<PointRec*> region((size_t)G);
     std::vector<unsigned long long*> hdrp((size_t)G);
     for (int r = 0; r < G; ++r) {
         if (r == me) {
             d.peer_recv[r] = d.recv.p;
             d.peer_hdr[r] = d.hdr.p;
+        } else if (all[r].pid == mine.pid) {
+            // the peer context lives in this process (one host thread per GPU): plain peer access, no IPC mapping
+            const cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+            cudaGetLastError();
+            d.peer_recv[r] = all[r].recv_ptr;
+            d.peer_hdr[r] = all[r].hdr_ptr;
+            same_process[r] = true;
         } else {
             CK(cudaIpcOpenMemHandle(&d.peer_recv[r], all[r].recv, cudaIpcMemLazyEnablePeerAccess));
             CK(cudaIpcOpenMemHandle(&d.peer_hdr[r], all[r].hdr, cudaIpcMemLazyEnablePeerAccess));
@@ -1560,6 +1578,8 @@ static int enqueue_detect(clsn_ctx* c, int mode, int slot, const unsigned long l
     mark(c, PH_TRAVERSE);
     Emit E;
     E.prec = c->prec.p; E.brec = c->brec.p; E.contacts = c->dbg_contacts ? c->contacts.p : nullptr;
+    CK(c->phdr.reserve(c->prec.n));
+    E.phdr = c->phdr.p;
     E.counters = ctr;
     E.cap_prec = (long long)c->prec.n; E.cap_brec = (long long)c->brec.n; E.cap_contacts = (long long)c->contacts.n;
     E.cnt = c->cnt.p; E.cnt_rg = c->cnt_rg.p; E.body_mass = c->body_mass.p;
@@ -1881,7 +1901,8 @@ static int reduce_records(clsn_ctx* c, int mode, int what = 3)  // what: bit 0 p
             size_t tmp = c->cub_tmp.n;
             CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->cnt.p, c->offs.p, V + 1, c->stream));
             CK(cudaMemsetAsync(c->fill.p, 0, ((size_t)V + 1) * sizeof(int), c->stream));
-            k_scatter<<<c->sm_count * 8, 256, 0, c->stream>>>(prec, n_prec_dev, cap_p, c->offs.p, c->fill.p, c->perm.p, c->skey.p);
+            k_scatter<<<c->sm_count * 8, 256, 0, c->stream>>>(prec, imported ? nullptr : c->phdr.p, n_prec_dev, cap_p, c->offs.p, c->fill.p,
+                                                              c->perm.p, c->skey.p);
         }
         if (mode == 1) {
             CK(c->acc_imp.reserve(3 * (size_t)V)); CK(c->acc_fric.reserve(3 * (size_t)V));

@@ -333,9 +333,11 @@ k_refit8(const int4* __restrict__ selem, Tree8 tr, const Vec4* __restrict__ xo, 
     }
     if (tr.nlev == 3) return;
     // levels 4 .. nlev: the last block to arrive reduces the level-3 boxes (a few thousand at most)
-    __threadfence();
-    __syncthreads();
-    if (t == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    // only thread 0's own stores (the block's level-3 box in `scratch`) are read by the last block: one fence, by it
+    if (t == 0) {
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
     __syncthreads();
     if (!s_last) return;
     if (t == 0) *ticket = 0u;   // armed for the next launch

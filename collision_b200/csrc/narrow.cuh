@@ -66,6 +66,7 @@ __device__ __forceinline__ unsigned long long reserve_owner(unsigned long long* 
 
 struct Emit {
     PointRec* prec;
+    ulonglong2* phdr;            // (key, point) of every record once more as a dense 16-byte array (k_scatter reads only this)
     BodyRec* brec;
     Contact* contacts;           // nullptr unless debug
     unsigned long long* counters; // see CTR_* in clsn.cu
@@ -184,7 +185,13 @@ __device__ __forceinline__ void put_prec(const Emit& E, const SegOut& S, unsigne
         if (s < E.cap_prec) store_prec(E.prec + s, key, point, imp, fric);
     } else {
         atomicAdd(&E.cnt[point], 1);
-        if ((long long)slot < E.cap_prec) store_prec(E.prec + slot, key, point, imp, fric);
+        if ((long long)slot < E.cap_prec) {
+            store_prec(E.prec + slot, key, point, imp, fric);
+            ulonglong2 h;
+            h.x = key;
+            h.y = (unsigned long long)(unsigned)point;
+            E.phdr[slot] = h;
+        }
         ++slot;
     }
 }

@@ -14,14 +14,17 @@
 namespace clsn {
 
 // records -> per-point slots.  fill[] must be zero.
-__global__ void k_scatter(const PointRec* __restrict__ rec, const unsigned long long* __restrict__ n_rec_ptr,
+// hdr: the (key, point) headers of the records as a dense 16-byte array when the emitting kernels wrote one (the
+// context's own list), else null: then the header is read out of the 64-byte record, which costs the whole record in
+// DRAM traffic (measured: k_scatter read 1.9 GB per step for 0.4 GB of headers).
+__global__ void k_scatter(const PointRec* __restrict__ rec, const ulonglong2* __restrict__ hdr, const unsigned long long* __restrict__ n_rec_ptr,
                           long long cap, const int* __restrict__ offs, int* fill, int* __restrict__ perm,
                           unsigned long long* __restrict__ skey)
 {
     const long long n = (long long)*n_rec_ptr;
     if (n > cap) return;   // the record list overflowed: offs[] describes records that were never stored; the step is repeated
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
-        const ulonglong2 h = *reinterpret_cast<const ulonglong2*>(rec + r);
+        const ulonglong2 h = hdr ? hdr[r] : *reinterpret_cast<const ulonglong2*>(rec + r);
         const int p = (int)(unsigned)h.y;
         const int slot = offs[p] + atomicAdd(fill + p, 1);
         perm[slot] = (int)r;
@@ -117,6 +120,9 @@ k_reduce_points(const PointRec* __restrict__ rec, const int* __restrict__ offs, 
             }
             __syncwarp();
         }
+        // One lane per component walks the records in key order.  (Fetching 32 records with the whole warp and handing the
+        // addends over by shuffles was measured: 1.7x SLOWER -- twelve shuffles per record cost more issue slots than the
+        // two dependent loads cost latency at 64 resident warps per SM.)
         double sum = 0.0;
         if (lane < 6) {
             for (int t = 0; t < n; ++t) {

@@ -36,15 +36,45 @@ bool isStaticRigidBody(const POINT* p) { return p->state->is_fixed; }
 bool isMovableRigidBody(const POINT* p) { return p->state->is_movableRG; }
 bool isRigidBody(const POINT* p) { return isStaticRigidBody(p) || isMovableRigidBody(p); }
 
-CollisionSolver::CollisionSolver(int dim) : has_collision(false), m_dim(dim), m_ctx(nullptr), m_topology_dirty(true)
+CollisionSolver::CollisionSolver(int dim, int device) : has_collision(false), m_dim(dim), m_ctx(nullptr), m_topology_dirty(true)
 {
     for (int i = 0; i < 3; ++i) { Boundary[i][0] = -1e30; Boundary[i][1] = 1e30; }
     std::memset(&m_stats, 0, sizeof(m_stats));
     std::memset(&m_zone_stats, 0, sizeof(m_zone_stats));
-    int rc = clsn_create(&m_ctx, 0);
+    int rc = clsn_create(&m_ctx, device);
     if (rc != CLSN_OK || !m_ctx) throw std::runtime_error("collision_b200: no usable CUDA device (there is no CPU fallback)");
     clsn_set_impact_zones(m_ctx, 1, 0);
     clsn_set_strain_limiting(m_ctx, 1);
+}
+
+void CollisionSolver::multiGPUUniqueId(unsigned char id[128])
+{
+    if (clsn_dist_unique_id(id) != CLSN_OK) throw std::runtime_error("collision_b200: NCCL is not available (clsn_dist_unique_id)");
+}
+
+void CollisionSolver::enableMultiGPU(int rank, int nranks, const unsigned char id[128])
+{
+    if (m_points.empty()) {   // the library wants the topology first: remember, join after the first assembleFromInterface
+        m_dist_rank = rank;
+        m_dist_nranks = nranks;
+        std::memcpy(m_dist_id, id, 128);
+        return;
+    }
+    int rc = clsn_dist_init(m_ctx, rank, nranks, id);
+    if (rc != CLSN_OK) fail(rc, "clsn_dist_init");
+    m_dist_nranks = 0;
+}
+
+void CollisionSolver::printDebugVariable() const
+{
+    long coplanar = 0, features = 0, contacts = 0;
+    for (int i = 0; i < m_stats.n_ccd_passes; ++i) {
+        coplanar += (long)m_stats.ccd[i].coplanar;
+        features += (long)m_stats.ccd[i].features;
+        contacts += (long)m_stats.ccd[i].contacts;
+    }
+    std::printf("    %ld isCoplanar true, %ld CCD feature tests after the culls, %ld contacts, %ld proximity contacts\n", coplanar, features,
+                contacts, (long)m_stats.proximity.contacts);
 }
 
 void CollisionSolver::setStrainLimiting(bool on)
@@ -166,6 +196,7 @@ void CollisionSolver::gatherTopology(const INTERFACE* intfc)
     m_xold.resize(3 * (size_t)V); m_xnew.resize(3 * (size_t)V); m_xout.resize(3 * (size_t)V); m_vel.resize(3 * (size_t)V);
     m_has.resize(V);
     m_topology_dirty = false;
+    if (m_dist_nranks > 0) enableMultiGPU(m_dist_rank, m_dist_nranks, m_dist_id);
 }
 
 void CollisionSolver3d::assembleFromInterface(const INTERFACE* intfc, double dt)  // dcollid3d.cpp:12-52

@@ -158,7 +158,9 @@ protected:
     std::vector<uint8_t> m_flags;
     std::vector<int32_t> m_body;
     std::vector<double> m_body_mass;
-    std::vector<HYPER_SURF*> m_body_hs;   // body index -> the caller's HYPER_SURF (center_of_mass / center_of_mass_velo)
+    std::vector<HYPER_SURF*> m_body_hs;
+    int m_dist_rank = -1, m_dist_nranks = 0;   // enableMultiGPU asked for before the topology was known
+    unsigned char m_dist_id[128];   // body index -> the caller's HYPER_SURF (center_of_mass / center_of_mass_velo)
     std::vector<double> m_xold, m_xnew, m_xout, m_vel;
     std::vector<uint8_t> m_has;
     clsn_step_stats m_stats;
@@ -170,7 +172,7 @@ protected:
     void fail(int rc, const char* where) const;
 
 public:
-    explicit CollisionSolver(int dim);
+    explicit CollisionSolver(int dim, int device = 0);
     virtual ~CollisionSolver();
     static void setRoundingTolerance(double);
     static double getRoundingTolerance();
@@ -206,12 +208,20 @@ public:
     const clsn_step_stats& lastStats() const { return m_stats; }
     bool stillColliding() const { return m_stats.still_colliding != 0; }  // MAX_ITER passes were not enough
     const clsn_zone_stats& lastZoneStats() const { return m_zone_stats; }
-    static void printDebugVariable() {}
+    // the reference's debug counters (collid.h:208-213: is_coplanar, edg_to_edg, pt_to_tri, printed by
+    // printDebugVariable, dcollid.cpp:838-847) restated from the statistics of the last step
+    void printDebugVariable() const;
+    // Multi-GPU (include/collision_b200.h: clsn_dist_*): one solver per GPU of a node, one process (MPI rank) or thread
+    // each.  Any rank obtains the 128-byte id once and hands it to all of them (MPI_Bcast ...); every rank then calls
+    // enableMultiGPU -- before or after assembleFromInterface -- and keeps calling resolveCollision as before: all ranks
+    // pass the same mesh state and get the same, complete result back (bit-identical to one GPU).
+    static void multiGPUUniqueId(unsigned char id[128]);
+    void enableMultiGPU(int rank, int nranks, const unsigned char id[128]);
 };
 
 class CollisionSolver3d : public CollisionSolver {
 public:
-    CollisionSolver3d() : CollisionSolver(3) {}
+    explicit CollisionSolver3d(int device = 0) : CollisionSolver(3, device) {}
     void assembleFromInterface(const INTERFACE*, double dt);
     void createImpZoneForRG(const INTERFACE*) {}  // the rigid-body lists are rebuilt from topology by clsn_set_topology
 };

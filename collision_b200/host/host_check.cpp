@@ -1,8 +1,15 @@
 // Drives the C++ host mirror the way the reference's test.cpp drives CollisionSolver3d (test.cpp:96-107):
 // reads a flat scene file written by tests/test_gpu_host_cpp.py, builds the POINT/TRI/BOND mesh, runs
 // `steps` x { spring solver stand-in; assembleFromInterface; setFrictionConstant; resolveCollision },
-// writes final coords + vel.  Usage: host_check scene.bin out.bin steps
+// writes final coords + vel.  Usage: host_check scene.bin out.bin steps [ngpus [nozones]]
+// ngpus > 1: one host thread per GPU, each with its own copy of the mesh and its own CollisionSolver3d(device), joined by
+// CollisionSolver::enableMultiGPU -- the multi-GPU step of the library driven through the reference-shaped C++ API; rank r
+// writes out.bin.r (all of them must equal the single-GPU out.bin bit for bit).  nozones: impact-zone fail-safe off (it is
+// not available in the multi-GPU step).
 #include <cmath>
+#include <cstring>
+#include <string>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -26,10 +33,10 @@ static double rest_length(const double* p, const double* q)
     return std::sqrt(s);
 }
 
-int main(int argc, char** argv)
+static int run(const char* scene_path, const std::string& out_path, int steps, int device, int rank, int nranks,
+               const unsigned char* id, bool zones)
 {
-    if (argc < 4) return 2;
-    FILE* f = fopen(argv[1], "rb");
+    FILE* f = fopen(scene_path, "rb");
     if (!f) return 2;
     int hdr[6];  // V T B n_surf n_curve nhs
     if (fread(hdr, sizeof(int), 6, f) != 6) return 2;
@@ -42,7 +49,6 @@ int main(int argc, char** argv)
     auto flags = rd<unsigned char>(f, V);
     auto vhs = rd<int>(f, V);
     fclose(f);
-    const int steps = atoi(argv[3]);
 
     std::vector<HYPER_SURF> hs(NH);
     for (int i = 0; i < NH; ++i) { hs[i] = HYPER_SURF(); hs[i].wave_type = kind[i]; hs[i].body_index = i; hs[i].total_mass = mass[i]; }
@@ -81,7 +87,9 @@ int main(int argc, char** argv)
     for (auto& c : cur) intfc.curves.push_back(&c);
     for (int i = 0; i < 3; ++i) { intfc.L[i] = par[7 + i]; intfc.U[i] = par[10 + i]; }
 
-    CollisionSolver3d* solver = new CollisionSolver3d();
+    CollisionSolver3d* solver = new CollisionSolver3d(device);
+    if (!zones) solver->setImpactZones(false);
+    if (nranks > 1) solver->enableMultiGPU(rank, nranks, id);
     CollisionSolver::setRoundingTolerance(par[0]);
     CollisionSolver::setFabricThickness(par[1]);
     CollisionSolver::setSpringConstant(par[2]);
@@ -99,11 +107,38 @@ int main(int argc, char** argv)
         CollisionSolver::setFrictionConstant(par[4]);
         solver->resolveCollision();
     }
-    FILE* o = fopen(argv[2], "wb");
+    FILE* o = fopen(out_path.c_str(), "wb");
     for (int v = 0; v < V; ++v) fwrite(pt[v].coords, sizeof(double), 3, o);
     for (int v = 0; v < V; ++v) fwrite(st[v].vel, sizeof(double), 3, o);
     fclose(o);
-    printf("host_check: %d steps, has_collision=%d, ccd passes last step=%d\n", steps, (int)solver->hasCollision(), solver->lastStats().n_ccd_passes);
+    printf("host_check[%d/%d]: %d steps, has_collision=%d, ccd passes last step=%d\n", rank, nranks, steps, (int)solver->hasCollision(),
+           solver->lastStats().n_ccd_passes);
     delete solver;
+    return 0;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 4) return 2;
+    const int steps = atoi(argv[3]);
+    const int ngpus = argc > 4 ? atoi(argv[4]) : 1;
+    const bool zones = !(argc > 5 && std::strcmp(argv[5], "nozones") == 0) && ngpus <= 1;
+    if (ngpus <= 1) return run(argv[1], argv[2], steps, 0, 0, 1, nullptr, zones);
+    unsigned char id[128];
+    CollisionSolver::multiGPUUniqueId(id);
+    std::vector<std::thread> th;
+    std::vector<int> rc((size_t)ngpus, 0);
+    for (int r = 0; r < ngpus; ++r)
+        th.emplace_back([&, r]() {
+            try {
+                rc[r] = run(argv[1], std::string(argv[2]) + "." + std::to_string(r), steps, r, r, ngpus, id, false);
+            } catch (const std::exception& e) {
+                fprintf(stderr, "rank %d: %s\n", r, e.what());
+                rc[r] = 3;
+            }
+        });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < ngpus; ++r)
+        if (rc[r]) return rc[r];
     return 0;
 }

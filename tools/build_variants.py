@@ -19,6 +19,7 @@ VARIANTS = {
     "c3": ["-DCULL_MIN_BLOCKS=3"],
     "c5": ["-DCULL_MIN_BLOCKS=5"],
     "c5co": ["-DCULL_MIN_BLOCKS=5", "-DCULL_SMEM_CARVEOUT=100"],   # 5 resident blocks: <= 102 registers + full carve-out
+    "g4": ["-DNARROW_GRID_MULT=4"],
     "g8": ["-DNARROW_GRID_MULT=8"],
     "g32": ["-DNARROW_GRID_MULT=32"],
     "t64": ["-DTRAV_THREADS=64"],
