@@ -246,8 +246,11 @@ __device__ __forceinline__ void node_store(Node8* nd, int c, const float b[6], c
 // Traffic per leaf: 16 B element + vertex gathers (L2) in, 48 B exact box + 24 B level-1 slot out.
 // scratch: 2 x cnt[3] x 6 floats (ping-pong of the upper levels), scratch_t: 2 x cnt[3] bytes, ticket: one zeroed word,
 // root_box: 6 floats (the scene box of this refit; volume rule of dcollid.cpp:377-385)
+#ifndef REFIT_MIN_BLOCKS
+#define REFIT_MIN_BLOCKS 3
+#endif
 template <bool MOVING>
-__global__ void __launch_bounds__(REFIT_LEAVES)
+__global__ void __launch_bounds__(REFIT_LEAVES, REFIT_MIN_BLOCKS)
 k_refit8(const int4* __restrict__ selem, Tree8 tr, const Vec4* __restrict__ xo, const Vec4* __restrict__ av, double dt,
          double* __restrict__ lbox, const uint8_t* __restrict__ vdirty, float* scratch, uint8_t* scratch_t, unsigned* ticket,
          float* root_box, const unsigned long long* __restrict__ gate)

@@ -22,6 +22,8 @@ VARIANTS = {
     "g4": ["-DNARROW_GRID_MULT=4"],
     "g8": ["-DNARROW_GRID_MULT=8"],
     "g32": ["-DNARROW_GRID_MULT=32"],
+    "rb3": ["-DREFIT_MIN_BLOCKS=3"],
+    "rb4": ["-DREFIT_MIN_BLOCKS=4"],
     "t64": ["-DTRAV_THREADS=64"],
     "t256": ["-DTRAV_THREADS=256"],
     "fa3": ["-DFAST_MIN_BLOCKS=3"],
