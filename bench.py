@@ -444,7 +444,7 @@ def run_b200(args):
         kernels = {}
         for k, b in bytes_.items():
             t = per_step.get(k, 0.0)
-            if t > 0:
+            if t > 1e-3 * step_ms:   # a phase that did not run in the timed steps (the tree is kept across steps) leaves ~0
                 kernels[k] = {"ms": t, "share": t / step_ms, "alg_bytes": int(b), "gbs": b / (t * 1e-3) / 1e9,
                               "frac_hbm": b / (t * 1e-3) / 1e9 / peak}
         fp64_peak, fp64_src = 18.48e12, "fallback: 148 SMs x 64 lanes x 1.965 GHz (profiles/r2_fp64_peak.json, measured on this pool)"
