@@ -27,6 +27,8 @@ SCENES = {
     "sheet_wall": lambda: scenes.sheet_wall(),
     "drape_small": lambda: scenes.drape(n=40, level=3),
     "layered_4x24": lambda: scenes.layered_cloth(4, 24, seed=99),
+    # config-5 family: cloth stack + fast movable rigid spheres (per-body accumulators, rigidification, updateFinalForRG)
+    "cloth_spheres": lambda: scenes.cloth_spheres(n_layers=2, n=17, n_side=2, level=1, seed=31),
 }
 
 
@@ -60,7 +62,7 @@ def test_phase_parity(name):
     gpu.close()
 
 
-@pytest.mark.parametrize("name", ["two_sheets", "mixed", "ball_plane", "layered_4x24", "sheet_wall"])
+@pytest.mark.parametrize("name", ["two_sheets", "mixed", "ball_plane", "layered_4x24", "sheet_wall", "cloth_spheres"])
 def test_whole_step_parity(name):
     """clsn_step_host (the drop-in call) against orc_resolve over several steps."""
     sc = SCENES[name]()
