@@ -426,7 +426,10 @@ def run_b200(args):
         "step_ms": step_ms, "wall_ms_per_step": wall_ms / args.steps,
         "value_reference_equivalent": ccd_pairs_ref / (step_ms * 1e-3),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                "h2d_bytes_per_step": int(2 * x_old.nbytes), "d2h_bytes_per_step": int(2 * x_old.nbytes + scene.V)},
+                # whole job: with the in-library multi-GPU step every rank uploads only its 1/N share of x_old / x_new (the ranks
+                # all-gather the rest over NVLink) and downloads the complete result (x, avgVel, has_collsn)
+                "h2d_bytes_per_step": int(2 * x_old.nbytes) * (1 if (world == 1 or lib_dist) else world),
+                "d2h_bytes_per_step": int(2 * x_old.nbytes + scene.V) * world},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
