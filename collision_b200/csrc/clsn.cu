@@ -1032,10 +1032,10 @@ extern "C" int clsn_create(clsn_ctx** out, int device)
     for (auto& e : c->ev) cudaEventCreate(&e);
     cudaEventCreate(&c->bracket[0]);
     cudaEventCreate(&c->bracket[1]);
-    cudaMallocHost((void**)&c->h_counters, (8 * 32 + 8) * sizeof(unsigned long long));   // + root box of the last refit
-    c->counters.reserve(256 + 8 * 32);
-    cudaMemset(c->counters.p, 0, (256 + 8 * 32) * sizeof(unsigned long long));
-    c->ctr = c->counters.p + 256 + 32 * 7;
+    cudaMallocHost((void**)&c->h_counters, (PASS_SLOTS * CTR_STRIDE + 8) * sizeof(unsigned long long));   // + root box of the last refit
+    c->counters.reserve(CTR_LEGACY + PASS_SLOTS * CTR_STRIDE);
+    cudaMemset(c->counters.p, 0, (CTR_LEGACY + PASS_SLOTS * CTR_STRIDE) * sizeof(unsigned long long));
+    c->ctr = pass_block(c, PASS_SLOT_STEP);
     c->bounds.reserve(8);
     clsn_params p;
     p.eps = 1e-6; p.thickness = 1e-4; p.dt = 1e-3; p.k = 1000; p.m = 0.01; p.lambda = 0.02; p.cr = 0.0;
@@ -1412,6 +1412,7 @@ extern "C" int clsn_set_topology(clsn_ctx* c, int V, int T, const int32_t* tri_i
         c->mrg_com.assign(3 * (size_t)nbody, 0.0);
         c->mrg_valid.assign((size_t)nbody, 0);
     }
+    if (c->dist.on) c->dist.per_rank = (V + c->nranks - 1) / c->nranks;   // vertex ownership follows the new vertex count
     // host-side restatement of createImpZoneForRG's union-find lists (topology only)
     int r = c->rigid.build(V, T, tri_idx, tri_surf, vflags);
     if (r != 0) return fail(c, CLSN_E_CUDA, "rigid-body topology upload failed");
@@ -1519,7 +1520,7 @@ extern "C" int clsn_avg_velocity(clsn_ctx* c)
 {
     if (!c || !c->V) return CLSN_E_ARG;
     cudaSetDevice(c->device);
-    k_avg_velocity<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->xo.p, c->xn.p, c->av.p, c->prm.dt, c->counters.p + 256 + 32 * 7);
+    k_avg_velocity<<<nblk(c->V, 256), 256, 0, c->stream>>>(c->V, c->xo.p, c->xn.p, c->av.p, c->prm.dt, pass_block(c, PASS_SLOT_STEP));
     CK(cudaGetLastError());
     c->launches += 1;
     c->dirty_valid = false;
@@ -1741,7 +1742,7 @@ static int grow_after_pass(clsn_ctx* c, const unsigned long long* h, bool moving
         CK(c->hits.reserve((size_t)(h[CTR_MAX_HITS] * 5 / 4 + 1024)));
         redo = true;
     }
-    if (h[CTR_PREC] > c->prec.n) {
+    if (!c->dist.on && h[CTR_PREC] > c->prec.n) {   // (multi-GPU: point records live in the receive regions, not here)
         size_t want = (size_t)(h[CTR_PREC] * 5 / 4 + 1024);
         CK(c->prec.reserve(want)); CK(c->perm.reserve(want)); CK(c->perm_sorted.reserve(want)); CK(c->skey.reserve(want));
         redo = true;

@@ -183,7 +183,9 @@ int clsn_synchronize(clsn_ctx*);
  * r traverses its slice of the Morton-ordered query leaves, impulse records are stored straight into the receive buffer of
  * the rank that owns the point (NVLink peer stores from inside the narrow-phase kernels, mapped with cudaIpc), each rank
  * reduces its own vertex range, NCCL all-reduces the pass counters (the device-side `while (is_collision)`) and
- * all-gathers avgVel / has_collsn.  No host read-back inside the step.  Not available in this mode: the impact-zone
+ * all-gathers avgVel / has_collsn.  No host read-back inside the step.  clsn_upload_state / clsn_step_host are collective
+ * in this mode (each rank moves only its share of the input arrays across PCIe, the rest arrives over NVLink), like
+ * clsn_resolve, clsn_detect and clsn_apply: every rank has to make the same calls.  Not available in this mode: the impact-zone
  * fail-safe (CLSN_E_UNSUPPORTED if a step still collides after MAX_ITER passes with clsn_set_impact_zones on). */
 int clsn_dist_unique_id(void* id128);
 int clsn_dist_init(clsn_ctx*, int rank, int nranks, const void* id128);

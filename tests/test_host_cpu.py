@@ -285,3 +285,28 @@ def test_vtk_dump_mirrors_the_reference_layout(tmp_path):
     col = arr(piece.find("CellData/DataArray")).astype(int).reshape(-1, 3)
     red_tris = (cnt[sc.tri_idx] > 0).any(axis=1)
     assert np.array_equal(col[sc.B:, 0] == 255, red_tris) and np.array_equal(col[sc.B:, 1] == 255, ~red_tris)
+
+
+def test_bench_reference_arm_line(tmp_path):
+    """`bench.py --impl reference` (here on a bounded sample, so that the CPU suite stays short): one JSON line on stdout with
+    the contract's keys, the reference's own library as the thing timed, nothing from the CUDA path loaded."""
+    import json
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built here")
+    env = dict(os.environ, TMPDIR=str(tmp_path))   # the per-box cache of the arm goes to the temp dir
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--sample-reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, "exactly one JSON line on stdout"
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "ccd_pairs_per_sec" and d["unit"] == "pairs/s" and d["higher_is_better"] is True
+    assert d["steps"] == 1 and d["warmup"] == 0 and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    # a second run on the same "box" reuses the measurement and says so
+    r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--sample-reference", "--steps", "1",
+                         "--warmup", "0", "--gpus", "2"], capture_output=True, text=True, timeout=600, env=env)
+    d2 = json.loads([ln for ln in r2.stdout.splitlines() if ln.strip()][0])
+    assert d2["value"] == d["value"] and "reused" in d2["cpu_baseline"]["sample"] and d2["n_gpus"] == 2
