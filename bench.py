@@ -5,11 +5,17 @@
     python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU path on host cores
 
-A step = one resolveCollision over the 1 M-triangle layered-cloth scene (config 4), always started
-from the same state.  metric = CCD pairs/s = narrow-phase callbacks (element pairs with overlapping
-moving leaf boxes, all CCD passes of the step) / step time; ms_per_step is the other half of the
-headline.  `value` times the step with x_old/x_new already in HBM; `e2e` times the drop-in call
-(clsn_step_host) with pinned host buffers, copies inside the timed region.
+A step = one resolveCollision over the 1 M-triangle layered-cloth scene (config 4), always started from the same
+state.  metric = CCD pairs/s = candidate element pairs handed to the narrow phase by the timed steps (all CCD passes) /
+step time; the reference-equivalent callback count and rate are reported beside it (config.ccd_pairs_reference_equivalent,
+value_reference_equivalent); ms_per_step is the other half of the headline.  `value` times the step with x_old / x_new
+already in HBM (CUDA events on the library's stream); `e2e` times the drop-in call (clsn_step_host) with pinned host
+buffers, copies inside the timed region; `e2e_api_default` the same call with the impact-zone fail-safe and strain
+limiting on (what the reference's resolveCollision does on this input); `roofline` = the dominant phase against the
+measured FP64 issue peak (bound "fp64") or the HBM copy peak, `roofline_memory` = the memory-bound passes against the
+HBM copy peak; `cpu_baseline` = the compiled reference on a bounded 50 K-triangle sample.
+N > 1 (torchrun): the in-library multi-GPU step (csrc/dist.cuh); --exchange owner|gather selects the python-driven protocols.
+--impl reference: the compiled reference on config 4 ITSELF, one step (~10 min on one core), see run_reference().
 
 The one JSON line on stdout is the contract; everything else goes to stderr.
 """

@@ -1136,7 +1136,13 @@ static int dist_alloc_regions(clsn_ctx* c, long long cap_region)
     if (d.peer_ipc)
         for (int r = 0; r < G; ++r)
             if (r != me && d.peer_recv[r] && !d.peer_local[r]) { cudaIpcCloseMemHandle(d.peer_recv[r]); cudaIpcCloseMemHandle(d.peer_hdr[r]); }
+    const bool had_buffers = d.recv.p != nullptr;
     for (int r = 0; r < CLSN_MAX_RANKS; ++r) d.peer_recv[r] = d.peer_hdr[r] = nullptr;
+    if (had_buffers) {
+        // nobody frees a buffer that a peer still has mapped: all ranks have closed their mappings before any rank goes on
+        NCK(d.api.AllReduce(d.maxblk.p, d.maxblk.p, 4, ncclUint64, ncclMax, d.comm, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
     d.recv.release();
     d.hdr.release();
     d.cap_region = cap_region;
@@ -1231,7 +1237,8 @@ extern "C" int clsn_dist_init(clsn_ctx* c, int rank, int nranks, const void* id1
     if (c->brec.n < (size_t)d.cap_brec_x) CK(c->brec.reserve((size_t)d.cap_brec_x));
     d.on = true;
     // receive regions: ~64 records per element spread over G x G (source, owner) regions; grown on demand
-    const long long cap = std::max<long long>(1 << 14, (64ll * c->N) / ((long long)nranks * nranks) + 1024);
+    long long cap = std::max<long long>(1 << 14, (64ll * c->N) / ((long long)nranks * nranks) + 1024);
+    if (const char* e = getenv("CLSN_DIST_REGION_CAP")) cap = std::max<long long>(64, atoll(e));   // tests: force the growth path
     return dist_alloc_regions(c, cap);
 }
 

@@ -198,6 +198,9 @@ public:
 
     virtual void assembleFromInterface(const INTERFACE*, double dt) = 0;
     virtual void createImpZoneForRG(const INTERFACE*) = 0;
+    // Single-pair entry points (collid.h:199-200): the pair's own contributions are added to the points' accumulators.
+    // Limitation: a rigid-rigid contact's body impulse (SpreadImpactZoneImpulse, dcollid.cpp:1101-1115) reaches only the
+    // points of the two elements, not the rest of their bodies -- the whole-step path (resolveCollision) handles bodies.
     bool isProximity(const CD_HSE*, const CD_HSE*);
     bool isCollision(const CD_HSE*, const CD_HSE*);
     void resolveCollision();
