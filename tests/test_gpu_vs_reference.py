@@ -25,6 +25,7 @@ SCENES = {
     "drape": lambda: scenes.drape(n=24, level=2),
     "layered": lambda: scenes.layered_cloth(4, 13),
     "sheet_wall": lambda: scenes.sheet_wall(n=10),
+    "cloth_spheres": lambda: scenes.cloth_spheres(n_layers=2, n=17, n_side=2, level=1, seed=31),   # config-5 family
 }
 EE_SUM_BOUND = 2.0   # see tests/test_oracle_vs_reference.py
 

@@ -23,6 +23,7 @@ SCENES = {
     "drape": lambda: scenes.drape(n=24, level=2),
     "layered": lambda: scenes.layered_cloth(4, 13),
     "sheet_wall": lambda: scenes.sheet_wall(n=10),
+    "cloth_spheres": lambda: scenes.cloth_spheres(n_layers=2, n=17, n_side=2, level=1, seed=31),   # config-5 family
 }
 # stated bound for points touched by an edge-edge contact: the reference's edge-edge normal at a coplanarity root is
 # v2 - v1 of two (nearly) coincident points (dcollid3d.cpp:729-744), so its direction -- and with it the impulse --
