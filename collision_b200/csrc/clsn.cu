@@ -21,6 +21,7 @@
 #include <string.h>
 #include <string>
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "narrow.cuh"
@@ -2483,6 +2484,32 @@ extern "C" int clsn_resolve(clsn_ctx* c, clsn_step_stats* stats)
     return resolve_io(c, stats, HostOut());
 }
 
+// updateFinalVelocity, dcollid.cpp:598-624: vel = avgVel where has_collsn.  A 24-byte copy per point out of freshly
+// DMA-written (cache-cold) memory: on a 504 K-vertex mesh one host thread needs longer for it than PCIe needs for the
+// arrays themselves, so large meshes are split over a few threads (disjoint vertex ranges).
+static void merge_final_velocity(int V, const double* av, const uint8_t* has, double* vel)
+{
+    auto run = [=](int lo, int hi) {
+        for (int p = lo; p < hi; ++p)
+            if (has[p])
+                for (int j = 0; j < 3; ++j) vel[3 * (size_t)p + j] = av[3 * (size_t)p + j];
+    };
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nt = V >= (1 << 16) ? (int)std::min(4u, std::max(1u, hw / 2)) : 1;
+    std::vector<std::thread> th;
+    int done = 0;   // vertices handed to helper threads so far
+    try {
+        for (int t = 1; t < nt; ++t) {
+            const int lo = (int)((long long)V * (t - 1) / nt), hi = (int)((long long)V * t / nt);
+            th.emplace_back(run, lo, hi);
+            done = hi;
+        }
+    } catch (...) {   // no more threads to be had: the calling thread does the rest
+    }
+    run(done, V);
+    for (auto& x : th) x.join();
+}
+
 extern "C" int clsn_step_host(clsn_ctx* c, const double* x_old, const double* x_new, double* x_out, double* vel_inout,
                               uint8_t* has_out, clsn_step_stats* stats)
 {
@@ -2496,14 +2523,45 @@ extern "C" int clsn_step_host(clsn_ctx* c, const double* x_old, const double* x_
     out.avgvel = vel_inout ? c->h_pin : nullptr;   // avgVel only travels back when the caller wants velocities updated
     out.has = has_out ? has_out : (vel_inout ? reinterpret_cast<uint8_t*>(c->h_pin + n) : nullptr);
     if ((r = resolve_io(c, stats, out))) return r;   // upload, step and download: one synchronisation
-    if (vel_inout) {  // updateFinalVelocity, dcollid.cpp:598-624
-        const double* av = out.avgvel;
-        const uint8_t* has = out.has;
-        for (int p = 0; p < c->V; ++p)
-            if (has[p])
-                for (int j = 0; j < 3; ++j) vel_inout[3 * (size_t)p + j] = av[3 * (size_t)p + j];
+    if (vel_inout) merge_final_velocity(c->V, out.avgvel, out.has, vel_inout);
+    return CLSN_OK;
+}
+
+// The same call with the raw per-point results instead of the merged velocity: x_out = final Coords, avgvel_out = avgVel
+// of EVERY point, has_out = has_collsn (any of the three may be NULL).  For host mirrors that keep STATE::avgVel of all
+// points like the reference does (collision_b200/host/collid_b200.cpp): upload, step and download with one synchronisation.
+extern "C" int clsn_step_host_state(clsn_ctx* c, const double* x_old, const double* x_new, double* x_out, double* avgvel_out,
+                                    uint8_t* has_out, clsn_step_stats* stats)
+{
+    if (!c || !c->V || !x_old || !x_new) return CLSN_E_ARG;
+    int r;
+    if ((r = clsn_upload_state(c, x_old, x_new))) return r;
+    HostOut out;
+    out.x = x_out;
+    out.avgvel = avgvel_out;
+    out.has = has_out;
+    return resolve_io(c, stats, out);
+}
+
+// Page-locked host memory for callers that do not link the CUDA runtime themselves: host arrays handed to
+// clsn_step_host* / clsn_upload_state / clsn_download_state from such a buffer move by true asynchronous DMA (pageable
+// arrays are staged by the driver).  Portable: usable with the contexts of every device of the process.
+extern "C" int clsn_host_alloc(void** out, size_t bytes)
+{
+    if (!out) return CLSN_E_ARG;
+    *out = nullptr;
+    if (bytes == 0) return CLSN_OK;
+    const cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        *out = nullptr;
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? CLSN_E_NOMEM : CLSN_E_CUDA;
     }
     return CLSN_OK;
+}
+extern "C" void clsn_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
 }
 
 // ------------------------------------------------------------------ updateFinalForRG

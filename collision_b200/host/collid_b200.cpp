@@ -36,7 +36,8 @@ bool isStaticRigidBody(const POINT* p) { return p->state->is_fixed; }
 bool isMovableRigidBody(const POINT* p) { return p->state->is_movableRG; }
 bool isRigidBody(const POINT* p) { return isStaticRigidBody(p) || isMovableRigidBody(p); }
 
-CollisionSolver::CollisionSolver(int dim, int device) : has_collision(false), m_dim(dim), m_ctx(nullptr), m_topology_dirty(true)
+CollisionSolver::CollisionSolver(int dim, int device)
+    : has_collision(false), m_dim(dim), m_ctx(nullptr), m_device(device), m_pair_ctx(nullptr), m_topology_dirty(true)
 {
     for (int i = 0; i < 3; ++i) { Boundary[i][0] = -1e30; Boundary[i][1] = 1e30; }
     std::memset(&m_stats, 0, sizeof(m_stats));
@@ -98,6 +99,7 @@ void CollisionSolver::computeImpactZone()  // dcollid.cpp:227-265, on the state 
 CollisionSolver::~CollisionSolver()
 {
     clearHseList();
+    clsn_destroy(m_pair_ctx);
     clsn_destroy(m_ctx);
 }
 
@@ -193,8 +195,9 @@ void CollisionSolver::gatherTopology(const INTERFACE* intfc)
     m_tri_len0.swap(tri_len0); m_bond_len0.swap(bond_len0);
     rc = clsn_set_rest_lengths(m_ctx, m_tri_len0.data(), m_bond_len0.data());
     if (rc != CLSN_OK) fail(rc, "clsn_set_rest_lengths");
-    m_xold.resize(3 * (size_t)V); m_xnew.resize(3 * (size_t)V); m_xout.resize(3 * (size_t)V); m_vel.resize(3 * (size_t)V);
-    m_has.resize(V);
+    if (!m_xold.resize(3 * (size_t)V) || !m_xnew.resize(3 * (size_t)V) || !m_xout.resize(3 * (size_t)V) ||
+        !m_avg.resize(3 * (size_t)V) || !m_has.resize((size_t)V))
+        fail(CLSN_E_NOMEM, "clsn_host_alloc");
     m_topology_dirty = false;
     if (m_dist_nranks > 0) enableMultiGPU(m_dist_rank, m_dist_nranks, m_dist_id);
 }
@@ -224,7 +227,6 @@ void CollisionSolver::resolveCollision()  // dcollid.cpp:317-362
         for (int j = 0; j < 3; ++j) {
             m_xold[3 * v + j] = p->state->x_old[j];
             m_xnew[3 * v + j] = p->coords[j];
-            m_vel[3 * v + j] = p->state->vel[j];
         }
     }
     clsn_params prm;
@@ -232,12 +234,9 @@ void CollisionSolver::resolveCollision()  // dcollid.cpp:317-362
     for (int i = 0; i < 3; ++i) { prm.lo[i] = Boundary[i][0]; prm.hi[i] = Boundary[i][1]; }
     int rc = clsn_set_params(m_ctx, &prm);
     if (rc != CLSN_OK) fail(rc, "clsn_set_params");
-    rc = clsn_upload_state(m_ctx, m_xold.data(), m_xnew.data());
-    if (rc != CLSN_OK) fail(rc, "clsn_upload_state");
-    rc = clsn_resolve(m_ctx, &m_stats);
-    if (rc != CLSN_OK) fail(rc, "clsn_resolve");  // NaN/Inf: the reference calls clean_up(ERROR) here
-    rc = clsn_download_state(m_ctx, m_xout.data(), m_xnew.data() /* reused: avgVel */, m_has.data());
-    if (rc != CLSN_OK) fail(rc, "clsn_download_state");
+    // upload, the whole step and the download of Coords / avgVel / has_collsn: one call, one synchronisation, pinned arrays
+    rc = clsn_step_host_state(m_ctx, m_xold.data(), m_xnew.data(), m_xout.data(), m_avg.data(), m_has.data(), &m_stats);
+    if (rc != CLSN_OK) fail(rc, "clsn_step_host_state");  // NaN/Inf: the reference calls clean_up(ERROR) here
     has_collision = m_stats.has_collision != 0;
     for (size_t v = 0; v < V; ++v) {
         POINT* p = m_points[v];
@@ -245,7 +244,7 @@ void CollisionSolver::resolveCollision()  // dcollid.cpp:317-362
         sl->has_collsn = m_has[v] != 0;
         for (int j = 0; j < 3; ++j) {
             p->coords[j] = m_xout[3 * v + j];      // updateFinalPosition, dcollid.cpp:562-584
-            sl->avgVel[j] = m_xnew[3 * v + j];
+            sl->avgVel[j] = m_avg[3 * v + j];
             if (sl->has_collsn) {                  // updateFinalVelocity, dcollid.cpp:598-624
                 sl->vel[j] = sl->avgVel[j];
                 p->vel[j] = sl->avgVel[j];
@@ -276,8 +275,8 @@ void CollisionSolver::resolveCollision()  // dcollid.cpp:317-362
 
 // Single-pair entry points of the reference (collid.h:199-200).  They run the same kernels on a
 // two-element problem and add the pair's contributions to the points' accumulators.
-static bool single_pair(const CD_HSE* a, const CD_HSE* b, int mode, double eps, double thickness, double dt, double k, double m,
-                        double lambda, double cr)
+static bool single_pair(clsn_ctx*& ctx, int device, const CD_HSE* a, const CD_HSE* b, int mode, double eps, double thickness, double dt,
+                        double k, double m, double lambda, double cr)
 {
     const bool ta = a->num_pts() == 3, tb = b->num_pts() == 3;
     if (a->num_pts() == 1 || b->num_pts() == 1) throw std::runtime_error("This case has not been implemented");  // dcollid.cpp:787-791
@@ -309,8 +308,13 @@ static bool single_pair(const CD_HSE* a, const CD_HSE* b, int mode, double eps, 
         mass[v] = pts[v]->hs ? pts[v]->hs->total_mass : 0.0;
         for (int j = 0; j < 3; ++j) { xo[3 * v + j] = pts[v]->state->x_old[j]; av[3 * v + j] = pts[v]->state->avgVel[j]; }
     }
-    clsn_ctx* c = nullptr;
-    if (clsn_create(&c, 0) != CLSN_OK) throw std::runtime_error("collision_b200: no usable CUDA device");
+    // one small context per solver, created on first use: clsn_set_topology resets everything a pair evaluation reads
+    // (body accumulators, has_collsn, the tree), so consecutive calls are independent of each other
+    if (!ctx && clsn_create(&ctx, device) != CLSN_OK) {
+        ctx = nullptr;
+        throw std::runtime_error("collision_b200: no usable CUDA device");
+    }
+    clsn_ctx* c = ctx;
     clsn_params prm;
     prm.eps = eps; prm.thickness = thickness; prm.dt = dt; prm.k = k; prm.m = m; prm.lambda = lambda; prm.cr = cr;
     for (int i = 0; i < 3; ++i) { prm.lo[i] = -1e30; prm.hi[i] = 1e30; }
@@ -325,8 +329,12 @@ static bool single_pair(const CD_HSE* a, const CD_HSE* b, int mode, double eps, 
     if (!rc) rc = clsn_set_avgvel(c, av.data());
     if (!rc) rc = clsn_detect(c, mode, &st);
     if (!rc) rc = clsn_get_accumulators(c, imp.data(), fric.data(), cnt.data(), irg.data(), crg.data());
-    clsn_destroy(c);
-    if (rc) throw std::runtime_error("collision_b200: single-pair evaluation failed");
+    if (rc) {
+        const std::string why = clsn_last_error(c);
+        clsn_destroy(c);   // do not keep a context that failed half-way
+        ctx = nullptr;
+        throw std::runtime_error("collision_b200: single-pair evaluation failed: " + why);
+    }
     for (int v = 0; v < V; ++v) {
         STATE* sl = pts[v]->state;
         for (int j = 0; j < 3; ++j) {
@@ -342,11 +350,11 @@ static bool single_pair(const CD_HSE* a, const CD_HSE* b, int mode, double eps, 
 
 bool CollisionSolver::isProximity(const CD_HSE* a, const CD_HSE* b)
 {
-    return single_pair(a, b, CLSN_PROXIMITY, s_eps, s_thickness, s_dt, s_k, s_m, s_lambda, s_cr);
+    return single_pair(m_pair_ctx, m_device, a, b, CLSN_PROXIMITY, s_eps, s_thickness, s_dt, s_k, s_m, s_lambda, s_cr);
 }
 bool CollisionSolver::isCollision(const CD_HSE* a, const CD_HSE* b)
 {
-    return single_pair(a, b, CLSN_COLLISION, s_eps, s_thickness, s_dt, s_k, s_m, s_lambda, s_cr);
+    return single_pair(m_pair_ctx, m_device, a, b, CLSN_COLLISION, s_eps, s_thickness, s_dt, s_k, s_m, s_lambda, s_cr);
 }
 
 // ---- adapters (dcollid.cpp:852-939) -------------------------------------------------------------

@@ -140,6 +140,35 @@ public:
     int num_pts() const { return 1; }
 };
 
+// Page-locked staging array (clsn_host_alloc): the per-vertex arrays that cross PCIe every step.  Pinned memory makes
+// the library's cudaMemcpyAsync a true DMA and lets upload, step and download share one synchronisation.
+template <class T>
+class PinnedArray {
+    T* p_ = nullptr;
+    size_t n_ = 0;
+
+public:
+    PinnedArray() = default;
+    PinnedArray(const PinnedArray&) = delete;
+    PinnedArray& operator=(const PinnedArray&) = delete;
+    ~PinnedArray() { clsn_host_free(p_); }
+    bool resize(size_t n)   // contents are not kept
+    {
+        if (n == n_) return true;
+        clsn_host_free(p_);
+        p_ = nullptr;
+        n_ = 0;
+        void* q = nullptr;
+        if (n && clsn_host_alloc(&q, n * sizeof(T)) != CLSN_OK) return false;
+        p_ = static_cast<T*>(q);
+        n_ = n;
+        return true;
+    }
+    T* data() { return p_; }
+    size_t size() const { return n_; }
+    T& operator[](size_t i) { return p_[i]; }
+};
+
 // ---- solver (collid.h:128-244) ----------------------------------------------------------------
 class CollisionSolver {
 private:
@@ -161,8 +190,10 @@ protected:
     std::vector<HYPER_SURF*> m_body_hs;
     int m_dist_rank = -1, m_dist_nranks = 0;   // enableMultiGPU asked for before the topology was known
     unsigned char m_dist_id[128];   // body index -> the caller's HYPER_SURF (center_of_mass / center_of_mass_velo)
-    std::vector<double> m_xold, m_xnew, m_xout, m_vel;
-    std::vector<uint8_t> m_has;
+    PinnedArray<double> m_xold, m_xnew, m_xout, m_avg;   // x_old, candidate Coords in; final Coords, avgVel out
+    PinnedArray<uint8_t> m_has;
+    int m_device;
+    clsn_ctx* m_pair_ctx;   // small context behind isProximity / isCollision, created on first use and kept
     clsn_step_stats m_stats;
     clsn_zone_stats m_zone_stats;
     std::vector<double> m_tri_len0, m_bond_len0;

@@ -1,7 +1,8 @@
 // Drives the C++ host mirror the way the reference's test.cpp drives CollisionSolver3d (test.cpp:96-107):
 // reads a flat scene file written by tests/test_gpu_host_cpp.py, builds the POINT/TRI/BOND mesh, runs
 // `steps` x { spring solver stand-in; assembleFromInterface; setFrictionConstant; resolveCollision },
-// writes final coords + vel.  Usage: host_check scene.bin out.bin steps [ngpus [nozones]]
+// writes final coords + vel.  Usage: host_check scene.bin out.bin steps [ngpus [nozones|pairs]]
+// pairs (one GPU): afterwards also exercise isProximity / isCollision on a few triangle pairs (check_single_pairs).
 // ngpus > 1: one host thread per GPU, each with its own copy of the mesh and its own CollisionSolver3d(device), joined by
 // CollisionSolver::enableMultiGPU -- the multi-GPU step of the library driven through the reference-shaped C++ API; rank r
 // writes out.bin.r (all of them must equal the single-GPU out.bin bit for bit).  nozones: impact-zone fail-safe off (it is
@@ -33,8 +34,47 @@ static double rest_length(const double* p, const double* q)
     return std::sqrt(s);
 }
 
+// The single-pair entry points (collid.h:199-200) on a few triangle pairs of the stepped mesh, each evaluated twice: the
+// first call of a solver creates its pair context, later calls reuse it -- verdict and accumulators must not depend on
+// what the context did before.  Returns the number of mismatches; *fired = evaluations that returned true.
+static int check_single_pairs(CollisionSolver3d* solver, std::vector<TRI>& tris, int* fired)
+{
+    const int T = (int)tris.size(), half = T / 2;
+    int bad = 0;
+    *fired = 0;
+    for (int t = 0; t < half && t < 24; ++t) {
+        CD_TRI a(&tris[t]), b(&tris[t + half]);
+        for (int mode = 0; mode < 2; ++mode) {
+            STATE got[2][6];
+            bool verdict[2];
+            for (int rep = 0; rep < 2; ++rep) {
+                for (int i = 0; i < 3; ++i)
+                    for (TRI* tr : {&tris[t], &tris[t + half]}) {
+                        STATE* sl = tr->pts[i]->state;
+                        for (int j = 0; j < 3; ++j) sl->collsnImpulse[j] = sl->friction[j] = sl->collsnImpulse_RG[j] = 0.0;
+                        sl->collsn_num = sl->collsn_num_RG = 0;
+                    }
+                verdict[rep] = mode ? solver->isCollision(&a, &b) : solver->isProximity(&a, &b);
+                for (int i = 0; i < 3; ++i) {
+                    got[rep][i] = *tris[t].pts[i]->state;
+                    got[rep][3 + i] = *tris[t + half].pts[i]->state;
+                }
+            }
+            if (verdict[0]) ++*fired;
+            if (verdict[0] != verdict[1]) ++bad;
+            for (int i = 0; i < 6; ++i)
+                if (std::memcmp(got[0][i].collsnImpulse, got[1][i].collsnImpulse, sizeof(double) * 3) ||
+                    std::memcmp(got[0][i].friction, got[1][i].friction, sizeof(double) * 3) ||
+                    std::memcmp(got[0][i].collsnImpulse_RG, got[1][i].collsnImpulse_RG, sizeof(double) * 3) ||
+                    got[0][i].collsn_num != got[1][i].collsn_num || got[0][i].collsn_num_RG != got[1][i].collsn_num_RG)
+                    ++bad;
+        }
+    }
+    return bad;
+}
+
 static int run(const char* scene_path, const std::string& out_path, int steps, int device, int rank, int nranks,
-               const unsigned char* id, bool zones)
+               const unsigned char* id, bool zones, bool pairs = false)
 {
     FILE* f = fopen(scene_path, "rb");
     if (!f) return 2;
@@ -113,8 +153,15 @@ static int run(const char* scene_path, const std::string& out_path, int steps, i
     fclose(o);
     printf("host_check[%d/%d]: %d steps, has_collision=%d, ccd passes last step=%d\n", rank, nranks, steps, (int)solver->hasCollision(),
            solver->lastStats().n_ccd_passes);
+    int rc = 0;
+    if (pairs) {
+        int fired = 0;
+        const int bad = check_single_pairs(solver, tris, &fired);
+        printf("host_check: single-pair entry points: %d evaluations fired, %d mismatches between first and repeated call\n", fired, bad);
+        if (bad) rc = 4;
+    }
     delete solver;
-    return 0;
+    return rc;
 }
 
 int main(int argc, char** argv)
@@ -123,7 +170,8 @@ int main(int argc, char** argv)
     const int steps = atoi(argv[3]);
     const int ngpus = argc > 4 ? atoi(argv[4]) : 1;
     const bool zones = !(argc > 5 && std::strcmp(argv[5], "nozones") == 0) && ngpus <= 1;
-    if (ngpus <= 1) return run(argv[1], argv[2], steps, 0, 0, 1, nullptr, zones);
+    const bool pairs = argc > 5 && std::strcmp(argv[5], "pairs") == 0;
+    if (ngpus <= 1) return run(argv[1], argv[2], steps, 0, 0, 1, nullptr, zones, pairs);
     unsigned char id[128];
     CollisionSolver::multiGPUUniqueId(id);
     std::vector<std::thread> th;

@@ -101,6 +101,10 @@ def load_library():
     L.clsn_resolve.argtypes = [V, P(clsn_step_stats)]
     L.clsn_download_state.argtypes = [V, P(D), P(D), P(C.c_uint8)]
     L.clsn_step_host.argtypes = [V, P(D), P(D), P(D), P(D), P(C.c_uint8), P(clsn_step_stats)]
+    L.clsn_step_host_state.argtypes = [V, P(D), P(D), P(D), P(D), P(C.c_uint8), P(clsn_step_stats)]
+    L.clsn_host_alloc.argtypes = [P(V), C.c_size_t]
+    L.clsn_host_free.restype = None
+    L.clsn_host_free.argtypes = [V]
     L.clsn_upload_state_device.argtypes = [V, V, V]
     L.clsn_download_state_device.argtypes = [V, V, V]
     L.clsn_avg_velocity.argtypes = [V]

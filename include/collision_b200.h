@@ -20,6 +20,7 @@
 #ifndef COLLISION_B200_H
 #define COLLISION_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -149,6 +150,16 @@ int clsn_download_state(clsn_ctx*, double* x, double* avgvel, uint8_t* has_colls
 /* upload + resolve + download + "vel = avgVel where has_collsn" (updateFinalVelocity) in one call */
 int clsn_step_host(clsn_ctx*, const double* x_old, const double* x_new, double* x_out, double* vel_inout,
                    uint8_t* has_collsn_out, clsn_step_stats* stats);
+/* the same single call (one synchronisation) with the raw per-point results instead of the merged velocity: avgvel_out[3V]
+ * = STATE::avgVel of EVERY point, as the reference leaves it (dcollid.cpp:677-751); any output pointer may be NULL.  For
+ * host mirrors that keep avgVel per point (collision_b200/host/collid_b200.cpp::resolveCollision). */
+int clsn_step_host_state(clsn_ctx*, const double* x_old, const double* x_new, double* x_out, double* avgvel_out,
+                         uint8_t* has_collsn_out, clsn_step_stats* stats);
+/* page-locked host memory for callers that do not link the CUDA runtime themselves: host arrays passed to the calls above
+ * from such a buffer move by asynchronous DMA (pageable arrays are staged by the driver).  Usable with every context of
+ * the process; free with clsn_host_free. */
+int clsn_host_alloc(void** out, size_t bytes);
+void clsn_host_free(void*);
 
 /* updateFinalForRG (dcollid.cpp:626-675, the tail of updateFinalVelocity): for every movable rigid body with a point
  * that collided in this step, write the body's centre-of-mass velocity (avgVel of the first such point in hseList order)
@@ -228,9 +239,10 @@ int clsn_set_exact_stats(clsn_ctx*, int on);
  * roots -- the outcome is then the static test at t = dt -- and only the rest gets the correctly rounded cubic
  * solve (k_exact); k_emit writes the records of the hit list.  0: staged -- correctly rounded solve of every
  * feature (k_roots), then the static tests and the records (k_contact); kept for A/B measurements.
- * 2 (experimental, not yet measured on a B200): like 1, but the per-point record counts are taken from the hit list
- * first, so that k_emit writes every impulse record straight into its point's segment and the reduction needs no
- * grouping pass (single-GPU contexts only; ranks of a multi-GPU run keep exchanging the plain record list).
+ * 2 (experimental; measured on a B200: no gain over 1 -- the reduction gets faster by what the emission gets slower):
+ * like 1, but the per-point record counts are taken from the hit list first, so that k_emit writes every impulse record
+ * straight into its point's segment and the reduction needs no grouping pass (single-GPU contexts only; ranks of a
+ * multi-GPU run keep exchanging the plain record list).
  * Results are bit-identical.  The environment variable CLSN_PIPELINE=0|1|2 sets the default of new contexts. */
 int clsn_set_pipeline(clsn_ctx*, int pipeline);
 int64_t clsn_num_candidates(clsn_ctx*);

@@ -47,3 +47,18 @@ def test_cpp_host_matches_python_host(name, tmp_path):
         x = xg
     assert same_bits(res[0], x) and same_bits(res[1], vel)
     gpu.close()
+
+
+def test_cpp_single_pair_entry_points(tmp_path):
+    """isProximity / isCollision of the C++ mirror (collid.h:199-200) on triangle pairs of a stepped two-sheet mesh: the
+    first call of a solver creates its small pair context, later calls reuse it -- verdicts and accumulators of the first
+    and of the repeated evaluation agree bit for bit (host_check.cpp::check_single_pairs)."""
+    exe = os.path.join(HOST, "host_check")
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    sc = scenes.two_sheets(n=16)
+    inp, out = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")
+    write_scene(sc, inp)
+    r = subprocess.run([exe, inp, out, "2", "1", "pairs"], capture_output=True, text=True)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert " 0 mismatches" in r.stdout
