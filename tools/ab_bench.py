@@ -28,7 +28,7 @@ def main():
         if pipe:
             env["CLSN_PIPELINE"] = pipe
         try:
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", steps, "--warmup", "3", "--no-cpu"],
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", steps, "--warmup", "3", "--no-cpu", "--no-api-default"],
                                env=env, capture_output=True, text=True, timeout=240)
             line = json.loads(r.stdout.strip().splitlines()[-1])
         except Exception as e:  # noqa: BLE001
