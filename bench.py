@@ -447,7 +447,7 @@ def run_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-    if phase_ms and world == 1:
+    if world == 1 and sum(phase_ms.values()) > 0.0:   # (CLSN_PHASE_TIMING=0: no marks were recorded, no per-phase figures)
         bytes_, flops_, units = algorithmic_bytes(scene, st)
         per_step = {k: v / args.steps for k, v in phase_ms.items()}
         kernels = {}
