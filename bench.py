@@ -298,6 +298,9 @@ def run_b200(args):
     solver.assembleFromInterface(scene, scene.dt)
     if args.pipeline is not None:
         solver.set_pipeline(args.pipeline)
+    # per-phase CUDA-event marks for the roofline figures: ON during the device-timed steps (they are part of what `value`
+    # times), OFF -- the library's default -- during the end-to-end steps
+    solver.set_phase_timing(not args.no_phase_marks)
     x_old = np.ascontiguousarray(scene.x)
     x_new = np.ascontiguousarray(scene.x_new())
     d_xo = torch.from_numpy(x_old).to(dev)
@@ -360,6 +363,7 @@ def run_b200(args):
 
     # ---- e2e through the drop-in call with pinned host buffers (N = 1: the C ABI call; N > 1: host
     # upload + distributed step + host download)
+    solver.set_phase_timing(False)
     h_xo = torch.from_numpy(x_old).pin_memory().numpy()
     h_xn = torch.from_numpy(x_new).pin_memory().numpy()
     h_out = torch.empty(x_new.shape, dtype=torch.float64).pin_memory().numpy()
@@ -447,7 +451,7 @@ def run_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-    if world == 1 and sum(phase_ms.values()) > 0.0:   # (CLSN_PHASE_TIMING=0: no marks were recorded, no per-phase figures)
+    if world == 1 and sum(phase_ms.values()) > 0.0:   # (--no-phase-marks: no marks were recorded, no per-phase figures)
         bytes_, flops_, units = algorithmic_bytes(scene, st)
         per_step = {k: v / args.steps for k, v in phase_ms.items()}
         kernels = {}
@@ -541,6 +545,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-spin", action="store_true", help="profiling runs: skip the untimed spin-up steps")
     ap.add_argument("--pipeline", type=int, default=None, help="CCD narrow-phase pipeline (default: the library's)")
+    ap.add_argument("--no-phase-marks", action="store_true",
+                    help="device-timed steps without the per-phase event marks (no kernels{} / roofline in the line)")
     ap.add_argument("--sample-reference", action="store_true",
                     help="--impl reference: time a bounded sample (16 K triangles) instead of the full workload")
     ap.add_argument("--no-cache", action="store_true", help="--impl reference: measure even if this box has a cached measurement")

@@ -894,7 +894,7 @@ struct clsn_ctx {
     DevBuf<double> imp_rg, imp_rg_keep;   // keep: start-of-step copy (a step that has to be repeated restores it)
     DevBuf<Vec4> xf;                      // final positions (x_new stays intact for a repeated step)
     bool final_valid = false;
-    bool phase_timing = true;             // record CUDA-event marks between kernel groups inside clsn_resolve
+    bool phase_timing = false;            // record CUDA-event marks between kernel groups inside clsn_resolve (clsn_set_phase_timing)
     DevBuf<int> cnt_rg;
     DevBuf<double> stage;  // 3V doubles, host<->device staging of packed arrays
     // bvh
@@ -1069,6 +1069,7 @@ extern "C" int clsn_create(clsn_ctx** out, int device)
     if (const char* e = getenv("CLSN_PAIR_CHUNK")) c->pair_chunk = std::max<long long>(1024, atoll(e));
     if (const char* e = getenv("CLSN_KEEP_TREE")) c->keep_tree = atoi(e) != 0;
     if (const char* e = getenv("CLSN_PHASE_TIMING")) c->phase_timing = atoi(e) != 0;
+    if (getenv("CLSN_TRACE")) c->phase_timing = true;   // the per-mark timeline needs the marks
     if (const char* e = getenv("CLSN_PIPELINE")) {
         const int v = atoi(e);
         if (v >= 0 && v <= 2) c->pipeline = v;
@@ -1285,6 +1286,13 @@ extern "C" int clsn_set_exact_stats(clsn_ctx* c, int on)
 {
     if (!c) return CLSN_E_ARG;
     c->exact_stats = on != 0;
+    return CLSN_OK;
+}
+
+extern "C" int clsn_set_phase_timing(clsn_ctx* c, int on)
+{
+    if (!c) return CLSN_E_ARG;
+    c->phase_timing = on != 0;
     return CLSN_OK;
 }
 

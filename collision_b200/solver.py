@@ -128,6 +128,7 @@ def load_library():
     L.clsn_set_debug.argtypes = [V, I, I]
     L.clsn_set_exact_stats.argtypes = [V, I]
     L.clsn_set_pipeline.argtypes = [V, I]
+    L.clsn_set_phase_timing.argtypes = [V, I]
     L.clsn_num_candidates.restype = C.c_int64
     L.clsn_num_candidates.argtypes = [V]
     L.clsn_get_candidates.argtypes = [V, P(C.c_int32)]
@@ -455,6 +456,10 @@ class CollisionSolver3d:
     def set_exact_stats(self, on=True):
         """full traversal in every pass so that stats['candidates'] equals the reference's callback count"""
         self.ctx.check(self.ctx.L.clsn_set_exact_stats(self.ctx.h, int(on)))
+
+    def set_phase_timing(self, on: bool):
+        """per-phase device times in last_stats["ms_phase"] (CUDA-event marks between the kernel groups of a step); off by default"""
+        self.ctx.check(self.ctx.L.clsn_set_phase_timing(self.ctx.h, int(bool(on))))
 
     def set_pipeline(self, pipeline: int):
         """1: plain-FP64 fast path, correctly rounded solve of the undecided features only (default);

@@ -185,6 +185,10 @@ int clsn_timer_start(clsn_ctx*);
 int clsn_timer_stop(clsn_ctx*, float* ms);
 int64_t clsn_launch_count(clsn_ctx*, int reset);
 int clsn_synchronize(clsn_ctx*);
+/* clsn_step_stats.ms_phase: CUDA-event marks between the kernel groups of clsn_resolve / clsn_step_host (about a hundred
+ * event records per step).  Off by default -- ms_phase stays zero, ms_total is always measured; the environment variable
+ * CLSN_PHASE_TIMING=1 sets the default of new contexts. */
+int clsn_set_phase_timing(clsn_ctx*, int on);
 
 /* ---- multi-GPU inside the library (csrc/dist.cuh): one context per GPU of a node, one process or thread each (the
  * natural fit for the reference's MPI-based host application: one MPI rank per GPU).  Any rank calls clsn_dist_unique_id

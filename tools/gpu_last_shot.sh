@@ -19,7 +19,7 @@ log "start"
 wait
 timeout 50 python tools/ab_bench.py --steps 10 cur opt > gpurun_out/shot_C.log 2>&1
 log "C exit $? : $(cut -c1-150 gpurun_out/shot_C.log | tr '\n' '|')"
-CLSN_PHASE_TIMING=0 timeout 25 python bench.py --steps 10 --warmup 3 --no-cpu --no-api-default > gpurun_out/shot_C_nomarks.json 2> gpurun_out/shot_C_nomarks.err
+timeout 25 python bench.py --steps 10 --warmup 3 --no-cpu --no-api-default --no-phase-marks > gpurun_out/shot_C_nomarks.json 2> gpurun_out/shot_C_nomarks.err
 log "C2 exit $? : $(cut -c1-200 gpurun_out/shot_C_nomarks.json)"
 timeout 25 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/shot_D.log 2>&1
 log "D exit $? : $(tail -1 gpurun_out/shot_D.log)"
