@@ -95,11 +95,6 @@ __host__ __device__ __forceinline__ void feature_slots(int type, int f, int sl[4
 #define CULL_SAT 1   // FP32 separating-axis test along the feature normal in front of the classifier (cubic.cuh: sat_normal_far)
 #endif
 #define CULL_KEEP_CAP 128  // per-warp buffer of kept features between slot reservations
-#ifndef CULL_EXPAND
-#define CULL_EXPAND 0   // 1: the warp's box survivors are expanded into a shared-memory list of (pair row, feature) codes
-                        // once per batch of 32 pairs; 0: every pooled round searches its owner row (binary search over the
-                        // prefix sums + n-th set bit)
-#endif
 #define CULL_ROW 19  // doubles per staged pair row (18 used): odd stride -> conflict-free column access
 
 // Work-list records.  They carry the four point ids of the feature test so that the consumer's gathers
@@ -178,14 +173,9 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
     __shared__ double s_x[CULL_THREADS][CULL_ROW];
     __shared__ double s_v[MOVING ? CULL_THREADS : 1][CULL_ROW];
     __shared__ unsigned s_mask[CULL_THREADS];
-#if !CULL_EXPAND
-    __shared__ int s_pref[CULL_THREADS];
-#endif
     __shared__ int s_id[CULL_THREADS][7];
     __shared__ unsigned short s_keep[CULL_THREADS / 32][CULL_KEEP_CAP];
-#if CULL_EXPAND
     __shared__ unsigned short s_list[CULL_THREADS / 32][32 * 15];   // (pair row << 4) | feature of every box survivor of the batch
-#endif
     const int tid = threadIdx.x, lane = tid & 31, wb = tid & ~31;
     long long n_pairs = (long long)counters[CTR_PAIRS];
     if (n_pairs > cap_pairs) n_pairs = cap_pairs;
@@ -280,15 +270,12 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         s_mask[tid] = mask;
-#if !CULL_EXPAND
-        s_pref[tid] = incl - cnt;
-#else
-        {   // this lane's survivors, in feature order, at its place in the warp's list: entry k of the list is exactly the
-            // (owner row, feature) the search below would find for k
+        {   // This lane's survivors, in feature order, at its place in the warp's list.  (Round 2 searched the owner row in
+            // every pooled round instead -- binary search over the prefix sums + n-th set bit: 10 % of the kernel's
+            // instructions behind a chain of six dependent shared-memory loads; measured: cull 4.74 -> 4.41 ms per step.)
             int pos = incl - cnt;
             for (unsigned m = mask & 0x7fffu; m; m &= m - 1u) s_list[tid >> 5][pos++] = (unsigned short)((lane << 4) | (__ffs(m) - 1));
         }
-#endif
         __syncwarp();
         // Features that stay are buffered per warp as 10-bit codes (pair row, feature, list end) and written out
         // in batches: one slot reservation per list end and batch instead of one per round of 32 -- a
@@ -302,19 +289,9 @@ k_cull(const int2* __restrict__ pairs, long long cap_pairs, const int4* __restri
             bool keep = false;
             unsigned code = 0;
             if (k < total) {
-#if CULL_EXPAND
                 const unsigned lc = s_list[tid >> 5][k];
-                const int o = (int)(lc >> 4), f = (int)(lc & 15u);
+                const int o = (int)(lc >> 4), f = (int)(lc & 15u);   // owner row inside the warp's batch, feature index
                 const unsigned m = s_mask[wb + o];
-#else
-                // owner = last lane whose exclusive prefix is <= k
-                int o = 0;
-#pragma unroll
-                for (int step = 16; step > 0; step >>= 1)
-                    if (s_pref[wb + o + step] <= k) o += step;
-                const unsigned m = s_mask[wb + o];
-                const int f = __fns(m & 0x7fffu, 0, k - s_pref[wb + o] + 1);
-#endif
                 const int type = (int)(m >> 16);
                 const bool edge = type == 0 ? f >= 6 : (type == 1 ? f >= 2 : true);
                 bool back = edge;

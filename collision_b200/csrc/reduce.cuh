@@ -91,9 +91,6 @@ __global__ void k_owner_scatter(const PointRec* __restrict__ rec, long long n, i
 // SEG: the records sit in per-point segments already (pipeline 2).  SORTED: perm[] is already in key order per point
 // (cub::DeviceSegmentedSort, used when movable rigid bodies are present: a sphere vertex that sweeps through a cloth stack
 // collects tens of thousands of records, and the all-pairs ranking is quadratic in that number).
-#ifndef REDUCE_PREFETCH
-#define REDUCE_PREFETCH 0
-#endif
 template <bool SEG, bool SORTED = false>
 __global__ void __launch_bounds__(256)
 k_reduce_points(const PointRec* __restrict__ rec, const int* __restrict__ offs, const int* __restrict__ cnt, int V,
@@ -105,29 +102,10 @@ k_reduce_points(const PointRec* __restrict__ rec, const int* __restrict__ offs, 
     if ((long long)*n_rec_ptr > cap) return;   // overflowed list (see k_scatter)
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
-#if REDUCE_PREFETCH
-    // Same point -> warp assignment as the plain loop (p = w, w + W, w + 2W ...), but the record counts of the warp's next
-    // 32 points are fetched by its 32 lanes at once and only the points that have records are visited: a pass that hit
-    // little (the later CCD passes, or a proximity pass without contacts) costs two rounds of independent loads per warp
-    // instead of one dependent load per point.
-    const int w_first = blockIdx.x * warps_per_block + (threadIdx.x >> 5), W = gridDim.x * warps_per_block;
-    for (long long p0 = w_first; p0 < V; p0 += 32ll * W) {
-        const long long pl = p0 + (long long)lane * W;
-        const int n_mine = pl < V ? cnt[pl] : 0;
-        unsigned todo = __ballot_sync(0xffffffffu, n_mine != 0);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            const int p = (int)(p0 + (long long)src * W);
-            const int n = __shfl_sync(0xffffffffu, n_mine, src);
-            const int base = offs[p];
-#else
     for (int p = blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < V; p += gridDim.x * warps_per_block) {
-        {
-            const int n = cnt[p];
-            if (n == 0) continue;
-            const int base = offs[p];
-#endif
+        const int n = cnt[p];
+        if (n == 0) continue;
+        const int base = offs[p];
         const int* order = perm_sorted;
         if (SORTED) {
             order = perm;
@@ -167,7 +145,6 @@ k_reduce_points(const PointRec* __restrict__ rec, const int* __restrict__ offs, 
             else acc_fric[3 * (size_t)p + lane - 3] = sum;
         }
         __syncwarp();
-        }
     }
 }
 

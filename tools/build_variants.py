@@ -30,9 +30,6 @@ VARIANTS = {
     "fa5": ["-DFAST_MIN_BLOCKS=5"],
     "ex5": ["-DEXACT_MIN_BLOCKS=5"],
     "r6": ["-DROOTS_MIN_BLOCKS=6"],
-    "ex": ["-DCULL_EXPAND=1"],      # k_cull: box survivors expanded into a shared-memory list instead of a search per pooled round
-    "rp": ["-DREDUCE_PREFETCH=1"],  # k_reduce_points: record counts of 32 points fetched at once, only points with records visited
-    "opt": ["-DCULL_EXPAND=1", "-DREDUCE_PREFETCH=1"],
     "pf": ["-DCULL_PREFILTER=1"],
     "nosat": ["-DCULL_SAT=0"],      # without the normal-axis separating test in k_cull   # FP32 Bernstein pre-filter in k_cull (cubic.cuh: coplanar_prefilter32)
 }
