@@ -2,13 +2,16 @@
 //
 // One context = one B200.  All state lives in HBM as padded per-vertex records (Vec4, one
 // 32-byte sector per gather); the host side only gathers/scatters caller arrays.
-// Pipeline of one detection pass (clsn_detect):
-//   [build, first pass of a step]  k_scene_bounds -> k_morton -> cub radix sort -> k_hierarchy
-//   k_refit<static|moving>   exact FP64 leaf boxes + FP32 node boxes, bottom-up
-//   k_traverse               stack-in-registers self query -> element pairs (a < b)
-//   k_narrow<static|moving>  one pair per thread, 15 feature tests, emits impulse records
-// and of clsn_apply: cub exclusive scan over per-point counts -> k_scatter -> k_reduce_points
-// (canonical-order sums, applied to avgVel) -> body records -> [rigid-body kernels].
+// One detection pass (enqueue_detect), nothing read back by the host:
+//   [tree order: k_scene_bounds -> k_morton -> cub radix sort -> k_gather_elems; kept across steps]
+//   k_refit8<static|moving>  exact FP64 leaf boxes + quantised 64-byte nodes of the implicit 8-ary tree (lbvh.cuh)
+//   k_traverse8              self query, exact FP64 leaf test -> element pairs (a < b)
+//   k_cull<static|moving>    feature-level swept-box cull, CCD: trig-free classifier of the coplanarity cubic -> work list
+//   proximity: k_contact<false>;  CCD: k_fast (plain-FP64 fast path) -> k_exact (correctly rounded solve) -> k_emit
+//   (contact + impulse records; narrow.cuh, cubic.cuh, fastpath.cuh, crmath.cuh)
+// and of the apply step (apply_impl): cub exclusive scan over per-point counts -> k_scatter -> k_reduce_points
+// (canonical-order sums, applied to avgVel) -> body records -> [rigid-body kernels] (reduce.cuh, rigid.cuh).
+// resolve_impl enqueues a whole step (proximity + up to five CCD passes, device-side gated) and synchronises once.
 // Compiled with --fmad=false: every FP64 expression rounds exactly like the reference's.
 #include "collision_b200.h"
 
