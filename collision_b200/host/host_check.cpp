@@ -9,6 +9,7 @@
 // not available in the multi-GPU step).
 #include <cmath>
 #include <cstring>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <cstdio>
@@ -171,7 +172,14 @@ int main(int argc, char** argv)
     const int ngpus = argc > 4 ? atoi(argv[4]) : 1;
     const bool zones = !(argc > 5 && std::strcmp(argv[5], "nozones") == 0) && ngpus <= 1;
     const bool pairs = argc > 5 && std::strcmp(argv[5], "pairs") == 0;
-    if (ngpus <= 1) return run(argv[1], argv[2], steps, 0, 0, 1, nullptr, zones, pairs);
+    if (ngpus <= 1) {
+        try {
+            return run(argv[1], argv[2], steps, 0, 0, 1, nullptr, zones, pairs);
+        } catch (const std::exception& e) {   // e.g. no CUDA device: the mirror throws, there is no CPU path behind it
+            fprintf(stderr, "host_check: %s\n", e.what());
+            return 3;
+        }
+    }
     unsigned char id[128];
     CollisionSolver::multiGPUUniqueId(id);
     std::vector<std::thread> th;

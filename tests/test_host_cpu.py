@@ -310,3 +310,22 @@ def test_bench_reference_arm_line(tmp_path):
                          "--warmup", "0", "--gpus", "2"], capture_output=True, text=True, timeout=600, env=env)
     d2 = json.loads([ln for ln in r2.stdout.splitlines() if ln.strip()][0])
     assert d2["value"] == d["value"] and "reused" in d2["cpu_baseline"]["sample"] and d2["n_gpus"] == 2
+
+
+def test_cpp_mirror_links_against_the_c_abi_and_has_no_cpu_path(tmp_path):
+    """collision_b200/host (the C++ mirror of collid.h + its test.cpp-like driver) compiles against include/collision_b200.h and
+    links against the library; without a CUDA device it stops with an error instead of computing anything on the host."""
+    import subprocess
+    import torch
+    from collision_b200 import scenes
+    from test_gpu_host_cpp import HOST, write_scene
+    _lib_path()
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present: the GPU suite runs the driver for real")
+    sc = scenes.two_sheets(n=6)
+    inp, out = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")
+    write_scene(sc, inp)
+    r = subprocess.run([os.path.join(HOST, "host_check"), inp, out, "1"], capture_output=True, text=True)
+    assert r.returncode == 3 and "no usable CUDA device" in r.stderr
+    assert not os.path.exists(out)
